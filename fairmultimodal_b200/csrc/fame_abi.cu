@@ -1,0 +1,266 @@
+// Host side of libfame_b200.so: argument validation, TMA descriptor encoding, kernel launches.
+// See include/fame_b200.h for the contract of each entry point.
+#include "../../include/fame_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include "attn_sm100.cuh"
+#include "gemm_sm100.cuh"
+#include "rowwise.cuh"
+
+namespace {
+
+thread_local int g_last_cuda_error = 0;
+
+int cuda_fail(cudaError_t e) {
+    g_last_cuda_error = static_cast<int>(e);
+    return FAME_ERR_CUDA;
+}
+
+struct DeviceInfo {
+    int checked = 0;
+    int ok = 0;
+    int sm_count = 0;
+};
+DeviceInfo g_dev[64];
+
+int device_info(DeviceInfo** out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    if (dev < 0 || dev >= 64) return FAME_ERR_ARCH;
+    DeviceInfo& d = g_dev[dev];
+    if (!d.checked) {
+        int major = 0, sms = 0;
+        e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        if (e != cudaSuccess) return cuda_fail(e);
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return cuda_fail(e);
+        d.ok = (major == 10);
+        d.sm_count = sms;
+        d.checked = 1;
+    }
+    *out = &d;
+    return d.ok ? FAME_OK : FAME_ERR_ARCH;
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+int get_encode() {
+    if (g_encode != nullptr) return FAME_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return cuda_fail(e);
+    if (fn == nullptr || qres != cudaDriverEntryPointSuccess) return cuda_fail(cudaErrorNotSupported);
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    return FAME_OK;
+}
+
+// bf16 row-major [rows, cols] with leading dimension ld (elements); box = box_rows x 64 columns, 128B swizzle.
+int encode_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    int rc = get_encode();
+    if (rc != FAME_OK) return rc;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        g_last_cuda_error = 100000 + static_cast<int>(r);
+        return FAME_ERR_CUDA;
+    }
+    return FAME_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int launch_status() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? FAME_OK : cuda_fail(e);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fame_strerror(int code) {
+    switch (code) {
+        case FAME_OK: return "ok";
+        case FAME_ERR_ARCH: return "device is not sm_100 (B200); this library has no fallback path";
+        case FAME_ERR_SHAPE: return "unsupported or inconsistent shape";
+        case FAME_ERR_ALIGN: return "pointer or leading dimension is not 16-byte aligned";
+        case FAME_ERR_WORKSPACE: return "workspace too small";
+        case FAME_ERR_NULLPTR: return "required pointer is NULL";
+        case FAME_ERR_CUDA: return "CUDA call failed (see fame_last_cuda_error)";
+        default: return "unknown fame error";
+    }
+}
+
+int fame_last_cuda_error(void) { return g_last_cuda_error; }
+int fame_abi_version(void) { return 1; }
+
+int fame_device_check(void) {
+    DeviceInfo* d = nullptr;
+    return device_info(&d);
+}
+
+int fame_sm_count(void) {
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    return rc == FAME_OK ? d->sm_count : rc;
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+int fame_gemm_bias_act(const fame_gemm_args* a, void* /*workspace*/, size_t /*workspace_bytes*/,
+                       fame_stream_t stream) {
+    if (a == nullptr || a->x == nullptr || a->w == nullptr || a->y == nullptr) return FAME_ERR_NULLPTR;
+    if (a->M < 0 || a->N <= 0 || a->K <= 0) return FAME_ERR_SHAPE;
+    if ((a->K & 7) || (a->N & 7)) return FAME_ERR_SHAPE;
+    if (a->act < FAME_ACT_NONE || a->act > FAME_ACT_RELU) return FAME_ERR_SHAPE;
+    if (a->y_dtype != FAME_DT_BF16 && a->y_dtype != FAME_DT_F32) return FAME_ERR_SHAPE;
+    if (a->ldx < a->K || a->ldw < a->K || a->ldy < a->N) return FAME_ERR_SHAPE;
+    if ((a->ldx & 7) || (a->ldw & 7) || (a->ldy & 7)) return FAME_ERR_ALIGN;
+    if (!aligned16(a->x) || !aligned16(a->w) || !aligned16(a->y)) return FAME_ERR_ALIGN;
+    if (a->bias != nullptr && !aligned16(a->bias)) return FAME_ERR_ALIGN;
+    if (a->residual != nullptr && (!aligned16(a->residual) || (a->ldr & 7) || a->ldr < a->N)) return FAME_ERR_ALIGN;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    if (a->M == 0) return FAME_OK;
+
+    CUtensorMap ta, tb;
+    rc = encode_bf16_2d(&ta, a->x, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->ldx, fame::kGemmBM);
+    if (rc != FAME_OK) return rc;
+    rc = encode_bf16_2d(&tb, a->w, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldw, fame::kGemmBN);
+    if (rc != FAME_OK) return rc;
+
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(fame::gemm_bf16_tcgen05_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, fame::kGemmSmemBytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+        attr_set[dev] = true;
+    }
+    fame::GemmParams p;
+    p.M = a->M; p.N = a->N; p.K = a->K;
+    p.bias = a->bias;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+    p.ldr = a->ldr;
+    p.y = a->y;
+    p.ldy = a->ldy;
+    p.act = a->act;
+    p.y_f32 = a->y_dtype == FAME_DT_F32;
+    const int m_tiles = (a->M + fame::kGemmBM - 1) / fame::kGemmBM;
+    const int n_tiles = (a->N + fame::kGemmBN - 1) / fame::kGemmBN;
+    const int tiles = m_tiles * n_tiles;
+    const int grid = tiles < d->sm_count ? tiles : d->sm_count;
+    fame::gemm_bf16_tcgen05_kernel<<<grid, fame::kGemmThreads, fame::kGemmSmemBytes, stream>>>(ta, tb, p);
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+int fame_layernorm(const fame_layernorm_args* a, void*, size_t, fame_stream_t stream) {
+    if (a == nullptr || a->x == nullptr || a->y == nullptr || a->gamma == nullptr || a->beta == nullptr)
+        return FAME_ERR_NULLPTR;
+    if (a->rows < 0 || a->cols <= 0 || (a->cols & 7) || a->cols > 1024) return FAME_ERR_SHAPE;
+    if ((a->ldx & 7) || (a->ldy & 7) || a->ldx < a->cols || a->ldy < a->cols) return FAME_ERR_ALIGN;
+    if (!aligned16(a->x) || !aligned16(a->y) || !aligned16(a->gamma) || !aligned16(a->beta)) return FAME_ERR_ALIGN;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    if (a->rows == 0) return FAME_OK;
+    const int grid = (a->rows + fame::kLnWarpsPerBlock - 1) / fame::kLnWarpsPerBlock;
+    fame::layernorm_bf16_kernel<<<grid, fame::kLnWarpsPerBlock * 32, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a->x), a->ldx, a->gamma, a->beta,
+        reinterpret_cast<__nv_bfloat16*>(a->y), a->ldy, a->rows, a->cols, a->eps);
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------ K4
+int fame_bert_embed(const fame_bert_embed_args* a, void*, size_t, fame_stream_t stream) {
+    if (a == nullptr || a->ids == nullptr || a->word == nullptr || a->pos == nullptr || a->type0 == nullptr ||
+        a->gamma == nullptr || a->beta == nullptr || a->y == nullptr)
+        return FAME_ERR_NULLPTR;
+    if (a->tokens < 0 || a->seq_len <= 0 || a->vocab <= 0 || a->hidden <= 0 || (a->hidden & 127) || a->hidden > 1024)
+        return FAME_ERR_SHAPE;
+    if (!aligned16(a->word) || !aligned16(a->pos) || !aligned16(a->type0) || !aligned16(a->gamma) ||
+        !aligned16(a->beta) || !aligned16(a->y))
+        return FAME_ERR_ALIGN;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    if (a->tokens == 0) return FAME_OK;
+    const int grid = (a->tokens + fame::kLnWarpsPerBlock - 1) / fame::kLnWarpsPerBlock;
+    fame::bert_embed_ln_kernel<<<grid, fame::kLnWarpsPerBlock * 32, 0, stream>>>(
+        reinterpret_cast<const long long*>(a->ids), a->word, a->pos, a->type0, a->gamma, a->beta,
+        reinterpret_cast<__nv_bfloat16*>(a->y), a->err_flag, a->tokens, a->seq_len, a->hidden, a->vocab, a->eps);
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+int fame_attn_fwd(const fame_attn_fwd_args* a, void*, size_t, fame_stream_t stream) {
+    if (a == nullptr || a->qkv == nullptr || a->ctx == nullptr) return FAME_ERR_NULLPTR;
+    if (a->head_dim != fame::kAttnD || a->seq <= 0 || a->seq > fame::kAttnMaxS || a->heads <= 0 || a->batch < 0)
+        return FAME_ERR_SHAPE;
+    const int64_t width = 3ll * a->heads * a->head_dim;
+    if (a->ld_qkv < width || a->ld_ctx < (int64_t)a->heads * a->head_dim) return FAME_ERR_SHAPE;
+    if ((a->ld_qkv & 7) || (a->ld_ctx & 7) || !aligned16(a->qkv) || !aligned16(a->ctx)) return FAME_ERR_ALIGN;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    if (a->batch == 0) return FAME_OK;
+    if (a->batch > 65535 || a->heads > 65535) return FAME_ERR_SHAPE;
+
+    CUtensorMap tq;
+    rc = encode_bf16_2d(&tq, a->qkv, (uint64_t)a->batch * a->seq, (uint64_t)width, (uint64_t)a->ld_qkv, 128);
+    if (rc != FAME_OK) return rc;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(fame::attn_fwd_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             fame::kAttnSmemBytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+        attr_set[dev] = true;
+    }
+    fame::AttnParams p;
+    p.key_mask = a->key_mask;
+    p.ctx = reinterpret_cast<__nv_bfloat16*>(a->ctx);
+    p.ld_ctx = a->ld_ctx;
+    p.batch = a->batch;
+    p.seq = a->seq;
+    p.heads = a->heads;
+    p.scale_log2e = a->scale * 1.4426950408889634f;
+    dim3 grid((a->seq + fame::kAttnBQ - 1) / fame::kAttnBQ, a->heads, a->batch);
+    fame::attn_fwd_d64_kernel<<<grid, fame::kAttnThreads, fame::kAttnSmemBytes, stream>>>(tq, p);
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------ K5
+int fame_segment_mean(const fame_segment_mean_args* a, void*, size_t, fame_stream_t stream) {
+    if (a == nullptr || a->offsets == nullptr || a->out == nullptr) return FAME_ERR_NULLPTR;
+    if (a->patients < 0 || a->cols <= 0 || (a->cols & 7)) return FAME_ERR_SHAPE;
+    if (a->x_dtype != FAME_DT_BF16 && a->x_dtype != FAME_DT_F32) return FAME_ERR_SHAPE;
+    const int64_t ld_align = a->x_dtype == FAME_DT_BF16 ? 7 : 3;
+    if ((a->ldx & ld_align) || !aligned16(a->out) || (a->x != nullptr && !aligned16(a->x))) return FAME_ERR_ALIGN;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    if (a->patients == 0) return FAME_OK;
+    if (a->x_dtype == FAME_DT_BF16)
+        fame::segment_mean_kernel<true><<<a->patients, 128, 0, stream>>>(a->x, a->ldx, a->offsets, a->out,
+                                                                        a->patients, a->cols);
+    else
+        fame::segment_mean_kernel<false><<<a->patients, 128, 0, stream>>>(a->x, a->ldx, a->offsets, a->out,
+                                                                         a->patients, a->cols);
+    return launch_status();
+}
+
+}  // extern "C"

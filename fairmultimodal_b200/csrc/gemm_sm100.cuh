@@ -1,0 +1,232 @@
+// K1: bf16 GEMM on tcgen05 tensor cores, accumulators in TMEM, operands staged by TMA.
+//
+//   Y[M,N] = act( X[M,K] . W[N,K]^T + bias[N] ) (+ residual[M,N])
+//
+// Replaces every nn.Linear on the FAME hot path (reference: HF modeling_bert.py Q/K/V, attention-output,
+// intermediate and output dense layers used through 10_FAME.py:140,199; nn.MultiheadAttention in/out
+// projections and linear1/linear2 of nn.TransformerEncoderLayer, 10_FAME.py:214).
+//
+// Structure (one persistent CTA per SM, 384 threads):
+//   warp 0   : TMA producer   (one lane)  global -> smem ring, kStages x {A 128x64, B 256x64} bf16, SW128
+//   warp 1   : MMA issuer     (one lane)  tcgen05.mma 128x256x16, 4 per k-block, commit -> frees ring slot
+//   warp 2   : TMEM allocator (512 columns = 2 accumulator buffers of 256 f32 columns)
+//   warps 4-11: epilogue      TMEM -> registers -> bias/act/residual -> global; overlaps the next tile's MMAs
+#pragma once
+#include "sm100_ptx.cuh"
+
+namespace fame {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBN = 256;
+constexpr int kGemmBK = 64;
+constexpr int kGemmStages = 4;
+constexpr int kGemmABytes = kGemmBM * kGemmBK * 2;  // 16 KB
+constexpr int kGemmBBytes = kGemmBN * kGemmBK * 2;  // 32 KB
+constexpr int kGemmStageBytes = kGemmABytes + kGemmBBytes;
+constexpr int kGemmThreads = 384;
+constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+enum { kActNone = 0, kActGelu = 1, kActRelu = 2 };
+
+struct GemmParams {
+    int M, N, K;
+    const float* bias;              // [N] or nullptr
+    const __nv_bfloat16* residual;  // [M, ldr] or nullptr
+    long long ldr;
+    void* y;                        // bf16 or f32 [M, ldy]
+    long long ldy;
+    int act;
+    int y_f32;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles must start on 1024-byte boundaries.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kGemmStages * kGemmABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
+    uint64_t* full_bar = bars;                       // [kStages]
+    uint64_t* empty_bar = bars + kGemmStages;        // [kStages]
+    uint64_t* tmem_full = bars + 2 * kGemmStages;    // [2]
+    uint64_t* tmem_empty = bars + 2 * kGemmStages + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGemmStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int m_tiles = (p.M + kGemmBM - 1) / kGemmBM;
+    const int n_tiles = (p.N + kGemmBN - 1) / kGemmBN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kGemmStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 8);  // one arrival per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], kGemmStageBytes);
+                    tma_load_2d(smem_a + stage * kGemmABytes, &tmap_a, &full_bar[stage], kb * kGemmBK,
+                                m_blk * kGemmBM, kEvictNormal);
+                    tma_load_2d(smem_b + stage * kGemmBBytes, &tmap_b, &full_bar[stage], kb * kGemmBK,
+                                n_blk * kGemmBN, kEvictLast);
+                    if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, kGemmBN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kGemmBN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem_a + stage * kGemmABytes);
+                    const uint32_t b_addr = smem_u32(smem_b + stage * kGemmBBytes);
+#pragma unroll
+                    for (int k = 0; k < kGemmBK / 16; ++k) {
+                        const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                        umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------- epilogue (8 warps)
+        const int q = warp & 3;           // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2; // which 128-column half of the accumulator
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * kGemmBM + q * 32 + lane;
+            const bool row_ok = row < p.M;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int col0 = n_blk * kGemmBN + half * 128 + c * 32;
+                if (col0 >= p.N) break;  // warp-uniform
+                uint32_t r[32];
+                tmem_ld_x32(tmem_base + (uint32_t(q * 32) << 16) + acc * kGemmBN + half * 128 + c * 32, r);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (col0 + j < p.N) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                        }
+                    }
+                }
+                if (p.act == kActGelu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                } else if (p.act == kActRelu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                }
+                if (row_ok) {
+                    if (p.residual != nullptr) {
+                        const __nv_bfloat16* rp = p.residual + (long long)row * p.ldr + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            if (col0 + j < p.N) {
+                                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + j));
+                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    const float2 f = __bfloat1622float2(h[t]);
+                                    v[j + 2 * t] += f.x;
+                                    v[j + 2 * t + 1] += f.y;
+                                }
+                            }
+                        }
+                    }
+                    if (p.y_f32) {
+                        float* yp = reinterpret_cast<float*>(p.y) + (long long)row * p.ldy + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (col0 + j < p.N)
+                                *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                    } else {
+                        __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + (long long)row * p.ldy + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            if (col0 + j < p.N) {
+                                uint4 o;
+                                o.x = pack_bf16x2(v[j], v[j + 1]);
+                                o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                                o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                                o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                                *reinterpret_cast<uint4*>(yp + j) = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace fame
