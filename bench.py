@@ -1,0 +1,267 @@
+"""bench.py -- FAME hot-path benchmark (driver contract: one JSON line on stdout from rank 0).
+
+Workload at every N: BASELINE.json configs[1], the BioClinicalBERT (BERT-base, vocab 28 996) note-chunk encoder
+forward over 256 chunks x 512 tokens in bf16 per GPU, followed by the chunk->patient mean pool (4 chunks per
+patient).  One step = one such batch.  Patients/chunks shard across ranks with no data-path collective
+("weak" scaling: per-GPU work fixed).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+  value : chunks/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e   : chunks/s through the public module API from pinned HOST buffers (H2D of ids/mask and D2H of the pooled
+          patient embeddings inside the timed region)
+  --impl reference : the reference's CPU path for the same step (oracle port of BioClinicalBERT_FT.forward called
+          one chunk at a time exactly like 10_FAME.py:157-169, fp32, all host threads), bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHUNKS, SEQ, CHUNKS_PER_PATIENT = 256, 512, 4
+WORKLOAD = "note_encoder_fwd_bert_base_256chunks_x_512tok_bf16 + chunk->patient mean pool (BASELINE configs[1])"
+METRIC = "512-tok note chunks/sec (BioClinicalBERT note-chunk encoder forward)"
+FLOP_PER_TOKEN = 188_743_680           # 12*(2*(4*768^2 + 2*768*3072) + 4*512*768)
+WSEED = 7
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_chunks_per_s(n_chunks, threads=None):
+    """The reference's CPU path for this workload: BioClinicalBERT_FT.forward on ONE chunk per call (10_FAME.py:
+    157-169), fp32, eager -- as restated by oracle/fame_oracle.py (the reference script itself cannot travel to
+    the GPU box).  Returns (chunks/s, threads, seconds)."""
+    import torch
+
+    from fairmultimodal_b200 import synth
+    from oracle import fame_oracle as O
+
+    if threads:
+        torch.set_num_threads(threads)
+    sd = {k: torch.from_numpy(v) for k, v in
+          synth.synth_state_dict(synth.bert_shapes("BioBert.", synth.VOCAB), WSEED).items()}
+    co = synth.make_cohort(max(1, (n_chunks + 3) // 4), lab_tokens=4, chunks="fixed4", seq_len=SEQ, seed=1234)
+    ids, mask = torch.from_numpy(co["input_ids"]), torch.from_numpy(co["attention_mask"])
+    with torch.no_grad():
+        O.note_cls(sd, ids[:1, :64], mask[:1, :64])            # warm the thread pool
+        t0 = time.perf_counter()
+        for j in range(n_chunks):
+            O.note_cls(sd, ids[j:j + 1], mask[j:j + 1])
+        dt = time.perf_counter() - t0
+    return n_chunks / dt, torch.get_num_threads(), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = 1
+    for _ in range(args.warmup):
+        pass                                                   # warm-up is inside cpu_reference (thread pool)
+    v, threads, dt = cpu_reference_chunks_per_s(per_step * args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "chunks/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{per_step} chunk(s) per step, one chunk per call"},
+        "cpu_baseline": {"value": v, "unit": "chunks/s", "cores": threads, "kind": "port",
+                         "sample": f"{per_step * args.steps} chunks x 512 tokens, fp32, oracle port of "
+                                   "BioClinicalBERT_FT.forward, one chunk per call"},
+        "e2e": {"value": v, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from fairmultimodal_b200 import modules, ops, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # random-init BERT-base (vocab 28 996), deterministic in the seed; every rank holds a replica
+    sd = {k: torch.from_numpy(v) for k, v in
+          synth.synth_state_dict(synth.bert_shapes("BioBert.", synth.VOCAB), WSEED).items()}
+    model = modules.BioClinicalBERT_FT.from_state_dict(sd).to(dev)
+    del sd
+    patients = CHUNKS // CHUNKS_PER_PATIENT
+    n_batches = 2                                               # rotate input batches between steps
+    co = synth.make_cohort(patients * n_batches, lab_tokens=4, chunks="fixed4", seq_len=SEQ, seed=1234 + rank)
+    ids_h = torch.from_numpy(co["input_ids"]).view(n_batches, CHUNKS, SEQ).pin_memory()
+    mask_h = torch.from_numpy(co["attention_mask"]).view(n_batches, CHUNKS, SEQ).pin_memory()
+    offs = torch.arange(0, CHUNKS + 1, CHUNKS_PER_PATIENT, dtype=torch.int32, device=dev)
+    ids_d, mask_d = ids_h.to(dev), mask_h.to(dev)
+    out_h = torch.empty((patients, 768), dtype=torch.float32).pin_memory()
+
+    def step_resident(i):
+        h = model.encode_chunks(ids_d[i % n_batches], mask_d[i % n_batches])
+        return modules.pool_chunks(h, offs, ldx=SEQ * 768, cols=768)
+
+    def step_e2e(i):
+        ids = ids_h[i % n_batches].to(dev, non_blocking=True)
+        mask = mask_h[i % n_batches].to(dev, non_blocking=True)
+        h = model.encode_chunks(ids, mask)
+        out_h.copy_(modules.pool_chunks(h, offs, ldx=SEQ * 768, cols=768), non_blocking=True)
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM; every launch bracketed by events for the roofline ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.LAUNCHES
+    ops.start_trace()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_resident(i)
+    e1.record()
+    barrier()
+    trace = ops.stop_trace()
+    launches = ops.LAUNCHES - launches0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed region 2: end to end from pinned host memory ----
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(i)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+
+    if rank == 0:
+        pk = peaks()
+        by = {}
+        for name, tag, a, b, work in trace:
+            d = by.setdefault(name, [0.0, 0.0, 0])
+            d[0] += a.elapsed_time(b); d[1] += work; d[2] += 1
+        g = by["fame_gemm_bias_act"]
+        gemm_tf = g[1] / (g[0] * 1e-3) / 1e12
+        kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] / args.steps,
+                       "share": v[0] / sum(x[0] for x in by.values())} for k, v in by.items()}
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("fame_gemm_bias_act")
+        value = world * CHUNKS * args.steps / (ms * 1e-3)
+        cpu_v, cpu_threads, cpu_dt = cpu_reference_chunks_per_s(args.cpu_chunks) if (world == 1 and args.cpu_chunks > 0) else (None, None, None)
+        line = {
+            "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "chunks_per_gpu_per_step": CHUNKS, "seq_len": SEQ,
+                       "patients_per_gpu_per_step": patients, "parallelism": f"dp{world} (chunks sharded, no collective)",
+                       "weights": "random-init BERT-base, vocab 28996 (no checkpoint reachable)",
+                       "l2": "per-step working set (216 MB bf16 weights + >1 GB activations) exceeds the 126 MB L2; "
+                             "input batches rotate between steps"},
+            "tflops_model": value * SEQ * FLOP_PER_TOKEN / 1e12,
+            "tensor_frac_of_sustained_peak": value / world * SEQ * FLOP_PER_TOKEN / 1e12 / pk["tf_sust"],
+            "e2e": {"value": world * CHUNKS * args.steps / (ms_e2e * 1e-3), "unit": "chunks/s",
+                    "h2d_bytes_per_step": int(ids_h[0].numel() * 8 + mask_h[0].numel() * 8),
+                    "d2h_bytes_per_step": int(out_h.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": gemm_tf,
+                         "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sust"],
+                         "traffic": traffic, "peak_source": f"{pk['src']} (sustained cuBLAS bf16)",
+                         "launches_per_step": g[2] / args.steps, "avg_launch_ms": g[0] / g[2]},
+            "kernels": kernels,
+            "clocks": clocks,
+        }
+        if cpu_v is not None:
+            line["cpu_baseline"] = {"value": cpu_v, "unit": "chunks/s", "cores": cpu_threads, "kind": "port",
+                                    "sample": f"{args.cpu_chunks} chunks x 512 tokens ({cpu_dt:.1f} s), fp32 oracle port "
+                                              "of BioClinicalBERT_FT.forward, one chunk per call as 10_FAME.py:157-169"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-chunks", type=int, default=3, help="chunks timed for the cpu_baseline leg")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

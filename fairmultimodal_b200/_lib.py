@@ -58,7 +58,7 @@ class AttnFwdArgs(C.Structure):
         ("key_mask", C.c_void_p),
         ("ctx", C.c_void_p), ("ld_ctx", C.c_int64),
         ("batch", C.c_int32), ("seq", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
-        ("scale", C.c_float),
+        ("scale", C.c_float), ("algo", C.c_int32),
     ]
 
 
@@ -66,7 +66,7 @@ class SegmentMeanArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("ldx", C.c_int64), ("x_dtype", C.c_int32),
         ("offsets", C.c_void_p), ("out", C.c_void_p),
-        ("patients", C.c_int32), ("cols", C.c_int32),
+        ("patients", C.c_int32), ("cols", C.c_int32), ("mode", C.c_int32),
     ]
 
 

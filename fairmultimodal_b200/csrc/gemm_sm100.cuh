@@ -10,7 +10,10 @@
 //   warp 0   : TMA producer   (one lane)  global -> smem ring, kStages x {A 128x64, B 256x64} bf16, SW128
 //   warp 1   : MMA issuer     (one lane)  tcgen05.mma 128x256x16, 4 per k-block, commit -> frees ring slot
 //   warp 2   : TMEM allocator (512 columns = 2 accumulator buffers of 256 f32 columns)
-//   warps 4-11: epilogue      TMEM -> registers -> bias/act/residual -> global; overlaps the next tile's MMAs
+//   warps 4-11: epilogue, two warpgroups of 128 threads, each owning 128 accumulator columns:
+//              TMEM -> registers -> bias/act/residual -> bf16 -> swizzled smem box (128 rows x 64 cols) ->
+//              TMA store (coalesced, asynchronous).  Runs concurrently with the next tile's MMAs.
+//              (f32 output, used only for tiny matrices, is written with direct vector stores instead.)
 #pragma once
 #include "sm100_ptx.cuh"
 
@@ -23,8 +26,9 @@ constexpr int kGemmStages = 4;
 constexpr int kGemmABytes = kGemmBM * kGemmBK * 2;  // 16 KB
 constexpr int kGemmBBytes = kGemmBN * kGemmBK * 2;  // 32 KB
 constexpr int kGemmStageBytes = kGemmABytes + kGemmBBytes;
+constexpr int kGemmCBoxBytes = 128 * 64 * 2;        // 16 KB staging box per epilogue warpgroup
 constexpr int kGemmThreads = 384;
-constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + 2 * kGemmCBoxBytes + 1024 /*align slack*/ + 256;
 
 enum { kActNone = 0, kActGelu = 1, kActRelu = 2 };
 
@@ -39,17 +43,39 @@ struct GemmParams {
     int y_f32;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf-GELU (HF "gelu", modeling_bert.py:339-342):  0.5 x (1 + erf(x / sqrt 2)).
+// erf(x/sqrt2) is evaluated as xc * Q(xc^2) with xc = clamp(x, +-3 sqrt2), Q of degree 8 fitted by
+// scripts/fit_gelu_poly.py (max |erf error| 3.1e-5, max |gelu error| 6.7e-5 -- far below the bf16 output ulp).
+// 13 FP32 instructions and no MUFU per element: the libdevice erff (~30 instructions, divergent branches) made the
+// 3072-wide FFN epilogue slower than its K = 768 main loop.
+__device__ __forceinline__ float gelu_erf(float x) {
+    constexpr float c0 = 7.978010774e-01f, c1 = -1.326614171e-01f, c2 = 1.961016096e-02f, c3 = -2.209631959e-03f,
+                    c4 = 1.854783768e-04f, c5 = -1.111321126e-05f, c6 = 4.429220439e-07f, c7 = -1.040250019e-08f,
+                    c8 = 1.080706497e-10f;
+    const float xc = fminf(fmaxf(x, -4.242640687f), 4.242640687f);
+    const float u = xc * xc;
+    float q = fmaf(c8, u, c7);
+    q = fmaf(q, u, c6);
+    q = fmaf(q, u, c5);
+    q = fmaf(q, u, c4);
+    q = fmaf(q, u, c3);
+    q = fmaf(q, u, c2);
+    q = fmaf(q, u, c1);
+    q = fmaf(q, u, c0);
+    const float h = 0.5f * x;
+    return fmaf(h, xc * q, h);
+}
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles must start on 1024-byte boundaries.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kGemmStages * kGemmABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
+    uint8_t* smem_c = smem + kGemmStages * kGemmStageBytes;  // 2 x 16 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * kGemmCBoxBytes);
     uint64_t* full_bar = bars;                       // [kStages]
     uint64_t* empty_bar = bars + kGemmStages;        // [kStages]
     uint64_t* tmem_full = bars + 2 * kGemmStages;    // [2]
@@ -67,6 +93,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        tma_prefetch_desc(&tmap_c);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kGemmStages; ++i) {
@@ -137,30 +164,49 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
         }
     } else if (warp >= 4) {
-        // ---------------------------------------------------- epilogue (8 warps)
-        const int q = warp & 3;           // TMEM lane quarter this warp may access
-        const int half = (warp - 4) >> 2; // which 128-column half of the accumulator
+        // ---------------------------------------------------- epilogue (2 warpgroups x 4 warps)
+        const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2;  // which 128-column half of the accumulator (= warpgroup)
+        const int r_local = q * 32 + lane; // row inside the tile
+        const bool wg_leader = (q == 0 && lane == 0);
+        uint8_t* cbox = smem_c + half * kGemmCBoxBytes;
+        uint8_t* crow = cbox + r_local * 128;
+        const int sw = r_local & 7;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const int row = m_blk * kGemmBM + q * 32 + lane;
+            const int row = m_blk * kGemmBM + r_local;
             const bool row_ok = row < p.M;
+            const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * kGemmBN + half * 128;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const int col0 = n_blk * kGemmBN + half * 128 + c * 32;
-                if (col0 >= p.N) break;  // warp-uniform
-                uint32_t r[32];
-                tmem_ld_x32(tmem_base + (uint32_t(q * 32) << 16) + acc * kGemmBN + half * 128 + c * 32, r);
-                tmem_ld_wait();
-                float v[32];
+            for (int cc = 0; cc < 2; ++cc) {
+                const int col0 = n_blk * kGemmBN + half * 128 + cc * 64;
+                const bool active = col0 < p.N;  // warpgroup-uniform
+                float v[64];
+                if (active) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_x32(t_addr + cc * 64, r0);
+                    tmem_ld_x32(t_addr + cc * 64 + 32, r1);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = __uint_as_float(r0[j]);
+                        v[32 + j] = __uint_as_float(r1[j]);
+                    }
+                }
+                if (cc == 1) {
+                    // accumulator fully read: hand the TMEM buffer back to the MMA warp before the math
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                }
+                if (!active) continue;
                 if (p.bias != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
+                    for (int j = 0; j < 64; j += 4) {
                         if (col0 + j < p.N) {
                             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
                             v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
@@ -169,56 +215,60 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
                 if (p.act == kActGelu) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    for (int j = 0; j < 64; ++j) v[j] = gelu_erf(v[j]);
                 } else if (p.act == kActRelu) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                    for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.0f);
                 }
-                if (row_ok) {
-                    if (p.residual != nullptr) {
-                        const __nv_bfloat16* rp = p.residual + (long long)row * p.ldr + col0;
+                if (p.residual != nullptr && row_ok) {
+                    const __nv_bfloat16* rp = p.residual + (long long)row * p.ldr + col0;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            if (col0 + j < p.N) {
-                                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + j));
-                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                    for (int j = 0; j < 64; j += 8) {
+                        if (col0 + j < p.N) {
+                            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + j));
+                            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    const float2 f = __bfloat1622float2(h[t]);
-                                    v[j + 2 * t] += f.x;
-                                    v[j + 2 * t + 1] += f.y;
-                                }
+                            for (int t = 0; t < 4; ++t) {
+                                const float2 f = __bfloat1622float2(h2[t]);
+                                v[j + 2 * t] += f.x;
+                                v[j + 2 * t + 1] += f.y;
                             }
                         }
                     }
-                    if (p.y_f32) {
+                }
+                if (p.y_f32) {
+                    if (row_ok) {
                         float* yp = reinterpret_cast<float*>(p.y) + (long long)row * p.ldy + col0;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
+                        for (int j = 0; j < 64; j += 4) {
                             if (col0 + j < p.N)
                                 *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                         }
-                    } else {
-                        __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + (long long)row * p.ldy + col0;
+                    }
+                } else {
+                    // the previous TMA store out of this warpgroup's box must have finished reading it
+                    if (wg_leader) tma_store_wait_read();
+                    named_bar_sync(1 + half, 128);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            if (col0 + j < p.N) {
-                                uint4 o;
-                                o.x = pack_bf16x2(v[j], v[j + 1]);
-                                o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                                o.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                                o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                                *reinterpret_cast<uint4*>(yp + j) = o;
-                            }
-                        }
+                    for (int c = 0; c < 8; ++c) {
+                        uint4 o;
+                        o.x = pack_bf16x2(v[8 * c], v[8 * c + 1]);
+                        o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+                        o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+                        o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+                        *reinterpret_cast<uint4*>(crow + ((c ^ sw) << 4)) = o;  // SW128: 16-byte chunk ^= row % 8
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1 + half, 128);
+                    if (wg_leader) {
+                        tma_store_2d(&tmap_c, cbox, col0, m_blk * kGemmBM);
+                        tma_store_commit();
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (wg_leader) tma_store_wait_all();
     }
 
     tc_fence_before();

@@ -159,12 +159,27 @@ bert_embed_ln_kernel(const long long* __restrict__ ids, const float* __restrict_
     }
 }
 
-// ---------------------------------------------------------------------------------------- K5 segment mean
+// ---------------------------------------------------------------------------------------- K5 segment mean / max
 // One block per patient; thread t owns columns [8t, 8t+8).  Rows (chunks) are streamed 4 at a time.
+// kMax = false: arithmetic mean (aggregation="mean", 10_FAME.py:171); true: column-wise max (the "max" branch).
 template <bool kBf16>
+__device__ __forceinline__ void load_row8(const void* __restrict__ x, long long off, float* f) {
+    if (kBf16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + off));
+        bf16x8_to_float(v, f);
+    } else {
+        const float* xr = reinterpret_cast<const float*>(x) + off;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(xr));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(xr) + 1);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+        f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+}
+
+template <bool kBf16, bool kMax>
 __global__ void __launch_bounds__(128)
-segment_mean_kernel(const void* __restrict__ x, long long ldx, const int* __restrict__ offsets,
-                    float* __restrict__ out, int patients, int cols) {
+segment_reduce_kernel(const void* __restrict__ x, long long ldx, const int* __restrict__ offsets,
+                      float* __restrict__ out, int patients, int cols) {
     const int p = blockIdx.x;
     if (p >= patients) return;
     const int beg = __ldg(offsets + p), end = __ldg(offsets + p + 1);
@@ -172,47 +187,25 @@ segment_mean_kernel(const void* __restrict__ x, long long ldx, const int* __rest
     for (int c0 = threadIdx.x * 8; c0 < cols; c0 += blockDim.x * 8) {
         float acc[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int j = 0; j < 8; ++j) acc[j] = (kMax && n > 0) ? -INFINITY : 0.f;
         int r = beg;
         for (; r + 4 <= end; r += 4) {
             float f[4][8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (kBf16) {
-                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(
-                        reinterpret_cast<const __nv_bfloat16*>(x) + (long long)(r + u) * ldx + c0));
-                    bf16x8_to_float(v, f[u]);
-                } else {
-                    const float* xr = reinterpret_cast<const float*>(x) + (long long)(r + u) * ldx + c0;
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(xr));
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(xr) + 1);
-                    f[u][0] = a.x; f[u][1] = a.y; f[u][2] = a.z; f[u][3] = a.w;
-                    f[u][4] = b.x; f[u][5] = b.y; f[u][6] = b.z; f[u][7] = b.w;
-                }
-            }
+            for (int u = 0; u < 4; ++u) load_row8<kBf16>(x, (long long)(r + u) * ldx + c0, f[u]);
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += f[u][j];
+                for (int j = 0; j < 8; ++j) acc[j] = kMax ? fmaxf(acc[j], f[u][j]) : acc[j] + f[u][j];
         }
         for (; r < end; ++r) {
             float f[8];
-            if (kBf16) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(
-                    reinterpret_cast<const __nv_bfloat16*>(x) + (long long)r * ldx + c0));
-                bf16x8_to_float(v, f);
-            } else {
-                const float* xr = reinterpret_cast<const float*>(x) + (long long)r * ldx + c0;
-                const float4 a = __ldg(reinterpret_cast<const float4*>(xr));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(xr) + 1);
-                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
-                f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-            }
+            load_row8<kBf16>(x, (long long)r * ldx + c0, f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            for (int j = 0; j < 8; ++j) acc[j] = kMax ? fmaxf(acc[j], f[j]) : acc[j] + f[j];
         }
-        // sum-then-divide, rows added in order: bit-identical to np.mean(axis=0) on f32 rows; n == 0 -> zeros
-        const float den = n > 0 ? (float)n : 1.0f;
+        // mean: sum-then-divide with rows added in order == np.mean(axis=0) on f32 rows, bit for bit; n == 0 -> zeros
+        const float den = (!kMax && n > 0) ? (float)n : 1.0f;
         float* o = out + (long long)p * cols + c0;
         *reinterpret_cast<float4*>(o) = make_float4(acc[0] / den, acc[1] / den, acc[2] / den, acc[3] / den);
         *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4] / den, acc[5] / den, acc[6] / den, acc[7] / den);

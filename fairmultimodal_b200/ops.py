@@ -15,6 +15,37 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# Launch accounting for bench.py: number of kernels launched, and (when tracing) CUDA-event pairs around each
+# launch on the launching stream, tagged so that per-kernel durations and algorithmic work can be summed.
+LAUNCHES = 0
+_TRACE = None
+
+
+def start_trace():
+    global _TRACE
+    _TRACE = []
+
+
+def stop_trace():
+    """Returns [(op name, tag, start_event, end_event, work)], work = algorithmic FLOPs or bytes of the launch."""
+    global _TRACE
+    t, _TRACE = _TRACE, None
+    return t
+
+
+def _call(name, args, work=0.0, tag=""):
+    global LAUNCHES
+    LAUNCHES += 1
+    if _TRACE is None:
+        _lib.call(name, args, _stream())
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.call(name, args, _stream())
+    e1.record()
+    _TRACE.append((name, tag, e0, e1, work))
+
+
 def _cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
     if not t.is_cuda:
         raise _lib.FameError(f"{name} must be a CUDA tensor (fairmultimodal_b200 has no CPU path)")
@@ -52,7 +83,7 @@ def gemm_bias_act(x, w, bias=None, residual=None, act=ACT_NONE, out=None, out_dt
     a.y, a.ldy = out.data_ptr(), _rowmajor(out, "out")
     a.y_dtype = DT_F32 if out.dtype == torch.float32 else DT_BF16
     a.M, a.N, a.K, a.act = M, N, K, act
-    _lib.call("fame_gemm_bias_act", a, _stream())
+    _call("fame_gemm_bias_act", a, 2.0 * M * N * K, f"{N}x{K}")
     return out
 
 
@@ -67,7 +98,7 @@ def layernorm(x, gamma, beta, eps, out=None):
     a.beta = _cuda(beta, "beta", torch.float32).data_ptr()
     a.y, a.ldy = out.data_ptr(), _rowmajor(out, "out")
     a.rows, a.cols, a.eps = rows, cols, eps
-    _lib.call("fame_layernorm", a, _stream())
+    _call("fame_layernorm", a, 4.0 * rows * cols)
     return out
 
 
@@ -86,11 +117,11 @@ def bert_embed(ids, word, pos, type_emb, gamma, beta, eps, seq_len, err_flag=Non
     a.y = out.data_ptr()
     a.err_flag = err_flag.data_ptr() if err_flag is not None else None
     a.tokens, a.seq_len, a.hidden, a.vocab, a.eps = ids.numel(), seq_len, hidden, word.shape[0], eps
-    _lib.call("fame_bert_embed", a, _stream())
+    _call("fame_bert_embed", a, ids.numel() * (8.0 + 10.0 * hidden))
     return out
 
 
-def attn_fwd(qkv, batch, seq, heads, head_dim, key_mask=None, scale=None, out=None):
+def attn_fwd(qkv, batch, seq, heads, head_dim, key_mask=None, scale=None, out=None, algo=0):
     """qkv bf16 [batch*seq, 3*heads*head_dim] -> ctx bf16 [batch*seq, heads*head_dim]."""
     _cuda(qkv, "qkv", torch.bfloat16)
     if out is None:
@@ -107,11 +138,12 @@ def attn_fwd(qkv, batch, seq, heads, head_dim, key_mask=None, scale=None, out=No
     a.ctx, a.ld_ctx = out.data_ptr(), _rowmajor(out, "ctx")
     a.batch, a.seq, a.heads, a.head_dim = batch, seq, heads, head_dim
     a.scale = float(scale) if scale is not None else head_dim ** -0.5
-    _lib.call("fame_attn_fwd", a, _stream())
+    a.algo = algo
+    _call("fame_attn_fwd", a, 4.0 * batch * heads * seq * seq * head_dim)
     return out
 
 
-def segment_mean(x, offsets, cols=None, ldx=None):
+def segment_mean(x, offsets, cols=None, ldx=None, mode="mean"):
     """out[p] = mean of rows offsets[p]:offsets[p+1] of x (row stride ldx elements); zeros for empty segments."""
     _cuda(x, "x")
     _cuda(offsets, "offsets", torch.int32)
@@ -128,5 +160,7 @@ def segment_mean(x, offsets, cols=None, ldx=None):
     a.x_dtype = DT_BF16 if x.dtype == torch.bfloat16 else DT_F32
     a.offsets, a.out = offsets.data_ptr(), out.data_ptr()
     a.patients, a.cols = patients, cols
-    _lib.call("fame_segment_mean", a, _stream())
+    a.mode = {"mean": 0, "max": 1}[mode]
+    # algorithmic bytes: rows read (not known without a sync: caller may refine) + offsets + output
+    _call("fame_segment_mean", a, 4.0 * (patients + 1) + 4.0 * patients * cols)
     return out

@@ -105,8 +105,10 @@ int fame_bert_embed(const fame_bert_embed_args* a, void* workspace, size_t works
  * K2  fame_attn_fwd:  ctx = softmax(Q K^T * scale + key_mask) V   per (sequence, head); tcgen05 + TMEM.
  * qkv: bf16 [batch*seq, 3*heads*head_dim] packed [Q | K | V] (the output of the fused QKV GEMM);
  * key_mask: uint8 [batch, seq], 1 = attend, 0 = masked (additive -inf), may be NULL;
- * ctx: bf16 [batch*seq, heads*head_dim].  head_dim == 64, seq <= 512 in this version.
- * Replaces the sdpa call in BertSelfAttention (HF:192-206) incl. the additive mask built at HF:709-713. */
+ * ctx: bf16 [batch*seq, heads*head_dim].  head_dim 64 or 96, any seq.  Masked keys get probability exactly 0; a row
+ * whose keys are ALL masked yields zeros (the reference path never produces one: [CLS] is always attended).
+ * Replaces the sdpa call in BertSelfAttention (HF:192-206) incl. the additive mask built at HF:709-713, and
+ * F.multi_head_attention_forward's attention core inside nn.TransformerEncoderLayer (10_FAME.py:214,222). */
 typedef struct {
     const void* qkv;
     int64_t ld_qkv;
@@ -115,6 +117,7 @@ typedef struct {
     int64_t ld_ctx;
     int32_t batch, seq, heads, head_dim;
     float scale;
+    int32_t algo; /* 0 = auto; 1 = full-row TMEM kernel (head_dim 64, seq <= 512); 2 = streaming flash kernel */
 } fame_attn_fwd_args;
 int fame_attn_fwd(const fame_attn_fwd_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
 
@@ -131,6 +134,7 @@ typedef struct {
     const int32_t* offsets;
     float* out; /* [patients, cols] */
     int32_t patients, cols;
+    int32_t mode; /* 0 = mean (aggregation="mean"), 1 = max (the reference's other aggregation branch) */
 } fame_segment_mean_args;
 int fame_segment_mean(const fame_segment_mean_args* a, void* workspace, size_t workspace_bytes,
                       fame_stream_t stream);

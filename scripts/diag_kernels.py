@@ -105,35 +105,38 @@ def run_attn():
     torch.manual_seed(1)
     dev = "cuda"
     ok = True
-    H, D = 12, 64
-    for (B, S, masked) in [(1, 128, False), (2, 512, False), (3, 512, True), (2, 300, True), (2, 77, False), (4, 256, True)]:
+    for (H, D, B, S, masked, algo) in [
+        (12, 64, 1, 128, False, 2), (12, 64, 2, 512, False, 2), (12, 64, 3, 512, True, 2), (12, 64, 2, 300, True, 2),
+        (12, 64, 2, 77, False, 2), (12, 64, 2, 1000, True, 2), (8, 96, 2, 128, False, 2), (8, 96, 3, 542, False, 2),
+        (8, 96, 2, 542, True, 2), (8, 96, 2, 12, False, 2), (8, 96, 1, 1300, False, 2), (12, 64, 3, 512, True, 1),
+    ]:
         qkv = (torch.randn(B * S, 3 * H * D, device=dev) * 1.0).bfloat16()
         mask = None
         if masked:
             lens = torch.randint(1, S + 1, (B,), device=dev)
             mask = (torch.arange(S, device=dev)[None, :] < lens[:, None]).to(torch.uint8).contiguous()
-        ctx = ops.attn_fwd(qkv, B, S, H, D, key_mask=mask)
+        ctx = ops.attn_fwd(qkv, B, S, H, D, key_mask=mask, algo=algo)
         torch.cuda.synchronize()
         q, k, v = qkv.float().view(B, S, 3, H, D).permute(2, 0, 3, 1, 4)
         s = (q @ k.transpose(-1, -2)) * D ** -0.5
         if mask is not None:
             s = s.masked_fill(mask[:, None, None, :] == 0, float("-inf"))
         ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * S, H * D)
-        ok &= _err_report(f"attn B{B} S{S} masked{int(masked)}", ctx, ref, 2e-2)
-    B, S = 256, 512
-    qkv = torch.randn(B * S, 3 * H * D, device=dev).bfloat16()
-    out = torch.empty(B * S, H * D, device=dev, dtype=torch.bfloat16)
-    for _ in range(3):
-        ops.attn_fwd(qkv, B, S, H, D, out=out)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(10):
-        ops.attn_fwd(qkv, B, S, H, D, out=out)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    print(f"[attn-time] B{B} S{S}: {ms:.3f} ms  {4.0 * B * H * S * S * D / ms / 1e9:.1f} TFLOP/s", flush=True)
+        ok &= _err_report(f"attn algo{algo} H{H} D{D} B{B} S{S} masked{int(masked)}", ctx, ref, 2e-2)
+    for (H, D, B, S, algo) in [(12, 64, 256, 512, 1), (12, 64, 256, 512, 2), (8, 96, 256, 542, 2)]:
+        qkv = torch.randn(B * S, 3 * H * D, device=dev).bfloat16()
+        out = torch.empty(B * S, H * D, device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            ops.attn_fwd(qkv, B, S, H, D, out=out, algo=algo)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            ops.attn_fwd(qkv, B, S, H, D, out=out, algo=algo)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"[attn-time] algo{algo} H{H} D{D} B{B} S{S}: {ms:.3f} ms  {4.0 * B * H * S * S * D / ms / 1e9:.1f} TFLOP/s", flush=True)
     return ok
 
 

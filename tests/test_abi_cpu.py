@@ -1,0 +1,84 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol the header
+declares; argument structs match the header; state_dict layouts match the reference's."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import __graft_entry__ as entry
+from fairmultimodal_b200 import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    entry.build()
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    header = open(os.path.join(ROOT, "include", "fame_b200.h")).read()
+    declared = set(re.findall(r"\b(fame_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/fame_b200.h but not exported"
+    assert declared == set(_lib.OP_TABLE) | set(_lib.PLAIN_SYMBOLS)
+
+
+def test_struct_sizes_match_header(lib):
+    # compile a tiny C program against the header and compare sizeof() with the ctypes mirrors
+    import subprocess, tempfile
+    names = {"fame_gemm_args": _lib.GemmArgs, "fame_layernorm_args": _lib.LayerNormArgs,
+             "fame_bert_embed_args": _lib.BertEmbedArgs, "fame_attn_fwd_args": _lib.AttnFwdArgs,
+             "fame_segment_mean_args": _lib.SegmentMeanArgs}
+    for extra in getattr(_lib, "EXTRA_STRUCTS", {}).items():
+        names[extra[0]] = extra[1]
+    src = '#include <stdio.h>\n#include "fame_b200.h"\nint main(){' + "".join(
+        f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "return 0;}"
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")], check=True)
+        out = subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout
+    for line in out.strip().splitlines():
+        n, sz = line.split()
+        assert ctypes.sizeof(names[n]) == int(sz), n
+
+
+def test_no_device_is_an_error_not_a_fallback(lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.fame_device_check() != 0
+    assert b"" != lib.fame_strerror(-1)
+    from fairmultimodal_b200 import ops
+    with pytest.raises(_lib.FameError):
+        ops.layernorm(torch.zeros(4, 768, dtype=torch.bfloat16), torch.ones(768), torch.zeros(768), 1e-5)
+
+
+def test_note_encoder_state_dict_layout():
+    from fairmultimodal_b200.bert import BertModelB200
+    m = BertModelB200(64, num_hidden_layers=2)
+    shapes = synth.bert_shapes("", 64, layers=2)
+    sd = m.state_dict()
+    assert set(sd) == set(shapes)
+    assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in sd)
+
+
+def test_hf_bert_round_trip():
+    from transformers import BertConfig, BertModel
+    from fairmultimodal_b200.bert import BertModelB200
+    hf = BertModel(BertConfig(vocab_size=50, num_hidden_layers=1))
+    m = BertModelB200.from_hf(hf)
+    hf.load_state_dict(m.state_dict(), strict=True)          # loads both ways
+
+
+def test_synth_cohort_shapes():
+    co = synth.make_cohort(10, lab_tokens=12, chunks="u1_16", seq_len=64, seed=0)
+    C = int(co["chunk_offsets"][-1])
+    assert co["input_ids"].shape == (C, 64) and (co["input_ids"][:, 0] == synth.CLS_ID).all()
+    v = co["valid_len"]
+    assert (co["input_ids"][range(C), v - 1] == synth.SEP_ID).all()
+    assert ((co["attention_mask"].sum(1)) == v).all()
+    assert co["insurance_ids"].max() <= 4 and co["age_ids"].max() <= 4

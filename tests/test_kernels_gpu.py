@@ -1,0 +1,115 @@
+"""Unit parity of each CUDA kernel, called through the C ABI, against a plain PyTorch fp32 statement of the op."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    import __graft_entry__ as entry
+    entry.build()
+
+
+def _close(got, ref, rel):
+    got, ref = got.float(), ref.float()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() <= rel * (ref.abs().max().item() + 1e-12)
+
+
+@pytest.mark.parametrize("M,N,K,bias,res,act,f32", [
+    (128, 256, 64, False, False, 0, False), (256, 512, 768, True, False, 0, False),
+    (200, 264, 72, True, True, 0, False), (1000, 768, 3072, True, True, 0, False),
+    (777, 3072, 768, True, False, 1, False), (512, 2048, 768, True, False, 2, False),
+    (33, 256, 768, True, False, 0, True), (1, 8, 8, False, False, 0, True),
+    (148 * 128 * 2 + 5, 768, 768, True, True, 0, False),
+])
+def test_gemm(M, N, K, bias, res, act, f32):
+    from fairmultimodal_b200 import ops
+    torch.manual_seed(M + N + K)
+    x = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda") if bias else None
+    r = torch.randn(M, N, device="cuda").bfloat16() if res else None
+    y = ops.gemm_bias_act(x, w, b, r, act, out_dtype=torch.float32 if f32 else torch.bfloat16)
+    ref = x.float() @ w.float().t()
+    if bias:
+        ref = ref + b
+    ref = torch.nn.functional.gelu(ref) if act == 1 else torch.relu(ref) if act == 2 else ref
+    if res:
+        ref = ref + r.float()
+    _close(y, ref, 1e-5 if f32 else 1e-2)        # bf16 output rounding: 2^-8 relative
+
+
+def test_gemm_rejects_bad_shapes():
+    from fairmultimodal_b200 import _lib, ops
+    x = torch.zeros(16, 12, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(8, 12, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(_lib.FameError):
+        ops.gemm_bias_act(x, w)                    # K % 8 != 0
+
+
+@pytest.mark.parametrize("H,D,B,S,masked,algo", [
+    # full-row TMEM kernel (head_dim 64, seq <= 512)
+    (12, 64, 1, 128, False, 1), (12, 64, 2, 512, False, 1), (12, 64, 3, 512, True, 1), (12, 64, 2, 300, True, 1),
+    (12, 64, 2, 77, False, 1), (12, 64, 2, 1, False, 1),
+    # streaming flash kernel: BERT heads (64) and lab-encoder heads (96; L = 542 is the real cohort's token count)
+    (12, 64, 2, 512, True, 2), (12, 64, 2, 300, True, 2), (12, 64, 2, 1, False, 2), (12, 64, 2, 1000, True, 2),
+    (8, 96, 3, 542, False, 2), (8, 96, 2, 542, True, 2), (8, 96, 2, 12, False, 2), (8, 96, 1, 1300, False, 2),
+    (8, 96, 5, 128, False, 0), (12, 64, 4, 256, True, 0),
+])
+def test_attention(H, D, B, S, masked, algo):
+    from fairmultimodal_b200 import ops
+    torch.manual_seed(S + B)
+    qkv = torch.randn(B * S, 3 * H * D, device="cuda").bfloat16()
+    mask = None
+    if masked:
+        lens = torch.randint(1, S + 1, (B,), device="cuda")
+        mask = (torch.arange(S, device="cuda")[None, :] < lens[:, None]).to(torch.uint8).contiguous()
+    ctx = ops.attn_fwd(qkv, B, S, H, D, key_mask=mask, algo=algo)
+    q, k, v = qkv.float().view(B, S, 3, H, D).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * D ** -0.5
+    if mask is not None:
+        s = s.masked_fill(mask[:, None, None, :] == 0, float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * S, H * D)
+    _close(ctx, ref, 2e-2)
+
+
+def test_layernorm_and_embed():
+    from fairmultimodal_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(1003, 768, device="cuda").bfloat16()
+    g, b = torch.randn(768, device="cuda"), torch.randn(768, device="cuda")
+    for eps in (1e-12, 1e-5):
+        _close(ops.layernorm(x, g, b, eps), torch.nn.functional.layer_norm(x.float(), (768,), g, b, eps), 1e-2)
+    V, S = 1000, 64
+    word, pos, typ = (torch.randn(n, 768, device="cuda") * 0.02 for n in (V, 512, 2))
+    ids = torch.randint(0, V, (5, S), device="cuda")
+    y = ops.bert_embed(ids, word, pos, typ[0].contiguous(), g, b, 1e-12, S)
+    ref = torch.nn.functional.layer_norm(word[ids] + typ[0] + pos[None, :S], (768,), g, b, 1e-12).view(-1, 768)
+    _close(y, ref, 1e-2)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.bert_embed(torch.full((1, S), V + 3, device="cuda"), word, pos, typ[0].contiguous(), g, b, 1e-12, S, err_flag=flag)
+    assert flag.item() == 1                       # out-of-range ids are reported, not silently read
+
+
+@pytest.mark.parametrize("mode", ["mean", "max"])
+def test_segment_reduce_bit_exact(mode):
+    """Chunk->patient indexing and the f32 mean are bit-exact against numpy (empty, single, ragged segments)."""
+    from fairmultimodal_b200 import ops
+    rng = np.random.default_rng(0)
+    counts = np.array([4, 0, 1, 16, 3, 7, 0, 2, 33], dtype=np.int32)
+    offs = np.zeros(len(counts) + 1, dtype=np.int32)
+    offs[1:] = counts.cumsum()
+    x = rng.standard_normal((int(offs[-1]), 768)).astype(np.float32)
+    out = ops.segment_mean(torch.from_numpy(x).cuda(), torch.from_numpy(offs).cuda(), mode=mode).cpu().numpy()
+    f = np.mean if mode == "mean" else np.max
+    ref = np.stack([f(x[offs[i]:offs[i + 1]], axis=0) if counts[i] else np.zeros(768, np.float32) for i in range(len(counts))])
+    np.testing.assert_array_equal(out, ref)
+    # CLS gather folded into the row stride (bf16 hidden state, seq 16)
+    hs = torch.randn(int(offs[-1]) * 16, 768, device="cuda").bfloat16()
+    out = ops.segment_mean(hs, torch.from_numpy(offs).cuda(), cols=768, ldx=16 * 768, mode=mode).cpu().numpy()
+    cls = hs.view(-1, 16, 768)[:, 0].float().cpu().numpy()
+    ref = np.stack([f(cls[offs[i]:offs[i + 1]], axis=0) if counts[i] else np.zeros(768, np.float32) for i in range(len(counts))])
+    np.testing.assert_array_equal(out, ref)
