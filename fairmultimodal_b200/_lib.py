@@ -25,7 +25,7 @@ class GemmArgs(C.Structure):
         ("x", C.c_void_p), ("ldx", C.c_int64),
         ("w", C.c_void_p), ("ldw", C.c_int64),
         ("bias", C.c_void_p),
-        ("residual", C.c_void_p), ("ldr", C.c_int64),
+        ("residual", C.c_void_p), ("ldr", C.c_int64), ("residual_dtype", C.c_int32),
         ("y", C.c_void_p), ("ldy", C.c_int64),
         ("y_dtype", C.c_int32),
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
@@ -35,9 +35,9 @@ class GemmArgs(C.Structure):
 
 class LayerNormArgs(C.Structure):
     _fields_ = [
-        ("x", C.c_void_p), ("ldx", C.c_int64),
+        ("x", C.c_void_p), ("ldx", C.c_int64), ("x_dtype", C.c_int32),
         ("gamma", C.c_void_p), ("beta", C.c_void_p),
-        ("y", C.c_void_p), ("ldy", C.c_int64),
+        ("y", C.c_void_p), ("y_f32", C.c_void_p), ("ldy", C.c_int64), ("stats", C.c_void_p),
         ("rows", C.c_int32), ("cols", C.c_int32),
         ("eps", C.c_float),
     ]
@@ -46,7 +46,7 @@ class LayerNormArgs(C.Structure):
 class BertEmbedArgs(C.Structure):
     _fields_ = [
         ("ids", C.c_void_p), ("word", C.c_void_p), ("pos", C.c_void_p), ("type0", C.c_void_p),
-        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("y", C.c_void_p), ("err_flag", C.c_void_p),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("y", C.c_void_p), ("y_f32", C.c_void_p), ("err_flag", C.c_void_p),
         ("tokens", C.c_int32), ("seq_len", C.c_int32), ("hidden", C.c_int32), ("vocab", C.c_int32),
         ("eps", C.c_float),
     ]
@@ -70,6 +70,76 @@ class SegmentMeanArgs(C.Structure):
     ]
 
 
+class LabEmbedArgs(C.Structure):
+    _fields_ = [
+        ("lab", C.c_void_p), ("w_tok", C.c_void_p), ("b_tok", C.c_void_p), ("pos", C.c_void_p), ("y", C.c_void_p),
+        ("batch", C.c_int32), ("L", C.c_int32), ("hidden", C.c_int32),
+    ]
+
+
+class SeqMeanArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("out", C.c_void_p), ("batch", C.c_int32), ("L", C.c_int32), ("cols", C.c_int32)]
+
+
+class DemoAddArgs(C.Structure):
+    _fields_ = [
+        ("cls", C.c_void_p), ("ld_cls", C.c_int64), ("cls_dtype", C.c_int32),
+        ("ids", C.c_void_p * 4), ("table", C.c_void_p * 4), ("n_rows", C.c_int32 * 4),
+        ("out", C.c_void_p), ("batch", C.c_int32), ("hidden", C.c_int32),
+    ]
+
+
+class FusionFwdArgs(C.Structure):
+    _fields_ = [
+        ("emb", C.c_void_p * 3), ("wp_t", C.c_void_p), ("bp", C.c_void_p), ("w_mod", C.c_float * 3),
+        ("sig_w", C.c_void_p), ("w3_t", C.c_void_p), ("b3", C.c_void_p), ("w4", C.c_void_p), ("b4", C.c_void_p),
+        ("wc", C.c_void_p), ("bc", C.c_void_p), ("proj", C.c_void_p), ("gated", C.c_void_p),
+        ("pre_relu", C.c_void_p), ("logits", C.c_void_p), ("mod_logits", C.c_void_p), ("sig_out", C.c_void_p),
+        ("B", C.c_int32),
+    ]
+
+
+class LossStatsArgs(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p), ("labels", C.c_void_p), ("attr", C.c_void_p * 3), ("pos_weight", C.c_void_p),
+        ("stats", C.c_void_p), ("B", C.c_int32),
+    ]
+
+
+class LossFwdBwdArgs(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p), ("labels", C.c_void_p), ("attr", C.c_void_p * 3), ("pos_weight", C.c_void_p),
+        ("stats", C.c_void_p), ("sig_w", C.c_void_p), ("n_sig", C.c_int32),
+        ("lambda_edd", C.c_float), ("lambda_l1", C.c_float),
+        ("dlogits", C.c_void_p), ("loss_out", C.c_void_p), ("B", C.c_int32),
+    ]
+
+
+class EvalCountsArgs(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p), ("ld", C.c_int64), ("labels", C.c_void_p), ("attr", C.c_void_p * 3),
+        ("thr", C.c_double * 3), ("sweep", C.c_void_p), ("out", C.c_void_p),
+        ("N", C.c_int32), ("logits_are_probs", C.c_int32),
+    ]
+
+
+class RankCountsArgs(C.Structure):
+    _fields_ = [
+        ("scores", C.c_void_p), ("y", C.c_void_p), ("N", C.c_int32), ("i0", C.c_int32), ("i1", C.c_int32),
+        ("auroc2", C.c_void_p), ("ap_sum", C.c_void_p), ("npos_nneg", C.c_void_p),
+    ]
+
+
+class SigmoidProbsArgs(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p), ("ld", C.c_int64), ("labels", C.c_void_p), ("probs", C.c_void_p),
+        ("y8", C.c_void_p), ("N", C.c_int32),
+    ]
+
+
+LOSS_STATS_LEN = 104
+EVAL_COUNTS_LEN = 914
+
 # name -> args struct for every `int fame_<op>(const args*, void* ws, size_t ws_bytes, stream)` entry point
 OP_TABLE = {
     "fame_gemm_bias_act": GemmArgs,
@@ -77,8 +147,27 @@ OP_TABLE = {
     "fame_bert_embed": BertEmbedArgs,
     "fame_attn_fwd": AttnFwdArgs,
     "fame_segment_mean": SegmentMeanArgs,
+    "fame_lab_embed": LabEmbedArgs,
+    "fame_seq_mean": SeqMeanArgs,
+    "fame_demo_add": DemoAddArgs,
+    "fame_fusion_fwd": FusionFwdArgs,
+    "fame_loss_stats": LossStatsArgs,
+    "fame_loss_fwd_bwd": LossFwdBwdArgs,
+    "fame_eval_counts": EvalCountsArgs,
+    "fame_rank_counts": RankCountsArgs,
+    "fame_sigmoid_probs": SigmoidProbsArgs,
 }
-PLAIN_SYMBOLS = ["fame_strerror", "fame_last_cuda_error", "fame_abi_version", "fame_device_check", "fame_sm_count"]
+PLAIN_SYMBOLS = ["fame_strerror", "fame_last_cuda_error", "fame_abi_version", "fame_device_check", "fame_sm_count",
+                 "fame_rank_counts_workspace_bytes"]
+# C struct name -> ctypes mirror (tests compare sizeof() of both)
+STRUCT_NAMES = {
+    "fame_gemm_args": GemmArgs, "fame_layernorm_args": LayerNormArgs, "fame_bert_embed_args": BertEmbedArgs,
+    "fame_attn_fwd_args": AttnFwdArgs, "fame_segment_mean_args": SegmentMeanArgs,
+    "fame_lab_embed_args": LabEmbedArgs, "fame_seq_mean_args": SeqMeanArgs, "fame_demo_add_args": DemoAddArgs,
+    "fame_fusion_fwd_args": FusionFwdArgs, "fame_loss_stats_args": LossStatsArgs,
+    "fame_loss_fwd_bwd_args": LossFwdBwdArgs, "fame_eval_counts_args": EvalCountsArgs,
+    "fame_rank_counts_args": RankCountsArgs, "fame_sigmoid_probs_args": SigmoidProbsArgs,
+}
 
 _lib = None
 
@@ -99,6 +188,8 @@ def load() -> C.CDLL:
     for name in ("fame_last_cuda_error", "fame_abi_version", "fame_device_check", "fame_sm_count"):
         getattr(lib, name).restype = C.c_int
         getattr(lib, name).argtypes = []
+    lib.fame_rank_counts_workspace_bytes.restype = C.c_size_t
+    lib.fame_rank_counts_workspace_bytes.argtypes = [C.c_int32]
     for name, struct in OP_TABLE.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int

@@ -134,6 +134,37 @@ class BertModelB200(nn.Module):
 
     # ------------------------------------------------------------------------------------------ forward
     @torch.no_grad()
+    def encode_f32(self, input_ids, attention_mask=None):
+        """Last hidden state as f32 [batch*seq, hidden], computed with an fp32 residual stream: GEMM operands are
+        bf16 (tensor cores), but every residual add, LayerNorm input and LayerNorm output stays in fp32.  Meant for
+        the small-batch towers (the demographic encoder runs M = batch rows) where the extra bytes are free and the
+        bf16 rounding of the residual stream would otherwise dominate the error of the final logits."""
+        if not input_ids.is_cuda:
+            raise RuntimeError("BertModelB200 runs on a B200 only: move inputs to cuda (no CPU fallback)")
+        c = self.config
+        B, S = input_ids.shape
+        pk = self._pack()
+        eps = c.layer_norm_eps
+        H, nh = c.hidden_size, c.num_attention_heads
+        mask = (attention_mask != 0).to(torch.uint8).contiguous() if attention_mask is not None else None
+        e = pk["emb"]
+        x32 = torch.empty((B * S, H), device=input_ids.device, dtype=torch.float32)
+        xb = ops.bert_embed(input_ids.to(torch.int64), e["word"], e["pos"], e["type0"], e["g"], e["b"], eps, S,
+                            out_f32=x32)
+        for l in pk["layers"]:
+            if S == 1:
+                ctx = ops.gemm_bias_act(xb, l["wqkv"][2 * H:], l["bqkv"][2 * H:])
+            else:
+                qkv = ops.gemm_bias_act(xb, l["wqkv"], l["bqkv"])
+                ctx = ops.attn_fwd(qkv, B, S, nh, H // nh, key_mask=mask)
+            t = ops.gemm_bias_act(ctx, l["wo"], l["bo"], residual=x32, out_dtype=torch.float32)
+            xb, x32 = ops.layernorm(t, l["ln1"][0], l["ln1"][1], eps, want_f32=True)
+            h = ops.gemm_bias_act(xb, l["w1"], l["b1"], act=ops.ACT_GELU_ERF)
+            t = ops.gemm_bias_act(h, l["w2"], l["b2"], residual=x32, out_dtype=torch.float32)
+            xb, x32 = ops.layernorm(t, l["ln2"][0], l["ln2"][1], eps, want_f32=True)
+        return x32
+
+    @torch.no_grad()
     def encode(self, input_ids, attention_mask=None):
         """Last hidden state as bf16 [batch*seq, hidden] (row-major, sequence-major)."""
         if not input_ids.is_cuda:
@@ -151,8 +182,13 @@ class BertModelB200(nn.Module):
         e = pk["emb"]
         x = ops.bert_embed(input_ids.to(torch.int64), e["word"], e["pos"], e["type0"], e["g"], e["b"], eps, S)
         for l in pk["layers"]:
-            qkv = ops.gemm_bias_act(x, l["wqkv"], l["bqkv"])
-            ctx = ops.attn_fwd(qkv, B, S, nh, H // nh, key_mask=mask)
+            if S == 1:
+                # one key per sequence: softmax == 1 exactly, so the context is the value projection itself and
+                # Q / K never influence the output (the demographic encoder's shape, 10_FAME.py:199, 715-716)
+                ctx = ops.gemm_bias_act(x, l["wqkv"][2 * H:], l["bqkv"][2 * H:])
+            else:
+                qkv = ops.gemm_bias_act(x, l["wqkv"], l["bqkv"])
+                ctx = ops.attn_fwd(qkv, B, S, nh, H // nh, key_mask=mask)
             t = ops.gemm_bias_act(ctx, l["wo"], l["bo"], residual=x)
             x = ops.layernorm(t, l["ln1"][0], l["ln1"][1], eps, out=t)
             h = ops.gemm_bias_act(x, l["w1"], l["b1"], act=ops.ACT_GELU_ERF)

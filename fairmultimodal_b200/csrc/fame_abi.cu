@@ -9,6 +9,8 @@
 #include "attn_sm100.cuh"
 #include "attn_flash_sm100.cuh"
 #include "gemm_sm100.cuh"
+#include "heads.cuh"
+#include "metrics.cuh"
 #include "rowwise.cuh"
 
 // which kernel algo == 0 (auto) picks for head_dim 64, seq <= 512: 1 = full-row TMEM kernel, 0 = flash kernel
@@ -161,6 +163,7 @@ int fame_gemm_bias_act(const fame_gemm_args* a, void* /*workspace*/, size_t /*wo
     if (!aligned16(a->x) || !aligned16(a->w) || !aligned16(a->y)) return FAME_ERR_ALIGN;
     if (a->bias != nullptr && !aligned16(a->bias)) return FAME_ERR_ALIGN;
     if (a->residual != nullptr && (!aligned16(a->residual) || (a->ldr & 7) || a->ldr < a->N)) return FAME_ERR_ALIGN;
+    if (a->residual_dtype != FAME_DT_BF16 && a->residual_dtype != FAME_DT_F32) return FAME_ERR_SHAPE;
     DeviceInfo* d = nullptr;
     int rc = device_info(&d);
     if (rc != FAME_OK) return rc;
@@ -189,8 +192,9 @@ int fame_gemm_bias_act(const fame_gemm_args* a, void* /*workspace*/, size_t /*wo
     fame::GemmParams p;
     p.M = a->M; p.N = a->N; p.K = a->K;
     p.bias = a->bias;
-    p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+    p.residual = a->residual;
     p.ldr = a->ldr;
+    p.res_f32 = a->residual_dtype == FAME_DT_F32;
     p.y = a->y;
     p.ldy = a->ldy;
     p.act = a->act;
@@ -205,19 +209,26 @@ int fame_gemm_bias_act(const fame_gemm_args* a, void* /*workspace*/, size_t /*wo
 
 // ------------------------------------------------------------------------------------------------ K3
 int fame_layernorm(const fame_layernorm_args* a, void*, size_t, fame_stream_t stream) {
-    if (a == nullptr || a->x == nullptr || a->y == nullptr || a->gamma == nullptr || a->beta == nullptr)
-        return FAME_ERR_NULLPTR;
+    if (a == nullptr || a->x == nullptr || a->gamma == nullptr || a->beta == nullptr) return FAME_ERR_NULLPTR;
+    if (a->y == nullptr && a->y_f32 == nullptr) return FAME_ERR_NULLPTR;
     if (a->rows < 0 || a->cols <= 0 || (a->cols & 7) || a->cols > 1024) return FAME_ERR_SHAPE;
+    if (a->x_dtype != FAME_DT_BF16 && a->x_dtype != FAME_DT_F32) return FAME_ERR_SHAPE;
     if ((a->ldx & 7) || (a->ldy & 7) || a->ldx < a->cols || a->ldy < a->cols) return FAME_ERR_ALIGN;
-    if (!aligned16(a->x) || !aligned16(a->y) || !aligned16(a->gamma) || !aligned16(a->beta)) return FAME_ERR_ALIGN;
+    if (!aligned16(a->x) || !aligned16(a->gamma) || !aligned16(a->beta)) return FAME_ERR_ALIGN;
+    if ((a->y != nullptr && !aligned16(a->y)) || (a->y_f32 != nullptr && !aligned16(a->y_f32))) return FAME_ERR_ALIGN;
     DeviceInfo* d = nullptr;
     int rc = device_info(&d);
     if (rc != FAME_OK) return rc;
     if (a->rows == 0) return FAME_OK;
     const int grid = (a->rows + fame::kLnWarpsPerBlock - 1) / fame::kLnWarpsPerBlock;
-    fame::layernorm_bf16_kernel<<<grid, fame::kLnWarpsPerBlock * 32, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(a->x), a->ldx, a->gamma, a->beta,
-        reinterpret_cast<__nv_bfloat16*>(a->y), a->ldy, a->rows, a->cols, a->eps);
+    if (a->x_dtype == FAME_DT_F32)
+        fame::layernorm_kernel<true><<<grid, fame::kLnWarpsPerBlock * 32, 0, stream>>>(
+            a->x, a->ldx, a->gamma, a->beta, reinterpret_cast<__nv_bfloat16*>(a->y), a->y_f32, a->ldy,
+            reinterpret_cast<float2*>(a->stats), a->rows, a->cols, a->eps);
+    else
+        fame::layernorm_kernel<false><<<grid, fame::kLnWarpsPerBlock * 32, 0, stream>>>(
+            a->x, a->ldx, a->gamma, a->beta, reinterpret_cast<__nv_bfloat16*>(a->y), a->y_f32, a->ldy,
+            reinterpret_cast<float2*>(a->stats), a->rows, a->cols, a->eps);
     return launch_status();
 }
 
@@ -238,7 +249,8 @@ int fame_bert_embed(const fame_bert_embed_args* a, void*, size_t, fame_stream_t 
     const int grid = (a->tokens + fame::kLnWarpsPerBlock - 1) / fame::kLnWarpsPerBlock;
     fame::bert_embed_ln_kernel<<<grid, fame::kLnWarpsPerBlock * 32, 0, stream>>>(
         reinterpret_cast<const long long*>(a->ids), a->word, a->pos, a->type0, a->gamma, a->beta,
-        reinterpret_cast<__nv_bfloat16*>(a->y), a->err_flag, a->tokens, a->seq_len, a->hidden, a->vocab, a->eps);
+        reinterpret_cast<__nv_bfloat16*>(a->y), a->y_f32, a->err_flag, a->tokens, a->seq_len, a->hidden, a->vocab,
+        a->eps);
     return launch_status();
 }
 
@@ -307,6 +319,203 @@ int fame_segment_mean(const fame_segment_mean_args* a, void*, size_t, fame_strea
     else if (!bf && !mx) FAME_SEG(false, false);
     else FAME_SEG(false, true);
 #undef FAME_SEG
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------ K4b / K6 / K4c
+int fame_lab_embed(const fame_lab_embed_args* a, void*, size_t, fame_stream_t stream) {
+    if (a == nullptr || a->lab == nullptr || a->w_tok == nullptr || a->b_tok == nullptr || a->pos == nullptr ||
+        a->y == nullptr)
+        return FAME_ERR_NULLPTR;
+    if (a->batch < 0 || a->L <= 0 || a->hidden <= 0 || (a->hidden & 7)) return FAME_ERR_SHAPE;
+    if (!aligned16(a->w_tok) || !aligned16(a->b_tok) || !aligned16(a->pos) || !aligned16(a->y)) return FAME_ERR_ALIGN;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    const long long tokens = (long long)a->batch * a->L;
+    if (tokens == 0) return FAME_OK;
+    if (tokens > 0x7fffffffll) return FAME_ERR_SHAPE;
+    const int grid = (int)((tokens + fame::kLnWarpsPerBlock - 1) / fame::kLnWarpsPerBlock);
+    fame::lab_embed_kernel<<<grid, fame::kLnWarpsPerBlock * 32, 0, stream>>>(
+        a->lab, a->w_tok, a->b_tok, a->pos, reinterpret_cast<__nv_bfloat16*>(a->y), (int)tokens, a->L, a->hidden);
+    return launch_status();
+}
+
+int fame_seq_mean(const fame_seq_mean_args* a, void*, size_t, fame_stream_t stream) {
+    if (a == nullptr || a->x == nullptr || a->out == nullptr) return FAME_ERR_NULLPTR;
+    if (a->batch < 0 || a->L <= 0 || a->cols <= 0 || (a->cols & 7)) return FAME_ERR_SHAPE;
+    if (!aligned16(a->x) || !aligned16(a->out)) return FAME_ERR_ALIGN;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    if (a->batch == 0) return FAME_OK;
+    // enough blocks to cover the SMs twice; splitting L needs a zeroed output and float atomics
+    int splits = 1;
+    while (a->batch * splits < 2 * d->sm_count && splits * 8 <= a->L) splits *= 2;
+    if (splits > 1) {
+        cudaError_t e = cudaMemsetAsync(a->out, 0, sizeof(float) * (size_t)a->batch * a->cols, stream);
+        if (e != cudaSuccess) return cuda_fail(e);
+    }
+    fame::seq_mean_kernel<<<dim3(a->batch, splits), 128, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a->x), a->out, a->L, a->cols, splits);
+    return launch_status();
+}
+
+int fame_demo_add(const fame_demo_add_args* a, void*, size_t, fame_stream_t stream) {
+    if (a == nullptr || a->cls == nullptr || a->out == nullptr) return FAME_ERR_NULLPTR;
+    for (int k = 0; k < 4; ++k)
+        if (a->ids[k] == nullptr || a->table[k] == nullptr || a->n_rows[k] <= 0) return FAME_ERR_NULLPTR;
+    if (a->batch < 0 || a->hidden <= 0) return FAME_ERR_SHAPE;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    if (a->batch == 0) return FAME_OK;
+    if (a->cls_dtype != FAME_DT_BF16 && a->cls_dtype != FAME_DT_F32) return FAME_ERR_SHAPE;
+#define FAME_DEMO_ADD(F)                                                                                              \
+    fame::demo_add_kernel<F><<<a->batch, 128, 0, stream>>>(                                                           \
+        a->cls, a->ld_cls, reinterpret_cast<const long long*>(a->ids[0]), reinterpret_cast<const long long*>(a->ids[1]), \
+        reinterpret_cast<const long long*>(a->ids[2]), reinterpret_cast<const long long*>(a->ids[3]), a->table[0],    \
+        a->table[1], a->table[2], a->table[3], a->n_rows[0], a->n_rows[1], a->n_rows[2], a->n_rows[3], a->out, a->hidden)
+    if (a->cls_dtype == FAME_DT_F32) FAME_DEMO_ADD(true);
+    else FAME_DEMO_ADD(false);
+#undef FAME_DEMO_ADD
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------ K7
+int fame_fusion_fwd(const fame_fusion_fwd_args* a, void*, size_t, fame_stream_t stream) {
+    if (a == nullptr || a->logits == nullptr || a->wp_t == nullptr || a->bp == nullptr || a->sig_w == nullptr ||
+        a->w3_t == nullptr || a->b3 == nullptr || a->w4 == nullptr || a->b4 == nullptr)
+        return FAME_ERR_NULLPTR;
+    for (int m = 0; m < 3; ++m)
+        if (a->emb[m] == nullptr || !aligned16(a->emb[m])) return a->emb[m] == nullptr ? FAME_ERR_NULLPTR : FAME_ERR_ALIGN;
+    if (a->mod_logits != nullptr && (a->wc == nullptr || a->bc == nullptr)) return FAME_ERR_NULLPTR;
+    if (a->B < 0) return FAME_ERR_SHAPE;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    if (a->B == 0) return FAME_OK;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(fame::fusion_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             fame::kFuSmemBytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+        attr_set[dev] = true;
+    }
+    fame::FusionParams p;
+    for (int m = 0; m < 3; ++m) { p.emb[m] = a->emb[m]; p.w_mod[m] = a->w_mod[m]; }
+    p.wp_t = a->wp_t; p.bp = a->bp; p.sig_w = a->sig_w; p.w3_t = a->w3_t; p.b3 = a->b3; p.w4 = a->w4; p.b4 = a->b4;
+    p.wc = a->wc; p.bc = a->bc; p.proj = a->proj; p.gated = a->gated; p.pre_relu = a->pre_relu;
+    p.logits = a->logits; p.mod_logits = a->mod_logits; p.sig_out = a->sig_out; p.B = a->B;
+    const int grid = (a->B + fame::kFuRows - 1) / fame::kFuRows;
+    fame::fusion_fwd_kernel<<<grid, fame::kFuThreads, fame::kFuSmemBytes, stream>>>(p);
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------ K8
+int fame_loss_stats(const fame_loss_stats_args* a, void*, size_t, fame_stream_t stream) {
+    if (a == nullptr || a->logits == nullptr || a->labels == nullptr || a->pos_weight == nullptr ||
+        a->stats == nullptr || a->attr[0] == nullptr || a->attr[1] == nullptr || a->attr[2] == nullptr)
+        return FAME_ERR_NULLPTR;
+    if (a->B < 0) return FAME_ERR_SHAPE;
+    static_assert(FAME_LOSS_STATS_LEN == fame::kLossStatsLen, "header / kernel stats layout mismatch");
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    if (a->B == 0) return FAME_OK;
+    fame::LossStatsParams p;
+    p.logits = a->logits; p.labels = a->labels; p.pos_weight = a->pos_weight;
+    for (int k = 0; k < 3; ++k) p.attr[k] = reinterpret_cast<const long long*>(a->attr[k]);
+    p.stats = reinterpret_cast<long long*>(a->stats);
+    p.B = a->B;
+    int grid = (a->B + 255) / 256;
+    if (grid > 2 * d->sm_count) grid = 2 * d->sm_count;
+    fame::loss_stats_kernel<<<grid, 256, 0, stream>>>(p);
+    return launch_status();
+}
+
+int fame_loss_fwd_bwd(const fame_loss_fwd_bwd_args* a, void*, size_t, fame_stream_t stream) {
+    if (a == nullptr || a->stats == nullptr || a->pos_weight == nullptr) return FAME_ERR_NULLPTR;
+    if (a->dlogits != nullptr && (a->logits == nullptr || a->labels == nullptr || a->attr[0] == nullptr ||
+                                  a->attr[1] == nullptr || a->attr[2] == nullptr))
+        return FAME_ERR_NULLPTR;
+    if (a->B < 0 || a->n_sig < 0) return FAME_ERR_SHAPE;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    fame::LossGradParams p;
+    p.logits = a->logits; p.labels = a->labels; p.pos_weight = a->pos_weight;
+    for (int k = 0; k < 3; ++k) p.attr[k] = reinterpret_cast<const long long*>(a->attr[k]);
+    p.stats = reinterpret_cast<const long long*>(a->stats);
+    p.sig_w = a->sig_w; p.n_sig = a->n_sig; p.lambda_edd = a->lambda_edd; p.lambda_l1 = a->lambda_l1;
+    p.dlogits = a->dlogits; p.loss_out = a->loss_out; p.B = a->B;
+    int grid = (a->B + 255) / 256;
+    if (grid < 1) grid = 1;
+    if (grid > 2 * d->sm_count) grid = 2 * d->sm_count;
+    fame::loss_fwd_bwd_kernel<<<grid, 256, 0, stream>>>(p);
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------ K10
+int fame_eval_counts(const fame_eval_counts_args* a, void*, size_t, fame_stream_t stream) {
+    if (a == nullptr || a->logits == nullptr || a->labels == nullptr || a->out == nullptr || a->attr[0] == nullptr ||
+        a->attr[1] == nullptr || a->attr[2] == nullptr)
+        return FAME_ERR_NULLPTR;
+    if (a->N < 0 || a->ld < 3) return FAME_ERR_SHAPE;
+    static_assert(FAME_EVAL_COUNTS_LEN == fame::kEvLen, "header / kernel count layout mismatch");
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    if (a->N == 0) return FAME_OK;
+    fame::EvalCountsParams p;
+    p.logits = a->logits; p.ld = a->ld; p.labels = a->labels;
+    for (int k = 0; k < 3; ++k) { p.attr[k] = reinterpret_cast<const long long*>(a->attr[k]); p.thr[k] = a->thr[k]; }
+    p.sweep = a->sweep;
+    p.out = reinterpret_cast<unsigned long long*>(a->out);
+    p.N = a->N;
+    p.logits_are_probs = a->logits_are_probs;
+    int grid = (a->N + 255) / 256;
+    if (grid > 4 * d->sm_count) grid = 4 * d->sm_count;
+    fame::eval_counts_kernel<<<grid, 256, 0, stream>>>(p);
+    return launch_status();
+}
+
+size_t fame_rank_counts_workspace_bytes(int32_t n_i) { return sizeof(double) * (size_t)((n_i + 255) / 256 + 1); }
+
+int fame_rank_counts(const fame_rank_counts_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream) {
+    if (a == nullptr || a->scores == nullptr || a->y == nullptr || a->auroc2 == nullptr || a->ap_sum == nullptr ||
+        a->npos_nneg == nullptr)
+        return FAME_ERR_NULLPTR;
+    if (a->N < 0 || a->i0 < 0 || a->i1 < a->i0 || a->i1 > a->N) return FAME_ERR_SHAPE;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    const int n_i = a->i1 - a->i0;
+    if (n_i == 0) return FAME_OK;
+    if (workspace == nullptr) return FAME_ERR_NULLPTR;
+    if (workspace_bytes < fame_rank_counts_workspace_bytes(n_i)) return FAME_ERR_WORKSPACE;
+    fame::RankParams p;
+    p.scores = a->scores; p.y = a->y; p.N = a->N; p.i0 = a->i0; p.i1 = a->i1;
+    p.auroc2 = reinterpret_cast<unsigned long long*>(a->auroc2);
+    p.ap_partial = reinterpret_cast<double*>(workspace);
+    p.npos_nneg = reinterpret_cast<unsigned long long*>(a->npos_nneg);
+    const int grid = (n_i + 255) / 256;
+    fame::rank_counts_kernel<<<grid, 256, 0, stream>>>(p);
+    fame::sum_partials_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<const double*>(workspace), grid, a->ap_sum);
+    return launch_status();
+}
+
+int fame_sigmoid_probs(const fame_sigmoid_probs_args* a, void*, size_t, fame_stream_t stream) {
+    if (a == nullptr || a->logits == nullptr || a->probs == nullptr) return FAME_ERR_NULLPTR;
+    if (a->y8 != nullptr && a->labels == nullptr) return FAME_ERR_NULLPTR;
+    if (a->N < 0 || a->ld < 3) return FAME_ERR_SHAPE;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    if (a->N == 0) return FAME_OK;
+    fame::sigmoid_probs_kernel<<<(a->N + 255) / 256, 256, 0, stream>>>(a->logits, a->ld, a->labels, a->probs, a->y8, a->N);
     return launch_status();
 }
 

@@ -35,8 +35,9 @@ enum { kActNone = 0, kActGelu = 1, kActRelu = 2 };
 struct GemmParams {
     int M, N, K;
     const float* bias;              // [N] or nullptr
-    const __nv_bfloat16* residual;  // [M, ldr] or nullptr
+    const void* residual;           // bf16 or f32 [M, ldr] or nullptr
     long long ldr;
+    int res_f32;
     void* y;                        // bf16 or f32 [M, ldy]
     long long ldy;
     int act;
@@ -221,17 +222,29 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.0f);
                 }
                 if (p.residual != nullptr && row_ok) {
-                    const __nv_bfloat16* rp = p.residual + (long long)row * p.ldr + col0;
+                    if (p.res_f32) {
+                        const float* rp = reinterpret_cast<const float*>(p.residual) + (long long)row * p.ldr + col0;
 #pragma unroll
-                    for (int j = 0; j < 64; j += 8) {
-                        if (col0 + j < p.N) {
-                            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + j));
-                            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                        for (int j = 0; j < 64; j += 4) {
+                            if (col0 + j < p.N) {
+                                const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + j));
+                                v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
+                            }
+                        }
+                    } else {
+                        const __nv_bfloat16* rp =
+                            reinterpret_cast<const __nv_bfloat16*>(p.residual) + (long long)row * p.ldr + col0;
 #pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const float2 f = __bfloat1622float2(h2[t]);
-                                v[j + 2 * t] += f.x;
-                                v[j + 2 * t + 1] += f.y;
+                        for (int j = 0; j < 64; j += 8) {
+                            if (col0 + j < p.N) {
+                                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + j));
+                                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    const float2 f = __bfloat1622float2(h2[t]);
+                                    v[j + 2 * t] += f.x;
+                                    v[j + 2 * t + 1] += f.y;
+                                }
                             }
                         }
                     }

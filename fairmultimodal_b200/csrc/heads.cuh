@@ -1,0 +1,383 @@
+// K7 fusion head forward, K8 joint BCE + LEDDI loss (statistics pass + loss / gradient pass).  fp32 CUDA-core
+// kernels: these stages are a few MFLOP per patient and bound by memory / latency, not by the tensor pipe.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rowwise.cuh"
+
+namespace fame {
+
+// ================================================================================================ K7 fusion fwd
+// MultimodalTransformer_EDDI_Sigmoid.forward after the encoders (10_FAME.py:276-308):
+//   proj_m  = relu(W_m e_m + b_m)                      m in {demo, lab, text},  768 -> 256
+//   gated   = [w_d proj_d | w_l proj_l | w_t proj_t] * sigmoid(sig_weights)
+//   pre     = W3 gated + b3 (768 -> 512);  logits = W4 relu(pre) + b4 (512 -> 3)      [dropout: identity here]
+//   modality_logits_m = Wc_m proj_m + bc_m (256 -> 3)
+// One CTA = 8 patients; inputs staged in shared memory, weights (pre-transposed, L2 resident) streamed coalesced.
+constexpr int kFuRows = 8;
+constexpr int kFuThreads = 256;
+constexpr int kFuSmemBytes = (3 * kFuRows * 768 + kFuRows * 768 + kFuRows * 512) * 4;
+
+struct FusionParams {
+    const float* emb[3];   // demo, lab, text  [B,768]
+    const float* wp_t;     // [3][768][256]  projector weights, transposed
+    const float* bp;       // [3][256]
+    float w_mod[3];        // EDDI modality weights (the "mortality" entry, 10_FAME.py:283-285)
+    const float* sig_w;    // [768]
+    const float* w3_t;     // [768][512]  fusion_mlp.0 weight, transposed
+    const float* b3;       // [512]
+    const float* w4;       // [3][512]    fusion_mlp.3 weight
+    const float* b4;       // [3]
+    const float* wc;       // [3][3][256] classifier_{demo,lab,text}.weight
+    const float* bc;       // [3][3]
+    float* proj;           // [B,768] relu outputs (unweighted), nullable
+    float* gated;          // [B,768] nullable
+    float* pre_relu;       // [B,512] nullable
+    float* logits;         // [B,3]
+    float* mod_logits;     // [3][B][3] nullable
+    float* sig_out;        // [768] sigmoid(sig_w), nullable
+    int B;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__global__ void __launch_bounds__(kFuThreads)
+fusion_fwd_kernel(const FusionParams p) {
+    extern __shared__ float fsm[];
+    float* xin = fsm;                          // [3][8][768]; after phase 1 xin[m][r][0..255] holds proj_m
+    float* g = xin + 3 * kFuRows * 768;        // [8][768] gated
+    float* hid = g + kFuRows * 768;            // [8][512] relu(pre)
+    const int t = threadIdx.x;
+    const int row0 = blockIdx.x * kFuRows;
+    const int nrow = min(kFuRows, p.B - row0);
+
+    for (int m = 0; m < 3; ++m)
+        for (int i = t; i < kFuRows * 192; i += kFuThreads) {
+            const int r = i / 192, c4 = i % 192;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nrow) v = __ldg(reinterpret_cast<const float4*>(p.emb[m] + (long long)(row0 + r) * 768) + c4);
+            reinterpret_cast<float4*>(xin + (m * kFuRows + r) * 768)[c4] = v;
+        }
+    if (blockIdx.x == 0 && p.sig_out != nullptr)
+        for (int i = t; i < 768; i += kFuThreads) p.sig_out[i] = 1.0f / (1.0f + expf(-p.sig_w[i]));
+    __syncthreads();
+
+    // ---- phase 1: projectors; thread t owns output column t of each modality for all 8 rows
+    float pr[3][kFuRows];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        float acc[kFuRows];
+#pragma unroll
+        for (int r = 0; r < kFuRows; ++r) acc[r] = 0.f;
+        const float* w = p.wp_t + (long long)m * 768 * 256 + t;
+        const float* xm = xin + m * kFuRows * 768;
+        for (int k = 0; k < 768; k += 4) {
+            const float w0 = __ldg(w + (k + 0) * 256), w1 = __ldg(w + (k + 1) * 256), w2 = __ldg(w + (k + 2) * 256),
+                        w3 = __ldg(w + (k + 3) * 256);
+#pragma unroll
+            for (int r = 0; r < kFuRows; ++r) {
+                const float4 x = *reinterpret_cast<const float4*>(xm + r * 768 + k);
+                acc[r] = fmaf(x.x, w0, acc[r]);
+                acc[r] = fmaf(x.y, w1, acc[r]);
+                acc[r] = fmaf(x.z, w2, acc[r]);
+                acc[r] = fmaf(x.w, w3, acc[r]);
+            }
+        }
+        const float b = __ldg(p.bp + m * 256 + t);
+#pragma unroll
+        for (int r = 0; r < kFuRows; ++r) pr[m][r] = fmaxf(acc[r] + b, 0.f);
+    }
+    __syncthreads();  // everyone is done reading xin
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        const float sg = 1.0f / (1.0f + expf(-__ldg(p.sig_w + m * 256 + t)));
+#pragma unroll
+        for (int r = 0; r < kFuRows; ++r) {
+            xin[(m * kFuRows + r) * 768 + t] = pr[m][r];
+            const float gv = (p.w_mod[m] * pr[m][r]) * sg;
+            g[r * 768 + m * 256 + t] = gv;
+            if (r < nrow) {
+                if (p.proj != nullptr) p.proj[(long long)(row0 + r) * 768 + m * 256 + t] = pr[m][r];
+                if (p.gated != nullptr) p.gated[(long long)(row0 + r) * 768 + m * 256 + t] = gv;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: hidden layer 768 -> 512; thread t owns columns t and t + 256
+    {
+        float a0[kFuRows], a1[kFuRows];
+#pragma unroll
+        for (int r = 0; r < kFuRows; ++r) a0[r] = a1[r] = 0.f;
+        const float* w = p.w3_t + t;
+        for (int k = 0; k < 768; k += 4) {
+            float wa[4], wb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                wa[u] = __ldg(w + (k + u) * 512);
+                wb[u] = __ldg(w + (k + u) * 512 + 256);
+            }
+#pragma unroll
+            for (int r = 0; r < kFuRows; ++r) {
+                const float4 x = *reinterpret_cast<const float4*>(g + r * 768 + k);
+                a0[r] = fmaf(x.x, wa[0], a0[r]); a0[r] = fmaf(x.y, wa[1], a0[r]);
+                a0[r] = fmaf(x.z, wa[2], a0[r]); a0[r] = fmaf(x.w, wa[3], a0[r]);
+                a1[r] = fmaf(x.x, wb[0], a1[r]); a1[r] = fmaf(x.y, wb[1], a1[r]);
+                a1[r] = fmaf(x.z, wb[2], a1[r]); a1[r] = fmaf(x.w, wb[3], a1[r]);
+            }
+        }
+        const float b0 = __ldg(p.b3 + t), b1 = __ldg(p.b3 + t + 256);
+#pragma unroll
+        for (int r = 0; r < kFuRows; ++r) {
+            const float v0 = a0[r] + b0, v1 = a1[r] + b1;
+            hid[r * 512 + t] = fmaxf(v0, 0.f);
+            hid[r * 512 + t + 256] = fmaxf(v1, 0.f);
+            if (r < nrow && p.pre_relu != nullptr) {
+                p.pre_relu[(long long)(row0 + r) * 512 + t] = v0;
+                p.pre_relu[(long long)(row0 + r) * 512 + t + 256] = v1;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: 3 fused logits and 9 modality logits per row; warp w owns row w
+    const int warp = t >> 5, lane = t & 31;
+    if (warp < nrow) {
+        const int r = warp;
+        float l[3] = {0.f, 0.f, 0.f};
+        for (int k = lane; k < 512; k += 32) {
+            const float h = hid[r * 512 + k];
+#pragma unroll
+            for (int o = 0; o < 3; ++o) l[o] = fmaf(h, __ldg(p.w4 + o * 512 + k), l[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            l[o] = warp_sum(l[o]);
+            if (lane == 0) p.logits[(long long)(row0 + r) * 3 + o] = l[o] + __ldg(p.b4 + o);
+        }
+        if (p.mod_logits != nullptr) {
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                float c[3] = {0.f, 0.f, 0.f};
+                for (int k = lane; k < 256; k += 32) {
+                    const float x = xin[(m * kFuRows + r) * 768 + k];
+#pragma unroll
+                    for (int o = 0; o < 3; ++o) c[o] = fmaf(x, __ldg(p.wc + (m * 3 + o) * 256 + k), c[o]);
+                }
+#pragma unroll
+                for (int o = 0; o < 3; ++o) {
+                    c[o] = warp_sum(c[o]);
+                    if (lane == 0)
+                        p.mod_logits[((long long)m * p.B + row0 + r) * 3 + o] = c[o] + __ldg(p.bc + m * 3 + o);
+                }
+            }
+        }
+    }
+}
+
+// ================================================================================================ K8 loss
+// Statistics layout (int64, identical on every rank so that one SUM all-reduce makes them global):
+//   [0..2]   sum_b |sigmoid(z)-y|  per outcome            fixed point 2^32
+//   [3..5]   sum_b bce term        per outcome            fixed point 2^24
+//   [6..77]  group error sums [outcome][attr][code 0..7]  fixed point 2^32
+//   [78..101] group counts [attr][code]                   integer
+//   [102]    patients                                     integer
+//   [103]    error flag (an attribute code outside 0..7)
+constexpr int kLossStatsLen = 104;
+constexpr int kLossSlots = 8;
+constexpr double kFixErr = 4294967296.0;   // 2^32
+constexpr double kFixBce = 16777216.0;     // 2^24
+
+struct LossStatsParams {
+    const float* logits;     // [B,3]
+    const float* labels;     // [B,3]
+    const long long* attr[3];  // age, ethnicity, insurance  [B]
+    const float* pos_weight; // [3]
+    long long* stats;        // [kLossStatsLen], zero-initialised by the caller's memset (done by the host wrapper)
+    int B;
+};
+
+// Each thread walks patients grid-stride with private accumulators (predicated adds over the 8 code slots, no
+// dynamic register indexing), then a warp-shuffle tree and one shared-memory pass per block; the block total is
+// converted to fixed point and added with integer atomics, so the result is independent of block order.
+__global__ void __launch_bounds__(256)
+loss_stats_kernel(const LossStatsParams p) {
+    float e_sum[3] = {0.f, 0.f, 0.f}, b_sum[3] = {0.f, 0.f, 0.f};
+    float g_sum[3][3][kLossSlots];
+    int g_cnt[3][kLossSlots];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int s = 0; s < kLossSlots; ++s) g_sum[i][a][s] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int s = 0; s < kLossSlots; ++s) g_cnt[a][s] = 0;
+    int n_local = 0, bad = 0;
+    float pw[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) pw[i] = __ldg(p.pos_weight + i);
+
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < p.B; b += gridDim.x * blockDim.x) {
+        float e[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float z = __ldg(p.logits + 3ll * b + i), y = __ldg(p.labels + 3ll * b + i);
+            const float pr = 1.0f / (1.0f + expf(-z));
+            e[i] = fabsf(pr - y);
+            // softplus(-z) = -log sigmoid(z), stable:  max(-z, 0) + log1p(exp(-|z|))
+            const float sp = fmaxf(-z, 0.f) + log1pf(expf(-fabsf(z)));
+            b_sum[i] += pw[i] * y * sp + (1.0f - y) * (sp + z);
+            e_sum[i] += e[i];
+        }
+        ++n_local;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const long long c = __ldg(p.attr[a] + b);
+            bad |= (c < 0 || c >= kLossSlots);
+#pragma unroll
+            for (int s = 0; s < kLossSlots; ++s) {
+                const bool hit = (c == s);
+                g_cnt[a][s] += hit;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) g_sum[i][a][s] += hit ? e[i] : 0.f;
+            }
+        }
+    }
+
+    __shared__ double sh[kLossStatsLen];
+    for (int i = threadIdx.x; i < kLossStatsLen; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    auto flush = [&](int idx, float v) {
+        v = warp_sum(v);
+        if (lane == 0 && v != 0.f) atomicAdd(&sh[idx], (double)v);
+    };
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        flush(i, e_sum[i]);
+        flush(3 + i, b_sum[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int s = 0; s < kLossSlots; ++s) flush(6 + (i * 3 + a) * kLossSlots + s, g_sum[i][a][s]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int s = 0; s < kLossSlots; ++s) flush(78 + a * kLossSlots + s, (float)g_cnt[a][s]);
+    flush(102, (float)n_local);
+    flush(103, (float)bad);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kLossStatsLen; i += blockDim.x) {
+        const double v = sh[i];
+        if (v == 0.0) continue;
+        const double scale = i < 3 ? kFixErr : (i < 6 ? kFixBce : (i < 78 ? kFixErr : 1.0));
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.stats + i), (unsigned long long)llrint(v * scale));
+    }
+}
+
+struct LossGradParams {
+    const float* logits;
+    const float* labels;
+    const long long* attr[3];
+    const float* pos_weight;
+    const long long* stats;   // GLOBAL statistics (after the all-reduce when data parallel)
+    const float* sig_w;       // [n_sig] for the L1 term, nullable
+    int n_sig;
+    float lambda_edd, lambda_l1;
+    float* dlogits;           // [B,3]  d(total)/d(logits) for the LOCAL patients, nullable
+    float* loss_out;          // [4]: total, bce, leddi, l1   (written by block 0)
+    int B;
+};
+
+// loss = BCE + lambda_edd * 10 * LEDDI + lambda_l1 * |sig_w|_1   (10_FAME.py:420-444), with
+// LEDDI = mean_{i,a} sqrt( mean_{g present} (e_{i,a,g} - e_i)^2 + 1e-8 ).  Gradient flows through every mean.
+__global__ void __launch_bounds__(256)
+loss_fwd_bwd_kernel(const LossGradParams p) {
+    __shared__ float coef[3][3][kLossSlots];  // d R_{i,a} / d e_b for a member of group g (excluding the common term)
+    __shared__ float cst[3][3];               // common term of d R_{i,a} / d e_b
+    __shared__ float s_leddi, s_bce, s_l1;
+    const double Bt = (double)p.stats[102];
+    if (threadIdx.x < 9) {
+        const int i = threadIdx.x / 3, a = threadIdx.x % 3;
+        const double ebar = (double)p.stats[i] / kFixErr / Bt;
+        double dev[kLossSlots], ss = 0.0, sd = 0.0;
+        int ng = 0;
+        for (int s = 0; s < kLossSlots; ++s) {
+            const long long c = p.stats[78 + a * kLossSlots + s];
+            dev[s] = 0.0;
+            if (c > 0) {
+                dev[s] = (double)p.stats[6 + (i * 3 + a) * kLossSlots + s] / kFixErr / (double)c - ebar;
+                ss += dev[s] * dev[s];
+                sd += dev[s];
+                ++ng;
+            }
+        }
+        const double R = sqrt(ss / (double)ng + 1e-8);
+        for (int s = 0; s < kLossSlots; ++s) {
+            const long long c = p.stats[78 + a * kLossSlots + s];
+            coef[i][a][s] = c > 0 ? (float)(dev[s] / ((double)c * R * (double)ng)) : 0.f;
+        }
+        cst[i][a] = (float)(-sd / (Bt * R * (double)ng));
+        // reuse coef slot storage is not possible for R itself; keep it in a register and reduce below
+        double r9 = R;
+        // 9 threads of warp 0: sum R over (i,a)
+        unsigned m9 = 0x1ffu;
+        for (int o = 8; o > 0; o >>= 1) {
+            const double other = __shfl_down_sync(m9, r9, o);
+            if (threadIdx.x + o < 9) r9 += other;
+        }
+        if (threadIdx.x == 0) {
+            s_leddi = (float)(r9 / 9.0);
+            s_bce = (float)(((double)p.stats[3] + (double)p.stats[4] + (double)p.stats[5]) / kFixBce / (3.0 * Bt));
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 64) {
+        float l1 = 0.f;
+        if (p.sig_w != nullptr)
+            for (int k = threadIdx.x - 32; k < p.n_sig; k += 32) l1 += fabsf(p.sig_w[k]);
+        l1 = warp_sum(l1);
+        if (threadIdx.x == 32) s_l1 = l1;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.loss_out != nullptr) {
+        const float l1 = p.lambda_l1 * s_l1;
+        p.loss_out[0] = s_bce + p.lambda_edd * (10.0f * s_leddi) + l1;
+        p.loss_out[1] = s_bce;
+        p.loss_out[2] = s_leddi;
+        p.loss_out[3] = l1;
+    }
+    if (p.dlogits == nullptr) return;
+    const float inv3B = (float)(1.0 / (3.0 * Bt));
+    const float k_edd = p.lambda_edd * 10.0f / 9.0f;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < p.B; b += gridDim.x * blockDim.x) {
+        int code[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const long long c = __ldg(p.attr[a] + b);
+            code[a] = (int)(c < 0 ? 0 : (c >= kLossSlots ? kLossSlots - 1 : c));
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float z = __ldg(p.logits + 3ll * b + i), y = __ldg(p.labels + 3ll * b + i);
+            const float pr = 1.0f / (1.0f + expf(-z));
+            const float pw = __ldg(p.pos_weight + i);
+            float gz = (-pw * y * (1.0f - pr) + (1.0f - y) * pr) * inv3B;
+            float dRde = 0.f;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) dRde += coef[i][a][code[a]] + cst[i][a];
+            const float d = pr - y;
+            const float sgn = d > 0.f ? 1.0f : (d < 0.f ? -1.0f : 0.f);
+            gz += k_edd * dRde * sgn * pr * (1.0f - pr);
+            p.dlogits[3ll * b + i] = gz;
+        }
+    }
+}
+
+}  // namespace fame

@@ -1,0 +1,251 @@
+// K10 evaluation metric kernels: thresholded confusion counts per (outcome, sensitive attribute, subgroup) for
+// EDDI / Equalized Odds, the 101-threshold F1 sweep histogram, and exact tie-aware AUROC / average-precision rank
+// counts.  Replaces the numpy / sklearn passes of compute_eddi (10_FAME.py:54-82), calculate_tpr_and_fpr (84-97),
+// calibrate_thresholds (470-481) and evaluate_model_multi (514-540).  All outputs are INTEGER counts (bit-exact,
+// order independent, summable across ranks); the few float64 divisions that turn counts into EDDI / EO / F1 / AUROC
+// happen on the host exactly as the reference does them.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rowwise.cuh"
+
+namespace fame {
+
+// float32 sigmoid evaluated the way torch.sigmoid does on float32 tensors: 1 / (1 + exp(-z)) with every step
+// rounded to float32 (exp correctly rounded via a float64 evaluation, IEEE add and divide, no FMA contraction).
+// The reference thresholds and ranks these float32 probabilities (10_FAME.py:471-476, 516-518), so both the strict
+// `>` decisions and the tie structure in the saturated tails (1 + e rounds to 1 for e < 2^-24) follow this form.
+__device__ __forceinline__ float sigmoid_f32_exact(float z) {
+    const float e = (float)exp(-(double)z);
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+}
+
+constexpr int kEvSlots = 8;                               // subgroup codes 0..7
+constexpr int kEvConfLen = 3 * 3 * kEvSlots * 4;          // [outcome][attr][code][TP,FN,FP,TN]
+constexpr int kEvTotLen = 3 * 4;                          // [outcome][TP,FN,FP,TN]
+constexpr int kEvHistLen = 3 * 2 * 102;                   // [outcome][label][#thresholds strictly below p]
+constexpr int kEvLen = kEvConfLen + kEvTotLen + kEvHistLen + 2;  // + patients + error flag
+
+struct EvalCountsParams {
+    const float* logits;        // [N, ld] (3 outcomes used)
+    long long ld;
+    const float* labels;        // [N,3]
+    const long long* attr[3];   // [N] each
+    double thr[3];              // decision threshold per outcome; prediction = (double)p_f32 > thr
+    const double* sweep;        // [101] ascending thresholds for the F1 sweep, nullable (histogram skipped)
+    unsigned long long* out;    // [kEvLen], zero-initialised
+    int N;
+    int logits_are_probs;       // 1: `logits` already holds float32 probabilities / 0-1 predictions
+};
+
+// Per-thread counters are packed four 8-bit cells (TP, FN, FP, TN) per register and flushed every 255 patients.
+__global__ void __launch_bounds__(256)
+eval_counts_kernel(const EvalCountsParams p) {
+    __shared__ unsigned int sh[kEvLen];
+    for (int i = threadIdx.x; i < kEvLen; i += blockDim.x) sh[i] = 0u;
+    __shared__ double sweep_s[101];
+    if (p.sweep != nullptr)
+        for (int i = threadIdx.x; i < 101; i += blockDim.x) sweep_s[i] = p.sweep[i];
+    __syncthreads();
+
+    unsigned int cnt[3][3][kEvSlots];
+    unsigned int tot[3];
+    const int lane = threadIdx.x & 31;
+    auto reset = [&]() {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            tot[i] = 0u;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int s = 0; s < kEvSlots; ++s) cnt[i][a][s] = 0u;
+        }
+    };
+    auto flush = [&]() {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const unsigned v = __reduce_add_sync(0xffffffffu, (tot[i] >> (8 * c)) & 0xffu);
+                if (lane == 0 && v) atomicAdd(&sh[kEvConfLen + i * 4 + c], v);
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int s = 0; s < kEvSlots; ++s)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const unsigned v = __reduce_add_sync(0xffffffffu, (cnt[i][a][s] >> (8 * c)) & 0xffu);
+                        if (lane == 0 && v) atomicAdd(&sh[((i * 3 + a) * kEvSlots + s) * 4 + c], v);
+                    }
+        }
+        reset();
+    };
+    reset();
+    int since = 0, n_local = 0, bad = 0;
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;; b += (long long)gridDim.x * blockDim.x) {
+        const bool live = b < p.N;
+        // the flush is warp-collective: all lanes must reach it together
+        if (!__any_sync(0xffffffffu, live)) break;
+        if (live) {
+            int code[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const long long c = __ldg(p.attr[a] + b);
+                bad |= (c < 0 || c >= kEvSlots);
+                code[a] = (int)c;
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float z = __ldg(p.logits + b * p.ld + i);
+                const float pr = p.logits_are_probs ? z : sigmoid_f32_exact(z);
+                const int y = __ldg(p.labels + 3 * b + i) != 0.f;
+                const int pred = (double)pr > p.thr[i];
+                const unsigned inc = 1u << (8 * ((1 - y) * 2 + (1 - pred)));  // cell: TP=0, FN=1, FP=2, TN=3
+                tot[i] += inc;
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int s = 0; s < kEvSlots; ++s) cnt[i][a][s] += (code[a] == s) ? inc : 0u;
+                if (p.sweep != nullptr) {
+                    // kk = number of sweep thresholds strictly below p  (p > t_k  <=>  k < kk); thresholds ascend
+                    int lo = 0, hi = 101;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if ((double)pr > sweep_s[mid]) lo = mid + 1; else hi = mid;
+                    }
+                    atomicAdd(&sh[kEvConfLen + kEvTotLen + (i * 2 + y) * 102 + lo], 1u);
+                }
+            }
+            ++n_local;
+        }
+        if (++since == 255) {
+            flush();
+            since = 0;
+        }
+    }
+    flush();
+    {
+        const unsigned v = __reduce_add_sync(0xffffffffu, (unsigned)n_local);
+        const unsigned e = __reduce_or_sync(0xffffffffu, (unsigned)bad);
+        if (lane == 0) {
+            atomicAdd(&sh[kEvLen - 2], v);
+            if (e) atomicOr(&sh[kEvLen - 1], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kEvLen; i += blockDim.x)
+        if (sh[i]) atomicAdd(p.out + i, (unsigned long long)sh[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ rank counts
+// For every sample i in [i0, i1) of one outcome:  ge_pos = #{j : y_j = 1, s_j >= s_i}, ge_neg, gt_neg (strict).
+//   AUROC = sum_{i pos} [ (Nneg - ge_neg_i) + (ge_neg_i - gt_neg_i) / 2 ] / (Npos * Nneg)   (ties count one half:
+//           identical to sklearn's trapezoid over distinct thresholds)
+//   AP    = (1 / Npos) sum_{i pos} ge_pos_i / (ge_pos_i + ge_neg_i)    (sklearn: sum_n (R_n - R_{n-1}) P_n)
+// Brute force O(N^2 / ranks) with the j scores staged through shared memory: exact, sort-free, and shardable over
+// i across GPUs (each rank needs all j scores = an all-gather of N floats per outcome).
+struct RankParams {
+    const float* scores;   // [N] probabilities of this outcome (all samples)
+    const uint8_t* y;      // [N] labels 0/1
+    int N, i0, i1;
+    unsigned long long* auroc2;  // += sum_{i pos in range} 2 (Nneg - ge_neg) + (ge_neg - gt_neg)
+    double* ap_partial;          // [gridDim.x] per-block partial sums of precision at each positive
+    unsigned long long* npos_nneg;  // [2] += positives / negatives among [i0, i1)
+};
+
+constexpr int kRankTile = 2048;
+
+__global__ void __launch_bounds__(256)
+rank_counts_kernel(const RankParams p) {
+    __shared__ float sj[kRankTile];
+    __shared__ uint8_t yj[kRankTile];
+    __shared__ double red_ap[8];
+    __shared__ unsigned long long red_au[8];
+    const int i = p.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < p.i1;
+    const float si = live ? p.scores[i] : 0.f;
+    const int yi = live ? p.y[i] : 0;
+    unsigned ge_pos = 0, ge_neg = 0, gt_neg = 0;
+    for (int j0 = 0; j0 < p.N; j0 += kRankTile) {
+        const int n = min(kRankTile, p.N - j0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            sj[j] = p.scores[j0 + j];
+            yj[j] = p.y[j0 + j];
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int j = 0; j < n; ++j) {
+            const float s = sj[j];
+            const unsigned pos = yj[j];
+            const unsigned ge = s >= si, gt = s > si;
+            ge_pos += ge & pos;
+            ge_neg += ge & (pos ^ 1u);
+            gt_neg += gt & (pos ^ 1u);
+        }
+    }
+    // totals of negatives are needed per i: Nneg = total negatives (all j) -- recomputed from the last pass
+    // by the finalizer, so emit the two tie-aware terms separately: A_i = ge_neg_i + gt_neg_i (= 2 gt + ties)
+    double ap = 0.0;
+    unsigned long long au = 0ull, np = 0ull, nn = 0ull;
+    if (live) {
+        if (yi) {
+            ap = (double)ge_pos / (double)(ge_pos + ge_neg);
+            au = (unsigned long long)ge_neg + (unsigned long long)gt_neg;  // subtracted from 2 Nneg per positive
+            np = 1;
+        } else {
+            nn = 1;
+        }
+    }
+    // block reduction (fixed order -> deterministic partials)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ap += __shfl_xor_sync(0xffffffffu, ap, o);
+        au += __shfl_xor_sync(0xffffffffu, au, o);
+        np += __shfl_xor_sync(0xffffffffu, np, o);
+        nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    }
+    if (lane == 0) {
+        red_ap[warp] = ap;
+        red_au[warp] = au;
+        atomicAdd(p.npos_nneg, np);
+        atomicAdd(p.npos_nneg + 1, nn);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+        unsigned long long u = 0ull;
+        for (int w = 0; w < 8; ++w) {
+            a += red_ap[w];
+            u += red_au[w];
+        }
+        p.ap_partial[blockIdx.x] = a;
+        atomicAdd(p.auroc2, u);
+    }
+}
+
+// fixed-order sum of the per-block partials (deterministic), accumulated into *dst
+__global__ void sum_partials_kernel(const double* __restrict__ part, int n, double* __restrict__ dst) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += part[i];
+        *dst += s;
+    }
+}
+
+// probs[o][n] = float32 sigmoid of logits[n, o]; y8[o][n] = labels[n, o] != 0   (outcome-major for the rank kernel)
+__global__ void sigmoid_probs_kernel(const float* __restrict__ logits, long long ld, const float* __restrict__ labels,
+                                     float* __restrict__ probs, uint8_t* __restrict__ y8, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        probs[(long long)o * N + n] = sigmoid_f32_exact(logits[n * ld + o]);
+        if (y8 != nullptr) y8[(long long)o * N + n] = labels[3ll * n + o] != 0.f;
+    }
+}
+
+}  // namespace fame

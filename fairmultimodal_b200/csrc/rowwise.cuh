@@ -37,26 +37,40 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float* f) {
 
 // ---------------------------------------------------------------------------------------- K3 LayerNorm
 // cols <= 1024, cols % 8 == 0.  Lane l owns the 8-element chunks l, l+32, l+64, l+96.
+// Input bf16 or f32; outputs bf16 and/or f32 (either may be null); optional per-row {mean, rstd} for the backward.
 constexpr int kLnWarpsPerBlock = 8;
 constexpr int kLnMaxChunks = 4;
 
+template <bool kInF32>
+__device__ __forceinline__ void ln_load8(const void* __restrict__ xr, int ch, float* f) {
+    if (kInF32) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(xr) + 2 * ch);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(xr) + 2 * ch + 1);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+        f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    } else {
+        bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(xr) + ch), f);
+    }
+}
+
+template <bool kInF32>
 __global__ void __launch_bounds__(kLnWarpsPerBlock * 32)
-layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
-                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, long long ldy, int rows,
-                      int cols, float eps) {
+layernorm_kernel(const void* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32,
+                 long long ldy, float2* __restrict__ stats, int rows, int cols, float eps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * kLnWarpsPerBlock + warp;
     if (row >= rows) return;
     const int nchunks = cols >> 3;
-    const __nv_bfloat16* xr = x + (long long)row * ldx;
+    const void* xr = kInF32 ? static_cast<const void*>(reinterpret_cast<const float*>(x) + (long long)row * ldx)
+                            : static_cast<const void*>(reinterpret_cast<const __nv_bfloat16*>(x) + (long long)row * ldx);
     float v[kLnMaxChunks][8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < kLnMaxChunks; ++i) {
         const int ch = lane + 32 * i;
         if (ch < nchunks) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr) + ch);
-            bf16x8_to_float(u, v[i]);
+            ln_load8<kInF32>(xr, ch, v[i]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) s += v[i][j];
         }
@@ -75,7 +89,7 @@ layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const 
         }
     }
     const float rstd = rsqrtf(warp_sum(q) / (float)cols + eps);
-    __nv_bfloat16* yr = y + (long long)row * ldy;
+    if (stats != nullptr && lane == 0) stats[row] = make_float2(mean, rstd);
 #pragma unroll
     for (int i = 0; i < kLnMaxChunks; ++i) {
         const int ch = lane + 32 * i;
@@ -89,7 +103,12 @@ layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const 
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
-            reinterpret_cast<uint4*>(yr)[ch] = float_to_bf16x8(o);
+            if (y_bf16 != nullptr) reinterpret_cast<uint4*>(y_bf16 + (long long)row * ldy)[ch] = float_to_bf16x8(o);
+            if (y_f32 != nullptr) {
+                float4* yo = reinterpret_cast<float4*>(y_f32 + (long long)row * ldy) + 2 * ch;
+                yo[0] = make_float4(o[0], o[1], o[2], o[3]);
+                yo[1] = make_float4(o[4], o[5], o[6], o[7]);
+            }
         }
     }
 }
@@ -102,7 +121,8 @@ __global__ void __launch_bounds__(kLnWarpsPerBlock * 32)
 bert_embed_ln_kernel(const long long* __restrict__ ids, const float* __restrict__ word,
                      const float* __restrict__ pos, const float* __restrict__ type0,
                      const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
-                     int* __restrict__ err_flag, int tokens, int seq_len, int hidden, int vocab, float eps) {
+                     float* __restrict__ y_f32, int* __restrict__ err_flag, int tokens, int seq_len, int hidden, int vocab,
+                     float eps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * kLnWarpsPerBlock + warp;
     if (t >= tokens) return;
@@ -147,10 +167,12 @@ bert_embed_ln_kernel(const long long* __restrict__ ids, const float* __restrict_
             const int ch = lane + 32 * i;
             const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + ch);
             const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + ch);
-            __nv_bfloat162 lo = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + b.x,
-                                                      (v[i].y - mean) * rstd * g.y + b.y);
-            __nv_bfloat162 hi = __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + b.z,
-                                                      (v[i].w - mean) * rstd * g.w + b.w);
+            const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
+            const float o2 = (v[i].z - mean) * rstd * g.z + b.z, o3 = (v[i].w - mean) * rstd * g.w + b.w;
+            if (y_f32 != nullptr)
+                reinterpret_cast<float4*>(y_f32 + (long long)t * hidden)[ch] = make_float4(o0, o1, o2, o3);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1);
+            __nv_bfloat162 hi = __floats2bfloat162_rn(o2, o3);
             uint2 o;
             o.x = *reinterpret_cast<uint32_t*>(&lo);
             o.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -209,6 +231,100 @@ segment_reduce_kernel(const void* __restrict__ x, long long ldx, const int* __re
         float* o = out + (long long)p * cols + c0;
         *reinterpret_cast<float4*>(o) = make_float4(acc[0] / den, acc[1] / den, acc[2] / den, acc[3] / den);
         *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4] / den, acc[5] / den, acc[6] / den, acc[7] / den);
+    }
+}
+
+// ---------------------------------------------------------------------------------------- K4b lab embedding
+// x[b*L + l, :] = lab[b, l] * w_tok + b_tok + pos[l, :]   (BEHRTModel_Lab.forward, 10_FAME.py:218-220) -> bf16.
+// One warp per token; hidden % 256 == 0 (lane owns 8-column chunks lane, lane+32, ...), hidden <= 1024.
+__global__ void __launch_bounds__(kLnWarpsPerBlock * 32)
+lab_embed_kernel(const float* __restrict__ lab, const float* __restrict__ w_tok, const float* __restrict__ b_tok,
+                 const float* __restrict__ pos, __nv_bfloat16* __restrict__ y, int tokens, int L, int hidden) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kLnWarpsPerBlock + warp;
+    if (t >= tokens) return;
+    const float v = __ldg(lab + t);
+    const float* pr = pos + (long long)(t % L) * hidden;
+    __nv_bfloat16* yr = y + (long long)t * hidden;
+    for (int ch = lane; ch < (hidden >> 3); ch += 32) {
+        float o[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(w_tok) + 2 * ch + h);
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(b_tok) + 2 * ch + h);
+            const float4 pp = __ldg(reinterpret_cast<const float4*>(pr) + 2 * ch + h);
+            // nn.Linear(1, H): x * w + b in one rounding per op as torch does (mul, add bias, add pos)
+            o[4 * h + 0] = (v * w.x + bb.x) + pp.x;
+            o[4 * h + 1] = (v * w.y + bb.y) + pp.y;
+            o[4 * h + 2] = (v * w.z + bb.z) + pp.z;
+            o[4 * h + 3] = (v * w.w + bb.w) + pp.w;
+        }
+        reinterpret_cast<uint4*>(yr)[ch] = float_to_bf16x8(o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------- K6 sequence mean
+// out[b, :] = mean_l x[b*L + l, :]  (BEHRTModel_Lab.forward, 10_FAME.py:224).  bf16 in, f32 out.
+// grid = (batch, splits): block (b, s) sums rows l = s, s + splits, ...; splits > 1 accumulates with atomicAdd
+// into a zero-initialised output (used only when batch alone cannot fill the GPU).
+__global__ void __launch_bounds__(128)
+seq_mean_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int L, int cols, int splits) {
+    const int b = blockIdx.x, sp = blockIdx.y;
+    const __nv_bfloat16* xb = x + (long long)b * L * cols;
+    const float inv = 1.0f / (float)L;
+    for (int c0 = threadIdx.x * 8; c0 < cols; c0 += blockDim.x * 8) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        int l = sp;
+        for (; l + 3 * splits < L; l += 4 * splits) {
+            float f[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(xb + (long long)(l + u * splits) * cols + c0)), f[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[u][j];
+        }
+        for (; l < L; l += splits) {
+            float f[8];
+            bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(xb + (long long)l * cols + c0)), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+        float* o = out + (long long)b * cols + c0;
+        if (splits == 1) {
+            *reinterpret_cast<float4*>(o) = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(o + j, acc[j] * inv);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------- K4c demographic add
+// out[b, :] = cls[b*ld_cls : , :] + (E_age[clamp(age[b])] + E_gen[..] + E_eth[..] + E_ins[..]) / 4
+// (BEHRTModel_Demo.forward, 10_FAME.py:195-206).  cls bf16 (CLS row of the demo BERT), tables f32, out f32.
+template <bool kClsF32>
+__global__ void __launch_bounds__(128)
+demo_add_kernel(const void* __restrict__ cls, long long ld_cls, const long long* __restrict__ age,
+                const long long* __restrict__ gen, const long long* __restrict__ eth, const long long* __restrict__ ins,
+                const float* __restrict__ e_age, const float* __restrict__ e_gen, const float* __restrict__ e_eth,
+                const float* __restrict__ e_ins, int n_age, int n_gen, int n_eth, int n_ins, float* __restrict__ out,
+                int hidden) {
+    const int b = blockIdx.x;
+    auto clampi = [](long long v, int n) { return (int)(v < 0 ? 0 : (v > n - 1 ? n - 1 : v)); };
+    const float* ra = e_age + (long long)clampi(age[b], n_age) * hidden;
+    const float* rg = e_gen + (long long)clampi(gen[b], n_gen) * hidden;
+    const float* re = e_eth + (long long)clampi(eth[b], n_eth) * hidden;
+    const float* ri = e_ins + (long long)clampi(ins[b], n_ins) * hidden;
+    for (int c = threadIdx.x; c < hidden; c += blockDim.x) {
+        const float extra = (((ra[c] + rg[c]) + re[c]) + ri[c]) / 4.0f;
+        const float cv = kClsF32 ? reinterpret_cast<const float*>(cls)[(long long)b * ld_cls + c]
+                                 : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(cls)[(long long)b * ld_cls + c]);
+        out[(long long)b * hidden + c] = cv + extra;
     }
 }
 

@@ -76,8 +76,11 @@ def gemm_bias_act(x, w, bias=None, residual=None, act=ACT_NONE, out=None, out_dt
     a.w, a.ldw = w.data_ptr(), _rowmajor(w, "w")
     a.bias = _cuda(bias, "bias", torch.float32).data_ptr() if bias is not None else None
     if residual is not None:
-        _cuda(residual, "residual", torch.bfloat16)
+        _cuda(residual, "residual")
+        if residual.dtype not in (torch.bfloat16, torch.float32):
+            raise _lib.FameError("residual must be bf16 or f32")
         a.residual, a.ldr = residual.data_ptr(), _rowmajor(residual, "residual")
+        a.residual_dtype = DT_F32 if residual.dtype == torch.float32 else DT_BF16
     else:
         a.residual, a.ldr = None, 0
     a.y, a.ldy = out.data_ptr(), _rowmajor(out, "out")
@@ -87,28 +90,43 @@ def gemm_bias_act(x, w, bias=None, residual=None, act=ACT_NONE, out=None, out_dt
     return out
 
 
-def layernorm(x, gamma, beta, eps, out=None):
-    _cuda(x, "x", torch.bfloat16)
+def layernorm(x, gamma, beta, eps, out=None, out_f32=None, want_f32=False, stats=None):
+    """x bf16 or f32 [rows, cols] -> bf16 `out` (default) and / or f32 `out_f32`; optional {mean, rstd} per row.
+    Returns out (bf16) unless want_f32, in which case (out_bf16, out_f32)."""
+    _cuda(x, "x")
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        raise _lib.FameError("layernorm: x must be bf16 or f32")
     rows, cols = x.shape
     if out is None:
-        out = torch.empty_like(x)
+        out = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16)
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty((rows, cols), device=x.device, dtype=torch.float32)
     a = _lib.LayerNormArgs()
     a.x, a.ldx = x.data_ptr(), _rowmajor(x, "x")
+    a.x_dtype = DT_F32 if x.dtype == torch.float32 else DT_BF16
     a.gamma = _cuda(gamma, "gamma", torch.float32).data_ptr()
     a.beta = _cuda(beta, "beta", torch.float32).data_ptr()
     a.y, a.ldy = out.data_ptr(), _rowmajor(out, "out")
+    if out_f32 is not None:
+        if _rowmajor(out_f32, "out_f32") != a.ldy:
+            raise _lib.FameError("layernorm: bf16 and f32 outputs must share the leading dimension")
+        a.y_f32 = out_f32.data_ptr()
+    if stats is not None:
+        a.stats = _cuda(stats, "stats", torch.float32).data_ptr()
     a.rows, a.cols, a.eps = rows, cols, eps
     _call("fame_layernorm", a, 4.0 * rows * cols)
-    return out
+    return (out, out_f32) if want_f32 else out
 
 
-def bert_embed(ids, word, pos, type_emb, gamma, beta, eps, seq_len, err_flag=None):
-    """ids int64 [tokens] (flattened [chunks, seq_len]) -> bf16 [tokens, hidden]."""
+def bert_embed(ids, word, pos, type_emb, gamma, beta, eps, seq_len, err_flag=None, out_f32=None):
+    """ids int64 [tokens] (flattened [chunks, seq_len]) -> bf16 [tokens, hidden] (+ optional f32 copy)."""
     _cuda(ids, "ids", torch.int64)
     ids = ids.contiguous().view(-1)
     hidden = word.shape[1]
     out = torch.empty((ids.numel(), hidden), device=ids.device, dtype=torch.bfloat16)
     a = _lib.BertEmbedArgs()
+    if out_f32 is not None:
+        a.y_f32 = _cuda(out_f32, "out_f32", torch.float32).data_ptr()
     a.ids = ids.data_ptr()
     a.word = _cuda(word, "word", torch.float32).data_ptr()
     a.pos = _cuda(pos, "pos", torch.float32).data_ptr()
@@ -164,3 +182,186 @@ def segment_mean(x, offsets, cols=None, ldx=None, mode="mean"):
     # algorithmic bytes: rows read (not known without a sync: caller may refine) + offsets + output
     _call("fame_segment_mean", a, 4.0 * (patients + 1) + 4.0 * patients * cols)
     return out
+
+
+def lab_embed(lab, w_tok, b_tok, pos):
+    """lab f32 [B, L] -> bf16 [B*L, hidden]:  lab * w_tok + b_tok + pos[l]."""
+    _cuda(lab, "lab", torch.float32)
+    B, L = lab.shape
+    hidden = pos.shape[1]
+    out = torch.empty((B * L, hidden), device=lab.device, dtype=torch.bfloat16)
+    a = _lib.LabEmbedArgs()
+    a.lab = lab.contiguous().data_ptr()
+    a.w_tok = _cuda(w_tok, "w_tok", torch.float32).data_ptr()
+    a.b_tok = _cuda(b_tok, "b_tok", torch.float32).data_ptr()
+    a.pos = _cuda(pos, "pos", torch.float32).data_ptr()
+    a.y = out.data_ptr()
+    a.batch, a.L, a.hidden = B, L, hidden
+    _call("fame_lab_embed", a, B * L * (4.0 + 2.0 * hidden))
+    return out
+
+
+def seq_mean(x, batch, L):
+    """x bf16 [batch*L, cols] -> f32 [batch, cols] (mean over the L rows of each sequence)."""
+    _cuda(x, "x", torch.bfloat16)
+    cols = x.shape[1]
+    out = torch.empty((batch, cols), device=x.device, dtype=torch.float32)
+    a = _lib.SeqMeanArgs()
+    a.x, a.out = x.data_ptr(), out.data_ptr()
+    a.batch, a.L, a.cols = batch, L, cols
+    _call("fame_seq_mean", a, 2.0 * batch * L * cols + 4.0 * batch * cols)
+    return out
+
+
+def demo_add(cls, ld_cls, ids, tables):
+    """out[b] = cls_row[b] + mean of the 4 demographic embedding rows (ids clamped to the table range)."""
+    _cuda(cls, "cls")
+    if cls.dtype not in (torch.bfloat16, torch.float32):
+        raise _lib.FameError("demo_add: cls must be bf16 or f32")
+    B = ids[0].numel()
+    hidden = tables[0].shape[1]
+    out = torch.empty((B, hidden), device=cls.device, dtype=torch.float32)
+    a = _lib.DemoAddArgs()
+    a.cls, a.ld_cls = cls.data_ptr(), ld_cls
+    a.cls_dtype = DT_F32 if cls.dtype == torch.float32 else DT_BF16
+    keep = []
+    for k in range(4):
+        i = _cuda(ids[k], "ids", torch.int64).contiguous()
+        t = _cuda(tables[k], "table", torch.float32).contiguous()
+        keep += [i, t]
+        a.ids[k], a.table[k], a.n_rows[k] = i.data_ptr(), t.data_ptr(), t.shape[0]
+    a.out, a.batch, a.hidden = out.data_ptr(), B, hidden
+    _call("fame_demo_add", a, B * hidden * (2.0 + 16.0 + 4.0))
+    return out
+
+
+def fusion_fwd(emb, packed, w_mod, want_mod_logits=False, want_intermediates=False):
+    """emb = (demo, lab, text) f32 [B,768]; packed = dict of fp32 fusion weights (see modules._pack_fusion).
+    Returns dict(logits, sig, [mod_logits], [proj, gated, pre_relu])."""
+    B = emb[0].shape[0]
+    dev = emb[0].device
+    a = _lib.FusionFwdArgs()
+    keep = []
+    for m in range(3):
+        e = _cuda(emb[m], "emb", torch.float32).contiguous()
+        keep.append(e)
+        a.emb[m] = e.data_ptr()
+        a.w_mod[m] = float(w_mod[m])
+    for k in ("wp_t", "bp", "sig_w", "w3_t", "b3", "w4", "b4", "wc", "bc"):
+        setattr(a, k, packed[k].data_ptr())
+    out = {"logits": torch.empty((B, 3), device=dev, dtype=torch.float32),
+           "sig": torch.empty(768, device=dev, dtype=torch.float32)}
+    a.logits, a.sig_out = out["logits"].data_ptr(), out["sig"].data_ptr()
+    if want_mod_logits:
+        out["mod_logits"] = torch.empty((3, B, 3), device=dev, dtype=torch.float32)
+        a.mod_logits = out["mod_logits"].data_ptr()
+    if want_intermediates:
+        out["proj"] = torch.empty((B, 768), device=dev, dtype=torch.float32)
+        out["gated"] = torch.empty((B, 768), device=dev, dtype=torch.float32)
+        out["pre_relu"] = torch.empty((B, 512), device=dev, dtype=torch.float32)
+        a.proj, a.gated, a.pre_relu = out["proj"].data_ptr(), out["gated"].data_ptr(), out["pre_relu"].data_ptr()
+    a.B = B
+    _call("fame_fusion_fwd", a, B * (3 * 768 * 4.0 + 3 * 4.0) + 4.0 * (3 * 768 * 256 + 768 * 512))
+    return out
+
+
+def _attr_ptrs(a, attrs, keep):
+    for k in range(3):
+        t = _cuda(attrs[k], "attr", torch.int64).contiguous()
+        keep.append(t)
+        a.attr[k] = t.data_ptr()
+
+
+def loss_stats(logits, labels, attrs, pos_weight, stats=None):
+    """Per-rank LEDDI / BCE statistics (int64 [104]); accumulates into `stats` when given."""
+    _cuda(logits, "logits", torch.float32)
+    B = logits.shape[0]
+    if stats is None:
+        stats = torch.zeros(_lib.LOSS_STATS_LEN, device=logits.device, dtype=torch.int64)
+    a = _lib.LossStatsArgs()
+    keep = [logits.contiguous(), _cuda(labels, "labels", torch.float32).contiguous(),
+            _cuda(pos_weight, "pos_weight", torch.float32).contiguous()]
+    a.logits, a.labels, a.pos_weight = keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr()
+    _attr_ptrs(a, attrs, keep)
+    a.stats, a.B = stats.data_ptr(), B
+    _call("fame_loss_stats", a, 48.0 * B)
+    return stats
+
+
+def loss_fwd_bwd(logits, labels, attrs, pos_weight, stats, sig_w, lambda_edd, lambda_l1, want_grad=True):
+    """Global statistics -> (loss_out f32 [4] = total, bce, leddi, l1;  dlogits f32 [B,3] or None)."""
+    B = logits.shape[0]
+    dev = logits.device
+    a = _lib.LossFwdBwdArgs()
+    keep = [logits.contiguous(), labels.contiguous(), pos_weight.contiguous()]
+    a.logits, a.labels, a.pos_weight = keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr()
+    _attr_ptrs(a, attrs, keep)
+    a.stats = _cuda(stats, "stats", torch.int64).data_ptr()
+    if sig_w is not None:
+        a.sig_w, a.n_sig = _cuda(sig_w, "sig_w", torch.float32).data_ptr(), sig_w.numel()
+    a.lambda_edd, a.lambda_l1 = float(lambda_edd), float(lambda_l1)
+    loss = torch.empty(4, device=dev, dtype=torch.float32)
+    dlogits = torch.empty((B, 3), device=dev, dtype=torch.float32) if want_grad else None
+    a.loss_out = loss.data_ptr()
+    a.dlogits = dlogits.data_ptr() if want_grad else None
+    a.B = B
+    _call("fame_loss_fwd_bwd", a, 60.0 * B)
+    return loss, dlogits
+
+
+def eval_counts(logits, labels, attrs, thr, sweep=None, out=None, logits_are_probs=False):
+    """Integer confusion counts per (outcome, attr, code) + totals (+ F1-sweep histogram).  uint64-as-int64 [914]."""
+    _cuda(logits, "logits", torch.float32)
+    N = logits.shape[0]
+    if out is None:
+        out = torch.zeros(_lib.EVAL_COUNTS_LEN, device=logits.device, dtype=torch.int64)
+    a = _lib.EvalCountsArgs()
+    keep = [_cuda(labels, "labels", torch.float32).contiguous()]
+    a.logits, a.ld, a.labels = logits.data_ptr(), _rowmajor(logits, "logits"), keep[0].data_ptr()
+    _attr_ptrs(a, attrs, keep)
+    for k in range(3):
+        a.thr[k] = float(thr[k])
+    if sweep is not None:
+        keep.append(_cuda(sweep, "sweep", torch.float64).contiguous())
+        a.sweep = keep[-1].data_ptr()
+    a.out, a.N, a.logits_are_probs = out.data_ptr(), N, int(logits_are_probs)
+    _call("fame_eval_counts", a, 48.0 * N)
+    return out
+
+
+def sigmoid_probs(logits, labels=None):
+    """float32 probabilities [3, N] (outcome-major) and uint8 labels [3, N]."""
+    N = logits.shape[0]
+    probs = torch.empty((3, N), device=logits.device, dtype=torch.float32)
+    y8 = torch.empty((3, N), device=logits.device, dtype=torch.uint8) if labels is not None else None
+    a = _lib.SigmoidProbsArgs()
+    a.logits, a.ld = _cuda(logits, "logits", torch.float32).data_ptr(), _rowmajor(logits, "logits")
+    if labels is not None:
+        labels = _cuda(labels, "labels", torch.float32).contiguous()
+        a.labels, a.y8 = labels.data_ptr(), y8.data_ptr()
+    a.probs, a.N = probs.data_ptr(), N
+    _call("fame_sigmoid_probs", a, 28.0 * N)
+    return probs, y8
+
+
+def rank_counts(scores, y8, i0=0, i1=None, acc=None):
+    """Tie-aware rank statistics of one outcome.  Returns acc = dict(auroc2 int64[1], ap f64[1], pn int64[2])."""
+    N = scores.numel()
+    i1 = N if i1 is None else i1
+    dev = scores.device
+    if acc is None:
+        acc = {"auroc2": torch.zeros(1, device=dev, dtype=torch.int64), "ap": torch.zeros(1, device=dev, dtype=torch.float64),
+               "pn": torch.zeros(2, device=dev, dtype=torch.int64)}
+    if i1 <= i0:
+        return acc
+    lib = _lib.load()
+    ws_bytes = lib.fame_rank_counts_workspace_bytes(i1 - i0)
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    a = _lib.RankCountsArgs()
+    a.scores, a.y = _cuda(scores, "scores", torch.float32).data_ptr(), _cuda(y8, "y8", torch.uint8).data_ptr()
+    a.N, a.i0, a.i1 = N, i0, i1
+    a.auroc2, a.ap_sum, a.npos_nneg = acc["auroc2"].data_ptr(), acc["ap"].data_ptr(), acc["pn"].data_ptr()
+    global LAUNCHES
+    LAUNCHES += 2
+    _lib.call("fame_rank_counts", a, _stream(), ws.data_ptr(), ws_bytes)
+    return acc

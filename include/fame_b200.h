@@ -58,6 +58,7 @@ typedef struct {
     const float* bias; /* may be NULL */
     const void* residual; /* may be NULL */
     int64_t ldr;
+    int32_t residual_dtype; /* FAME_DT_BF16 (default) or FAME_DT_F32 (fp32 residual stream of the small-batch towers) */
     void* y;
     int64_t ldy;
     int32_t y_dtype; /* FAME_DT_* */
@@ -74,10 +75,13 @@ int fame_gemm_bias_act(const fame_gemm_args* a, void* workspace, size_t workspac
 typedef struct {
     const void* x;
     int64_t ldx;
+    int32_t x_dtype; /* FAME_DT_BF16 or FAME_DT_F32 */
     const float* gamma;
     const float* beta;
-    void* y;
+    void* y;      /* bf16 output, may be NULL */
+    float* y_f32; /* f32 output, may be NULL (at least one output is required); same ldy */
     int64_t ldy;
+    float* stats; /* [rows][2] = {mean, rstd} saved for the backward pass, may be NULL */
     int32_t rows, cols;
     float eps;
 } fame_layernorm_args;
@@ -95,6 +99,7 @@ typedef struct {
     const float* gamma;
     const float* beta;
     void* y; /* bf16 [tokens, hidden] */
+    float* y_f32; /* optional f32 copy of the same rows, may be NULL */
     int32_t* err_flag;
     int32_t tokens, seq_len, hidden, vocab;
     float eps;
@@ -138,6 +143,151 @@ typedef struct {
 } fame_segment_mean_args;
 int fame_segment_mean(const fame_segment_mean_args* a, void* workspace, size_t workspace_bytes,
                       fame_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K4b fame_lab_embed:  Y[b*L + l, :] = lab[b,l] * w_tok + b_tok + pos[l, :]  -> bf16 [batch*L, hidden]
+ * Replaces token_embedding + pos_embedding of BEHRTModel_Lab.forward (10_FAME.py:218-220). hidden % 8 == 0. */
+typedef struct {
+    const float* lab;   /* [batch, L] */
+    const float* w_tok; /* [hidden] (Linear(1, hidden).weight[:, 0]) */
+    const float* b_tok; /* [hidden] */
+    const float* pos;   /* [L, hidden] */
+    void* y;            /* bf16 [batch*L, hidden] */
+    int32_t batch, L, hidden;
+} fame_lab_embed_args;
+int fame_lab_embed(const fame_lab_embed_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
+
+/* K6 fame_seq_mean:  out[b, :] = mean_l x[b*L + l, :]   (x.mean(dim=1), 10_FAME.py:224).  x bf16, out f32. */
+typedef struct {
+    const void* x; /* bf16 [batch*L, cols] contiguous */
+    float* out;    /* [batch, cols] */
+    int32_t batch, L, cols;
+} fame_seq_mean_args;
+int fame_seq_mean(const fame_seq_mean_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
+
+/* K4c fame_demo_add:  out[b,:] = cls[b*ld_cls : +hidden] + (E_age[clamp(age_b)] + E_gender[..] + E_eth[..] + E_ins[..]) / 4
+ * (clamp + 4 lookups + average of BEHRTModel_Demo.forward, 10_FAME.py:195-206).  cls bf16, tables f32, out f32. */
+typedef struct {
+    const void* cls;
+    int64_t ld_cls;
+    int32_t cls_dtype;       /* FAME_DT_BF16 or FAME_DT_F32 */
+    const int64_t* ids[4];   /* age, gender, ethnicity, insurance  [batch] */
+    const float* table[4];   /* [n_rows[k], hidden] */
+    int32_t n_rows[4];
+    float* out;              /* [batch, hidden] */
+    int32_t batch, hidden;
+} fame_demo_add_args;
+int fame_demo_add(const fame_demo_add_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K7 fame_fusion_fwd: EDDI-weighted, sigmoid-gated modality fusion and heads (10_FAME.py:276-308), fp32.
+ * Weights wp_t / w3_t are the TRANSPOSED projector / fusion_mlp.0 matrices ([in, out]); hidden sizes are the
+ * reference's fixed 768 -> 3 x 256 -> 768 -> 512 -> 3.  Optional outputs may be NULL. */
+typedef struct {
+    const float* emb[3];  /* demo, lab, text embeddings [B,768] */
+    const float* wp_t;    /* [3][768][256] */
+    const float* bp;      /* [3][256] */
+    float w_mod[3];       /* (w_demo, w_lab, w_text) */
+    const float* sig_w;   /* [768] */
+    const float* w3_t;    /* [768][512] */
+    const float* b3;      /* [512] */
+    const float* w4;      /* [3][512] */
+    const float* b4;      /* [3] */
+    const float* wc;      /* [3][3][256] classifier_{demo,lab,text}.weight */
+    const float* bc;      /* [3][3] */
+    float* proj;          /* [B,768] relu(projector) outputs, unweighted */
+    float* gated;         /* [B,768] "gated_vector" */
+    float* pre_relu;      /* [B,512] "fusion_pre_relu" */
+    float* logits;        /* [B,3]   "fused_logits" (required) */
+    float* mod_logits;    /* [3][B][3] "modality_logits" */
+    float* sig_out;       /* [768]   "sigmoid_weights" */
+    int32_t B;
+} fame_fusion_fwd_args;
+int fame_fusion_fwd(const fame_fusion_fwd_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K8 joint loss of train_step (10_FAME.py:420-444), two passes so that data-parallel ranks can SUM-all-reduce the
+ * statistics in between (every rank then evaluates the GLOBAL-batch loss and the gradient of its own patients):
+ *   fame_loss_stats   : per-rank statistics -> stats[FAME_LOSS_STATS_LEN] (int64; counts and fixed-point sums)
+ *   fame_loss_fwd_bwd : stats -> loss_out = {total, bce, leddi, l1} and dlogits = d total / d fused_logits
+ * stats layout: [0..2] sum|p-y| (2^32 fixed point); [3..5] BCE sums (2^24); [6..77] subgroup error sums
+ * [outcome][attr][code 0..7] (2^32); [78..101] subgroup counts [attr][code]; [102] patients; [103] bad-code flag.
+ * Subgroup membership = the int64 code itself (0..7), groups "present" = count > 0 (torch.unique, 10_FAME.py:432). */
+#define FAME_LOSS_STATS_LEN 104
+typedef struct {
+    const float* logits; /* [B,3] */
+    const float* labels; /* [B,3] */
+    const int64_t* attr[3]; /* age_ids, ethnicity_ids, insurance_ids [B] */
+    const float* pos_weight; /* [3] */
+    int64_t* stats; /* [FAME_LOSS_STATS_LEN]; ACCUMULATED into (caller zeroes it) */
+    int32_t B;
+} fame_loss_stats_args;
+int fame_loss_stats(const fame_loss_stats_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
+
+typedef struct {
+    const float* logits;
+    const float* labels;
+    const int64_t* attr[3];
+    const float* pos_weight;
+    const int64_t* stats; /* global statistics */
+    const float* sig_w;   /* [n_sig] for the L1 term, may be NULL */
+    int32_t n_sig;
+    float lambda_edd, lambda_l1;
+    float* dlogits;  /* [B,3], may be NULL (loss only) */
+    float* loss_out; /* [4] */
+    int32_t B;       /* local patients */
+} fame_loss_fwd_bwd_args;
+int fame_loss_fwd_bwd(const fame_loss_fwd_bwd_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K10 fame_eval_counts: one pass over predictions -> integer counts (uint64, accumulated; caller zeroes):
+ *   out[((o*3 + a)*8 + code)*4 + {TP,FN,FP,TN}]  per outcome o, attribute a (age, ethnicity, insurance), code 0..7
+ *   out[288 + o*4 + {TP,FN,FP,TN}]               per outcome
+ *   out[300 + (o*2 + label)*102 + k]             F1-sweep histogram: k = #sweep thresholds strictly below p
+ *   out[912] = patients, out[913] = bad-code flag
+ * prediction = (double)float32(sigmoid(logit)) > thr[o]  (strict, float64 compare: 10_FAME.py:55, 476, 518).
+ * Replaces compute_eddi / calculate_tpr_and_fpr / confusion_matrix / the f1 sweep (10_FAME.py:54-97, 470-481, 514-540). */
+#define FAME_EVAL_COUNTS_LEN 914
+typedef struct {
+    const float* logits; /* [N, ld] */
+    int64_t ld;
+    const float* labels; /* [N,3] */
+    const int64_t* attr[3];
+    double thr[3];
+    const double* sweep; /* device [101] or NULL */
+    uint64_t* out;
+    int32_t N;
+    int32_t logits_are_probs;
+} fame_eval_counts_args;
+int fame_eval_counts(const fame_eval_counts_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
+
+/* fame_rank_counts: exact tie-aware rank statistics of one outcome for samples [i0, i1) against all N samples.
+ *   auroc2 += sum_{i positive} (#neg with s >= s_i) + (#neg with s > s_i);   AUROC = 1 - auroc2 / (2 Npos Nneg)
+ *   ap_sum += sum_{i positive} #pos(s >= s_i) / #all(s >= s_i);              AP    = ap_sum / Npos
+ *   npos_nneg[0..1] += positives / negatives among [i0, i1)
+ * Equal to sklearn roc_auc_score / average_precision_score on the same float32 scores (10_FAME.py:520-526).
+ * workspace: fame_rank_counts_workspace_bytes(i1 - i0). */
+typedef struct {
+    const float* scores;  /* [N] float32 probabilities */
+    const uint8_t* y;     /* [N] 0/1 */
+    int32_t N, i0, i1;
+    uint64_t* auroc2;
+    double* ap_sum;
+    uint64_t* npos_nneg;
+} fame_rank_counts_args;
+size_t fame_rank_counts_workspace_bytes(int32_t n_i);
+int fame_rank_counts(const fame_rank_counts_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
+
+/* fame_sigmoid_probs: p = float32 sigmoid (correctly rounded) of logits[:, outcome]; y8 = (labels[:, outcome] != 0). */
+typedef struct {
+    const float* logits;
+    int64_t ld;
+    const float* labels; /* [N,3] or NULL */
+    float* probs;        /* [3][N] outcome-major */
+    uint8_t* y8;         /* [3][N] or NULL */
+    int32_t N;
+} fame_sigmoid_probs_args;
+int fame_sigmoid_probs(const fame_sigmoid_probs_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
 
 #ifdef __cplusplus
 }

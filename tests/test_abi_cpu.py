@@ -31,11 +31,9 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_sizes_match_header(lib):
     # compile a tiny C program against the header and compare sizeof() with the ctypes mirrors
     import subprocess, tempfile
-    names = {"fame_gemm_args": _lib.GemmArgs, "fame_layernorm_args": _lib.LayerNormArgs,
-             "fame_bert_embed_args": _lib.BertEmbedArgs, "fame_attn_fwd_args": _lib.AttnFwdArgs,
-             "fame_segment_mean_args": _lib.SegmentMeanArgs}
-    for extra in getattr(_lib, "EXTRA_STRUCTS", {}).items():
-        names[extra[0]] = extra[1]
+    names = dict(_lib.STRUCT_NAMES)
+    header = open(os.path.join(ROOT, "include", "fame_b200.h")).read()
+    assert set(re.findall(r"\}\s*(fame_[a-z0-9_]+_args)\s*;", header)) == set(names)
     src = '#include <stdio.h>\n#include "fame_b200.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "return 0;}"
     with tempfile.TemporaryDirectory() as d:
