@@ -46,7 +46,8 @@ class LayerNormArgs(C.Structure):
 class BertEmbedArgs(C.Structure):
     _fields_ = [
         ("ids", C.c_void_p), ("word", C.c_void_p), ("pos", C.c_void_p), ("type0", C.c_void_p),
-        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("y", C.c_void_p), ("y_f32", C.c_void_p), ("err_flag", C.c_void_p),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("y", C.c_void_p), ("y_f32", C.c_void_p), ("sum_out", C.c_void_p),
+        ("stats", C.c_void_p), ("err_flag", C.c_void_p),
         ("tokens", C.c_int32), ("seq_len", C.c_int32), ("hidden", C.c_int32), ("vocab", C.c_int32),
         ("eps", C.c_float),
     ]
@@ -137,8 +138,46 @@ class SigmoidProbsArgs(C.Structure):
     ]
 
 
+class GemmOperand(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("ld", C.c_int64), ("stride_b0", C.c_int64), ("stride_b1", C.c_int64),
+                ("mn_major", C.c_int32)]
+
+
+class GemmExArgs(C.Structure):
+    _fields_ = [
+        ("a", GemmOperand), ("b", GemmOperand), ("bias", C.c_void_p),
+        ("aux", C.c_void_p), ("ld_aux", C.c_int64), ("aux_stride_b0", C.c_int64), ("aux_stride_b1", C.c_int64),
+        ("aux_mode", C.c_int32),
+        ("y", C.c_void_p), ("ldy", C.c_int64), ("y_stride_b0", C.c_int64), ("y_stride_b1", C.c_int64),
+        ("y_dtype", C.c_int32),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("nb0", C.c_int32), ("nb1", C.c_int32),
+        ("act", C.c_int32), ("alpha", C.c_float), ("n_valid", C.c_int32),
+    ]
+
+
+AUX_NONE, AUX_ADD_BF16, AUX_ADD_F32, AUX_RELU_MASK_BF16 = 0, 1, 2, 3
 LOSS_STATS_LEN = 104
 EVAL_COUNTS_LEN = 914
+
+_P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+# flat-argument entry points (backward pass / optimizer): name -> argument types, the stream is appended
+FLAT_OPS = {
+    "fame_layernorm_bwd": [_P, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32],
+    "fame_gelu_fwd": [_P, _P, _I64],
+    "fame_gelu_bwd": [_P, _P, _P, _I64],
+    "fame_colsum": [_P, _I32, _I64, _I32, _I32, _P],
+    "fame_seq_mean_bwd": [_P, _P, _I32, _I32, _I32],
+    "fame_lab_embed_bwd": [_P, _P, _P, _P, _P, _I32, _I32, _I32],
+    "fame_attn_bwd_softmax": [_P, _P, _P, _P, _I64, _I32, _I32, _F],
+    "fame_bert_embed_bwd": [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32],
+    "fame_demo_add_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32],
+    "fame_sgemm_small": [_P, _I64, _I64, _P, _I64, _I64, _P, _I64, _I32, _I32, _I32, _F, _I32],
+    "fame_fusion_bwd_hidden": [_P, _P, _P, _P, _I32],
+    "fame_fusion_bwd_gate": [_P, _P, _P, _F, _F, _F, _F, _P, _P, _I32],
+    "fame_grad_sumsq": [_P, _I64, _P],
+    "fame_clip_adamw": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _I32, _P],
+    "fame_cast_bf16": [_P, _P, _I64],
+}
 
 # name -> args struct for every `int fame_<op>(const args*, void* ws, size_t ws_bytes, stream)` entry point
 OP_TABLE = {
@@ -156,6 +195,7 @@ OP_TABLE = {
     "fame_eval_counts": EvalCountsArgs,
     "fame_rank_counts": RankCountsArgs,
     "fame_sigmoid_probs": SigmoidProbsArgs,
+    "fame_gemm_ex": GemmExArgs,
 }
 PLAIN_SYMBOLS = ["fame_strerror", "fame_last_cuda_error", "fame_abi_version", "fame_device_check", "fame_sm_count",
                  "fame_rank_counts_workspace_bytes"]
@@ -167,6 +207,7 @@ STRUCT_NAMES = {
     "fame_fusion_fwd_args": FusionFwdArgs, "fame_loss_stats_args": LossStatsArgs,
     "fame_loss_fwd_bwd_args": LossFwdBwdArgs, "fame_eval_counts_args": EvalCountsArgs,
     "fame_rank_counts_args": RankCountsArgs, "fame_sigmoid_probs_args": SigmoidProbsArgs,
+    "fame_gemm_ex_args": GemmExArgs,
 }
 
 _lib = None
@@ -194,6 +235,10 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(struct), C.c_void_p, C.c_size_t, C.c_void_p]
+    for name, argtypes in FLAT_OPS.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = list(argtypes) + [C.c_void_p]
     _lib = lib
     return lib
 
@@ -209,3 +254,8 @@ def check(code: int, what: str) -> None:
 def call(name: str, args, stream: int, workspace: int = 0, workspace_bytes: int = 0) -> None:
     lib = load()
     check(getattr(lib, name)(C.byref(args), workspace, workspace_bytes, stream), name)
+
+
+def call_flat(name: str, stream: int, *args) -> None:
+    lib = load()
+    check(getattr(lib, name)(*args, stream), name)

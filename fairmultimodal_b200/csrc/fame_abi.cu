@@ -8,6 +8,7 @@
 
 #include "attn_sm100.cuh"
 #include "attn_flash_sm100.cuh"
+#include "backward.cuh"
 #include "gemm_sm100.cuh"
 #include "heads.cuh"
 #include "metrics.cuh"
@@ -92,6 +93,8 @@ int launch_status() {
     return e == cudaSuccess ? FAME_OK : cuda_fail(e);
 }
 
+#include "gemm_host.inc"
+
 template <int D>
 static int launch_flash(const fame_attn_fwd_args* a, const CUtensorMap& tq, fame_stream_t stream) {
     static bool attr_set[64] = {};
@@ -164,47 +167,25 @@ int fame_gemm_bias_act(const fame_gemm_args* a, void* /*workspace*/, size_t /*wo
     if (a->bias != nullptr && !aligned16(a->bias)) return FAME_ERR_ALIGN;
     if (a->residual != nullptr && (!aligned16(a->residual) || (a->ldr & 7) || a->ldr < a->N)) return FAME_ERR_ALIGN;
     if (a->residual_dtype != FAME_DT_BF16 && a->residual_dtype != FAME_DT_F32) return FAME_ERR_SHAPE;
-    DeviceInfo* d = nullptr;
-    int rc = device_info(&d);
-    if (rc != FAME_OK) return rc;
-    if (a->M == 0) return FAME_OK;
-
-    CUtensorMap ta, tb;
-    rc = encode_bf16_2d(&ta, a->x, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->ldx, fame::kGemmBM);
-    if (rc != FAME_OK) return rc;
-    rc = encode_bf16_2d(&tb, a->w, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldw, fame::kGemmBN);
-    if (rc != FAME_OK) return rc;
-    CUtensorMap tc = ta;  // unused by the f32-output path
-    if (a->y_dtype == FAME_DT_BF16) {
-        rc = encode_bf16_2d(&tc, a->y, (uint64_t)a->M, (uint64_t)a->N, (uint64_t)a->ldy, 128);
-        if (rc != FAME_OK) return rc;
+    fame_gemm_ex_args e = {};
+    e.a.ptr = a->x; e.a.ld = a->ldx;
+    e.b.ptr = a->w; e.b.ld = a->ldw;
+    e.bias = a->bias;
+    if (a->residual != nullptr) {
+        e.aux = a->residual;
+        e.ld_aux = a->ldr;
+        e.aux_mode = a->residual_dtype == FAME_DT_F32 ? FAME_AUX_ADD_F32 : FAME_AUX_ADD_BF16;
     }
+    e.y = a->y; e.y_dtype = a->y_dtype; e.ldy = a->ldy;
+    e.M = a->M; e.N = a->N; e.K = a->K;
+    e.nb0 = e.nb1 = 1;
+    e.act = a->act;
+    e.alpha = 1.0f;
+    return gemm_ex(&e, stream);
+}
 
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(fame::gemm_bf16_tcgen05_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, fame::kGemmSmemBytes);
-        if (e != cudaSuccess) return cuda_fail(e);
-        attr_set[dev] = true;
-    }
-    fame::GemmParams p;
-    p.M = a->M; p.N = a->N; p.K = a->K;
-    p.bias = a->bias;
-    p.residual = a->residual;
-    p.ldr = a->ldr;
-    p.res_f32 = a->residual_dtype == FAME_DT_F32;
-    p.y = a->y;
-    p.ldy = a->ldy;
-    p.act = a->act;
-    p.y_f32 = a->y_dtype == FAME_DT_F32;
-    const int m_tiles = (a->M + fame::kGemmBM - 1) / fame::kGemmBM;
-    const int n_tiles = (a->N + fame::kGemmBN - 1) / fame::kGemmBN;
-    const int tiles = m_tiles * n_tiles;
-    const int grid = tiles < d->sm_count ? tiles : d->sm_count;
-    fame::gemm_bf16_tcgen05_kernel<<<grid, fame::kGemmThreads, fame::kGemmSmemBytes, stream>>>(ta, tb, tc, p);
-    return launch_status();
+int fame_gemm_ex(const fame_gemm_ex_args* a, void* /*workspace*/, size_t /*workspace_bytes*/, fame_stream_t stream) {
+    return gemm_ex(a, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ K3
@@ -249,8 +230,8 @@ int fame_bert_embed(const fame_bert_embed_args* a, void*, size_t, fame_stream_t 
     const int grid = (a->tokens + fame::kLnWarpsPerBlock - 1) / fame::kLnWarpsPerBlock;
     fame::bert_embed_ln_kernel<<<grid, fame::kLnWarpsPerBlock * 32, 0, stream>>>(
         reinterpret_cast<const long long*>(a->ids), a->word, a->pos, a->type0, a->gamma, a->beta,
-        reinterpret_cast<__nv_bfloat16*>(a->y), a->y_f32, a->err_flag, a->tokens, a->seq_len, a->hidden, a->vocab,
-        a->eps);
+        reinterpret_cast<__nv_bfloat16*>(a->y), a->y_f32, a->sum_out, reinterpret_cast<float2*>(a->stats), a->err_flag,
+        a->tokens, a->seq_len, a->hidden, a->vocab, a->eps);
     return launch_status();
 }
 
@@ -506,6 +487,9 @@ int fame_rank_counts(const fame_rank_counts_args* a, void* workspace, size_t wor
     fame::sum_partials_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<const double*>(workspace), grid, a->ap_sum);
     return launch_status();
 }
+
+#include <math.h>
+#include "train_abi.inc"
 
 int fame_sigmoid_probs(const fame_sigmoid_probs_args* a, void*, size_t, fame_stream_t stream) {
     if (a == nullptr || a->logits == nullptr || a->probs == nullptr) return FAME_ERR_NULLPTR;

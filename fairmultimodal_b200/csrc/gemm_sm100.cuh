@@ -1,19 +1,23 @@
 // K1: bf16 GEMM on tcgen05 tensor cores, accumulators in TMEM, operands staged by TMA.
 //
-//   Y[M,N] = act( X[M,K] . W[N,K]^T + bias[N] ) (+ residual[M,N])
+//   C[b][m, n] = epi( sum_k A[b](m, k) * B[b](n, k) )        b = optional 2-level batch index (b0, b1)
 //
-// Replaces every nn.Linear on the FAME hot path (reference: HF modeling_bert.py Q/K/V, attention-output,
-// intermediate and output dense layers used through 10_FAME.py:140,199; nn.MultiheadAttention in/out
-// projections and linear1/linear2 of nn.TransformerEncoderLayer, 10_FAME.py:214).
+// One kernel serves the forward, data-gradient and weight-gradient products of every nn.Linear on the FAME hot path
+// and the five batched products of the attention backward, through the operand "major":
+//   K-major  operand: stored [rows = m or n, cols = k]  (k contiguous)  -- forward X and W, dY in dgrad
+//   MN-major operand: stored [rows = k, cols = m or n]  (m/n contiguous) -- W in dgrad, dY and X in wgrad, V/K/Q/dO
+//   forward  Y  = X . W^T        A = X  (K),  B = W  (K)          HF modeling_bert.py:179-181,295,340,353; 10_FAME.py:214
+//   dgrad    dX = dY . W         A = dY (K),  B = W  (MN)
+//   wgrad    dW = dY^T . X       A = dY (MN), B = X  (MN)         contraction over tokens
+// Epilogue: + bias[n], GELU(erf) / ReLU, + residual (bf16 or f32) or ReLU-mask by another tensor; bf16 output through
+// swizzled smem + TMA store, f32 output (small matrices, weight gradients) through direct vector stores.
 //
 // Structure (one persistent CTA per SM, 384 threads):
 //   warp 0   : TMA producer   (one lane)  global -> smem ring, kStages x {A 128x64, B 256x64} bf16, SW128
 //   warp 1   : MMA issuer     (one lane)  tcgen05.mma 128x256x16, 4 per k-block, commit -> frees ring slot
 //   warp 2   : TMEM allocator (512 columns = 2 accumulator buffers of 256 f32 columns)
-//   warps 4-11: epilogue, two warpgroups of 128 threads, each owning 128 accumulator columns:
-//              TMEM -> registers -> bias/act/residual -> bf16 -> swizzled smem box (128 rows x 64 cols) ->
-//              TMA store (coalesced, asynchronous).  Runs concurrently with the next tile's MMAs.
-//              (f32 output, used only for tiny matrices, is written with direct vector stores instead.)
+//   warps 4-11: epilogue, two warpgroups of 128 threads, each owning 128 accumulator columns; runs concurrently
+//              with the next tile's MMAs (double-buffered TMEM).
 #pragma once
 #include "sm100_ptx.cuh"
 
@@ -27,21 +31,25 @@ constexpr int kGemmABytes = kGemmBM * kGemmBK * 2;  // 16 KB
 constexpr int kGemmBBytes = kGemmBN * kGemmBK * 2;  // 32 KB
 constexpr int kGemmStageBytes = kGemmABytes + kGemmBBytes;
 constexpr int kGemmCBoxBytes = 128 * 64 * 2;        // 16 KB staging box per epilogue warpgroup
+constexpr int kGemmSubTile = 64 * 64 * 2;           // 8 KB: one {64 mn x 64 k} box of an MN-major operand
 constexpr int kGemmThreads = 384;
 constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + 2 * kGemmCBoxBytes + 1024 /*align slack*/ + 256;
 
 enum { kActNone = 0, kActGelu = 1, kActRelu = 2 };
+enum { kResNone = 0, kResAddBf16 = 1, kResAddF32 = 2, kResReluMaskBf16 = 3 };
 
 struct GemmParams {
-    int M, N, K;
+    int M, N, K;                    // per-batch output rows / cols and contraction length
+    int nb0, nb1;                   // batch counts (1, 1 when unbatched); tile -> (b0, b1, m_blk, n_blk)
     const float* bias;              // [N] or nullptr
-    const void* residual;           // bf16 or f32 [M, ldr] or nullptr
-    long long ldr;
-    int res_f32;
-    void* y;                        // bf16 or f32 [M, ldy]
-    long long ldy;
+    const void* residual;           // [nb0][nb1][M, ldr] or nullptr
+    long long ldr, rs_b0, rs_b1;    // leading dimension and batch strides of the residual (elements)
+    int res_mode;
+    void* y;                        // f32 output only: [nb0][nb1][M, ldy]; bf16 output goes through tmap_c
+    long long ldy, ys_b0, ys_b1;
     int act;
     int y_f32;
+    float alpha;                    // scales the accumulator before bias / activation
 };
 
 // erf-GELU (HF "gelu", modeling_bert.py:339-342):  0.5 x (1 + erf(x / sqrt 2)).
@@ -67,6 +75,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaf(h, xc * q, h);
 }
 
+template <bool kAMn, bool kBMn>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
@@ -88,7 +97,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
     const int m_tiles = (p.M + kGemmBM - 1) / kGemmBM;
     const int n_tiles = (p.N + kGemmBN - 1) / kGemmBN;
-    const int num_tiles = m_tiles * n_tiles;
+    const int tiles_per_batch = m_tiles * n_tiles;
+    const int num_tiles = tiles_per_batch * p.nb0 * p.nb1;
     const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
 
     if (warp == 0 && lane == 0) {
@@ -122,14 +132,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                const int bidx = tile / tiles_per_batch, t2 = tile % tiles_per_batch;
+                const int b0 = bidx / p.nb1, b1 = bidx % p.nb1;
+                const int m_blk = t2 / n_tiles, n_blk = t2 % n_tiles;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], kGemmStageBytes);
-                    tma_load_2d(smem_a + stage * kGemmABytes, &tmap_a, &full_bar[stage], kb * kGemmBK,
-                                m_blk * kGemmBM, kEvictNormal);
-                    tma_load_2d(smem_b + stage * kGemmBBytes, &tmap_b, &full_bar[stage], kb * kGemmBK,
-                                n_blk * kGemmBN, kEvictLast);
+                    uint8_t* sa = smem_a + stage * kGemmABytes;
+                    uint8_t* sb = smem_b + stage * kGemmBBytes;
+                    if (kAMn) {
+#pragma unroll
+                        for (int s = 0; s < kGemmBM / 64; ++s)
+                            tma_load_4d(sa + s * kGemmSubTile, &tmap_a, &full_bar[stage], m_blk * kGemmBM + 64 * s,
+                                        kb * kGemmBK, b1, b0, kEvictNormal);
+                    } else {
+                        tma_load_4d(sa, &tmap_a, &full_bar[stage], kb * kGemmBK, m_blk * kGemmBM, b1, b0, kEvictNormal);
+                    }
+                    if (kBMn) {
+#pragma unroll
+                        for (int s = 0; s < kGemmBN / 64; ++s)
+                            tma_load_4d(sb + s * kGemmSubTile, &tmap_b, &full_bar[stage], n_blk * kGemmBN + 64 * s,
+                                        kb * kGemmBK, b1, b0, kEvictLast);
+                    } else {
+                        tma_load_4d(sb, &tmap_b, &full_bar[stage], kb * kGemmBK, n_blk * kGemmBN, b1, b0, kEvictLast);
+                    }
                     if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -137,7 +163,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     } else if (warp == 1) {
         if (lane == 0) {
             // ------------------------------------------------ MMA issuer
-            constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, kGemmBN, 0, 0);
+            constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, kGemmBN, kAMn ? 1 : 0, kBMn ? 1 : 0);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -153,8 +179,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     const uint32_t b_addr = smem_u32(smem_b + stage * kGemmBBytes);
 #pragma unroll
                     for (int k = 0; k < kGemmBK / 16; ++k) {
-                        const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-                        const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                        // K-major: 16 k-elements = 32 B inside the 128 B row; SBO = 8 rows.  MN-major: 16 k-rows of
+                        // 128 B = 2 KB; LBO = distance between 64-wide MN sub-tiles, SBO = 8 k-rows.
+                        const uint64_t adesc = kAMn ? make_smem_desc_sw128(a_addr + k * 2048, kGemmSubTile, 1024)
+                                                    : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                        const uint64_t bdesc = kBMn ? make_smem_desc_sw128(b_addr + k * 2048, kGemmSubTile, 1024)
+                                                    : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
                         umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
                     }
                     umma_commit(&empty_bar[stage]);
@@ -176,7 +206,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            const int bidx = tile / tiles_per_batch, t2 = tile % tiles_per_batch;
+            const int b0 = bidx / p.nb1, b1 = bidx % p.nb1;
+            const int m_blk = t2 / n_tiles, n_blk = t2 % n_tiles;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const int row = m_blk * kGemmBM + r_local;
@@ -194,8 +226,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        v[j] = __uint_as_float(r0[j]);
-                        v[32 + j] = __uint_as_float(r1[j]);
+                        v[j] = __uint_as_float(r0[j]) * p.alpha;
+                        v[32 + j] = __uint_as_float(r1[j]) * p.alpha;
                     }
                 }
                 if (cc == 1) {
@@ -221,9 +253,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                     for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.0f);
                 }
-                if (p.residual != nullptr && row_ok) {
-                    if (p.res_f32) {
-                        const float* rp = reinterpret_cast<const float*>(p.residual) + (long long)row * p.ldr + col0;
+                if (p.res_mode != kResNone && row_ok) {
+                    const long long roff = (long long)b0 * p.rs_b0 + (long long)b1 * p.rs_b1 + (long long)row * p.ldr + col0;
+                    if (p.res_mode == kResAddF32) {
+                        const float* rp = reinterpret_cast<const float*>(p.residual) + roff;
 #pragma unroll
                         for (int j = 0; j < 64; j += 4) {
                             if (col0 + j < p.N) {
@@ -232,8 +265,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             }
                         }
                     } else {
-                        const __nv_bfloat16* rp =
-                            reinterpret_cast<const __nv_bfloat16*>(p.residual) + (long long)row * p.ldr + col0;
+                        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
+                        const bool mask = p.res_mode == kResReluMaskBf16;
 #pragma unroll
                         for (int j = 0; j < 64; j += 8) {
                             if (col0 + j < p.N) {
@@ -242,8 +275,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                                 for (int t = 0; t < 4; ++t) {
                                     const float2 f = __bfloat1622float2(h2[t]);
-                                    v[j + 2 * t] += f.x;
-                                    v[j + 2 * t + 1] += f.y;
+                                    if (mask) {  // ReLU backward: keep the gradient where the saved activation is > 0
+                                        v[j + 2 * t] = f.x > 0.f ? v[j + 2 * t] : 0.f;
+                                        v[j + 2 * t + 1] = f.y > 0.f ? v[j + 2 * t + 1] : 0.f;
+                                    } else {
+                                        v[j + 2 * t] += f.x;
+                                        v[j + 2 * t + 1] += f.y;
+                                    }
                                 }
                             }
                         }
@@ -251,7 +289,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
                 if (p.y_f32) {
                     if (row_ok) {
-                        float* yp = reinterpret_cast<float*>(p.y) + (long long)row * p.ldy + col0;
+                        float* yp = reinterpret_cast<float*>(p.y) + (long long)b0 * p.ys_b0 + (long long)b1 * p.ys_b1 +
+                                    (long long)row * p.ldy + col0;
 #pragma unroll
                         for (int j = 0; j < 64; j += 4) {
                             if (col0 + j < p.N)
@@ -274,7 +313,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     fence_proxy_async_smem();
                     named_bar_sync(1 + half, 128);
                     if (wg_leader) {
-                        tma_store_2d(&tmap_c, cbox, col0, m_blk * kGemmBM);
+                        tma_store_4d(&tmap_c, cbox, col0, m_blk * kGemmBM, b1, b0);
                         tma_store_commit();
                     }
                 }

@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(kLnWarpsPerBlock * 32)
 bert_embed_ln_kernel(const long long* __restrict__ ids, const float* __restrict__ word,
                      const float* __restrict__ pos, const float* __restrict__ type0,
                      const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
-                     float* __restrict__ y_f32, int* __restrict__ err_flag, int tokens, int seq_len, int hidden, int vocab,
-                     float eps) {
+                     float* __restrict__ y_f32, float* __restrict__ sum_out, float2* __restrict__ stats,
+                     int* __restrict__ err_flag, int tokens, int seq_len, int hidden, int vocab, float eps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * kLnWarpsPerBlock + warp;
     if (t >= tokens) return;
@@ -148,6 +148,7 @@ bert_embed_ln_kernel(const long long* __restrict__ ids, const float* __restrict_
             v[i].z = (w.z + ty.z) + po.z;
             v[i].w = (w.w + ty.w) + po.w;
             s += v[i].x + v[i].y + v[i].z + v[i].w;
+            if (sum_out != nullptr) reinterpret_cast<float4*>(sum_out + (long long)t * hidden)[ch] = v[i];
         }
     }
     const float mean = warp_sum(s) / (float)hidden;
@@ -160,6 +161,7 @@ bert_embed_ln_kernel(const long long* __restrict__ ids, const float* __restrict_
         }
     }
     const float rstd = rsqrtf(warp_sum(q) / (float)hidden + eps);
+    if (stats != nullptr && lane == 0) stats[t] = make_float2(mean, rstd);
     __nv_bfloat16* yr = y + (long long)t * hidden;
 #pragma unroll
     for (int i = 0; i < kEmbMaxChunks; ++i) {

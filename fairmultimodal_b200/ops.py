@@ -118,8 +118,10 @@ def layernorm(x, gamma, beta, eps, out=None, out_f32=None, want_f32=False, stats
     return (out, out_f32) if want_f32 else out
 
 
-def bert_embed(ids, word, pos, type_emb, gamma, beta, eps, seq_len, err_flag=None, out_f32=None):
-    """ids int64 [tokens] (flattened [chunks, seq_len]) -> bf16 [tokens, hidden] (+ optional f32 copy)."""
+def bert_embed(ids, word, pos, type_emb, gamma, beta, eps, seq_len, err_flag=None, out_f32=None, sum_out=None,
+               stats=None):
+    """ids int64 [tokens] (flattened [chunks, seq_len]) -> bf16 [tokens, hidden] (+ optional f32 copy, pre-LN sum
+    and {mean, rstd} for the backward pass)."""
     _cuda(ids, "ids", torch.int64)
     ids = ids.contiguous().view(-1)
     hidden = word.shape[1]
@@ -127,6 +129,10 @@ def bert_embed(ids, word, pos, type_emb, gamma, beta, eps, seq_len, err_flag=Non
     a = _lib.BertEmbedArgs()
     if out_f32 is not None:
         a.y_f32 = _cuda(out_f32, "out_f32", torch.float32).data_ptr()
+    if sum_out is not None:
+        a.sum_out = _cuda(sum_out, "sum_out", torch.float32).data_ptr()
+    if stats is not None:
+        a.stats = _cuda(stats, "stats", torch.float32).data_ptr()
     a.ids = ids.data_ptr()
     a.word = _cuda(word, "word", torch.float32).data_ptr()
     a.pos = _cuda(pos, "pos", torch.float32).data_ptr()

@@ -1,0 +1,162 @@
+"""Torch-tensor wrappers over the backward / optimizer entry points of the C ABI (see include/fame_b200.h)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, ops
+from ._lib import AUX_ADD_BF16, AUX_ADD_F32, AUX_NONE, AUX_RELU_MASK_BF16, DT_BF16, DT_F32  # noqa: F401
+
+
+def _dt(t):
+    return DT_F32 if t.dtype == torch.float32 else DT_BF16
+
+
+def _flat(name, *args):
+    ops.LAUNCHES += 1
+    if ops._TRACE is None:
+        _lib.call_flat(name, ops._stream(), *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.call_flat(name, ops._stream(), *args)
+    e1.record()
+    ops._TRACE.append((name, "", e0, e1, 0.0))
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def gemm_ex(a, b, y, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldy=None, bias=None, aux=None,
+            aux_mode=AUX_NONE, ld_aux=0, act=0, alpha=1.0, nb0=1, nb1=1, sa=(0, 0), sb=(0, 0), sy=(0, 0), saux=(0, 0),
+            n_valid=0, a_off=0, b_off=0, y_off=0, aux_off=0, tag=""):
+    """General tcgen05 GEMM (fame_gemm_ex).  a / b / y / aux are tensors (any shape); geometry is explicit:
+    leading dimensions, element offsets and batch strides (b0, b1) in elements."""
+    g = _lib.GemmExArgs()
+    g.a.ptr = a.data_ptr() + 2 * a_off
+    g.a.ld, g.a.stride_b0, g.a.stride_b1, g.a.mn_major = lda, sa[0], sa[1], int(a_mn)
+    g.b.ptr = b.data_ptr() + 2 * b_off
+    g.b.ld, g.b.stride_b0, g.b.stride_b1, g.b.mn_major = ldb, sb[0], sb[1], int(b_mn)
+    g.bias = _p(bias)
+    if aux is not None:
+        g.aux = aux.data_ptr() + aux.element_size() * aux_off
+        g.ld_aux, g.aux_stride_b0, g.aux_stride_b1, g.aux_mode = ld_aux, saux[0], saux[1], aux_mode
+    g.y = y.data_ptr() + y.element_size() * y_off
+    g.ldy, g.y_stride_b0, g.y_stride_b1, g.y_dtype = ldy, sy[0], sy[1], _dt(y)
+    g.M, g.N, g.K, g.nb0, g.nb1 = M, N, K, nb0, nb1
+    g.act, g.alpha, g.n_valid = act, alpha, n_valid
+    ops._call("fame_gemm_ex", g, 2.0 * M * N * K * nb0 * nb1, tag)
+    return y
+
+
+def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, aux=None, aux_mode=AUX_NONE):
+    """dX[T, K] = dY[T, N] @ W[N, K]  (+ aux residual gradient, or ReLU-masked by aux)."""
+    T, N = dy.shape
+    K = w.shape[1]
+    if out is None:
+        out = torch.empty((T, K), device=dy.device, dtype=out_dtype)
+    return gemm_ex(dy, w, out, T, K, N, a_mn=False, b_mn=True, lda=dy.stride(0), ldb=w.stride(0), ldy=out.stride(0),
+                   aux=aux, aux_mode=aux_mode, ld_aux=aux.stride(0) if aux is not None else 0, tag="dgrad")
+
+
+def linear_wgrad(dy, x, out):
+    """dW[N, K] = dY[T, N]^T @ X[T, K] -> f32 `out` (a view into the flat gradient buffer)."""
+    T, N = dy.shape
+    K = x.shape[1]
+    return gemm_ex(dy, x, out, N, K, T, a_mn=True, b_mn=True, lda=dy.stride(0), ldb=x.stride(0), ldy=out.stride(0),
+                   tag="wgrad")
+
+
+def layernorm_bwd(x, dy, stats, gamma, dgamma, dbeta, want_bf16=True, want_f32=False):
+    rows, cols = x.shape
+    dxb = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    dxf = torch.empty((rows, cols), device=x.device, dtype=torch.float32) if want_f32 else None
+    _flat("fame_layernorm_bwd", x.data_ptr(), _dt(x), dy.data_ptr(), _dt(dy), stats.data_ptr(), gamma.data_ptr(),
+          _p(dxb), _p(dxf), _p(dgamma), _p(dbeta), rows, cols)
+    return dxb, dxf
+
+
+def gelu_fwd(pre):
+    h = torch.empty_like(pre)
+    _flat("fame_gelu_fwd", pre.data_ptr(), h.data_ptr(), pre.numel())
+    return h
+
+
+def gelu_bwd(pre, dh):
+    d = torch.empty_like(pre)
+    _flat("fame_gelu_bwd", pre.data_ptr(), dh.data_ptr(), d.data_ptr(), pre.numel())
+    return d
+
+
+def colsum(x, out):
+    rows, cols = x.shape
+    _flat("fame_colsum", x.data_ptr(), _dt(x), x.stride(0), rows, cols, out.data_ptr())
+
+
+def seq_mean_bwd(dout, batch, L):
+    cols = dout.shape[1]
+    dx = torch.empty((batch * L, cols), device=dout.device, dtype=torch.bfloat16)
+    _flat("fame_seq_mean_bwd", dout.data_ptr(), dx.data_ptr(), batch, L, cols)
+    return dx
+
+
+def lab_embed_bwd(dx, lab, dpos, dw, dbias):
+    B, L = lab.shape
+    _flat("fame_lab_embed_bwd", dx.data_ptr(), lab.data_ptr(), dpos.data_ptr(), dw.data_ptr(), dbias.data_ptr(), B, L,
+          dpos.shape[1])
+
+
+def attn_bwd_softmax(s, dp, rows, seq, ld, scale):
+    p = torch.empty((rows, ld), device=s.device, dtype=torch.bfloat16)
+    ds = torch.empty((rows, ld), device=s.device, dtype=torch.bfloat16)
+    _flat("fame_attn_bwd_softmax", s.data_ptr(), dp.data_ptr(), p.data_ptr(), ds.data_ptr(), rows, seq, ld, float(scale))
+    return p, ds
+
+
+def bert_embed_bwd(d_sum, ids, dword, dpos, dtype0, seq, pad_idx=0):
+    tokens, hidden = d_sum.shape
+    _flat("fame_bert_embed_bwd", d_sum.data_ptr(), ids.data_ptr(), dword.data_ptr(), dpos.data_ptr(), dtype0.data_ptr(),
+          tokens, seq, hidden, dword.shape[0], pad_idx)
+
+
+def demo_add_bwd(dout, ids, dtables):
+    B, hidden = dout.shape
+    _flat("fame_demo_add_bwd", dout.data_ptr(), ids[0].data_ptr(), ids[1].data_ptr(), ids[2].data_ptr(),
+          ids[3].data_ptr(), dtables[0].data_ptr(), dtables[1].data_ptr(), dtables[2].data_ptr(), dtables[3].data_ptr(),
+          dtables[0].shape[0], dtables[1].shape[0], dtables[2].shape[0], dtables[3].shape[0], B, hidden)
+
+
+def sgemm(a, sam, sak, b, sbk, sbn, c, M, N, K, alpha=1.0, accumulate=False):
+    """C[M,N] = alpha * sum_k A(m,k) B(k,n) (+C) in fp32 with explicit element strides."""
+    _flat("fame_sgemm_small", a.data_ptr(), sam, sak, b.data_ptr(), sbk, sbn, c.data_ptr(), c.stride(0), M, N, K,
+          float(alpha), int(accumulate))
+    return c
+
+
+def fusion_bwd_hidden(dlogits, w4, pre):
+    B = dlogits.shape[0]
+    dhid = torch.empty((B, 512), device=dlogits.device, dtype=torch.float32)
+    _flat("fame_fusion_bwd_hidden", dlogits.data_ptr(), w4.data_ptr(), pre.data_ptr(), dhid.data_ptr(), B)
+    return dhid
+
+
+def fusion_bwd_gate(dgated, proj, sig_w, w_mod, lambda_l1, dsig):
+    B = dgated.shape[0]
+    dproj = torch.empty((B, 768), device=dgated.device, dtype=torch.float32)
+    _flat("fame_fusion_bwd_gate", dgated.data_ptr(), proj.data_ptr(), sig_w.data_ptr(), float(w_mod[0]), float(w_mod[1]),
+          float(w_mod[2]), float(lambda_l1), dproj.data_ptr(), dsig.data_ptr(), B)
+    return dproj
+
+
+def grad_sumsq(g, out):
+    _flat("fame_grad_sumsq", g.data_ptr(), g.numel(), out.data_ptr())
+
+
+def clip_adamw(p, g, m, v, sumsq, max_norm, lr, beta1, beta2, eps, weight_decay, step, grad_norm_out=None):
+    _flat("fame_clip_adamw", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), sumsq.data_ptr(),
+          float(max_norm), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+          _p(grad_norm_out))
+
+
+def cast_bf16(x, y):
+    _flat("fame_cast_bf16", x.data_ptr(), y.data_ptr(), x.numel())

@@ -1,0 +1,418 @@
+"""FAME training step on the B200 (drop-in for ``train_step``, 10_FAME.py:401-449).
+
+The reference runs  forward -> BCE + 10*lambda*LEDDI + L1 -> total_loss.backward() -> clip_grad_norm_(1.0) ->
+AdamW.step()  through torch.autograd.  Here the same step is an explicit sequence of sm_100a kernels:
+
+  forward   demo tower (12-layer BERT over one token, fp32 residual stream), lab tower (2 post-norm layers, flash
+            attention head_dim 96), fusion head -- activations needed by the backward are kept
+  loss      fame_loss_stats -> [SUM all-reduce of 104 int64 when data parallel] -> fame_loss_fwd_bwd (loss, dlogits)
+  backward  fusion head (fp32), lab tower and demo tower: dgrad / wgrad tensor-core GEMMs (fame_gemm_ex with MN-major
+            operands, no transposed copies), LayerNorm / GELU / softmax backward kernels, batched attention backward
+  update    [all-reduce of the flat gradient buffer when data parallel] -> squared norm -> fused clip + AdamW
+
+All trainable parameters live in ONE flat fp32 buffer (``FlatTrainState``): the nn.Parameters of the model are views
+into it, their ``.grad`` are views into a flat gradient buffer, AdamW state is two more flat buffers and a bf16 shadow
+feeds the tensor cores.  Parameters that receive no gradient in the reference (the three modality classifiers and
+the BERT pooler: they are not on the loss path, 10_FAME.py:444) are left out, exactly as torch skips ``grad is None``.
+
+Dropout: the reference trains with p = 0.1 everywhere; this implementation currently runs the training step with
+dropout disabled (the parity configuration of SURVEY.md 7.2).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+from . import ops_train as T
+
+NO_GRAD_PREFIXES = ("classifier_demo.", "classifier_lab.", "classifier_text.", "behrt_demo.bert.pooler.")
+ATTR_IDX = (2, 4, 5)          # age_ids, ethnicity_ids, insurance_ids inside the 9-tensor batch (10_FAME.py:431)
+
+
+class FlatTrainState:
+    """Flat parameter / gradient / AdamW-state buffers for one MultimodalTransformer_EDDI_Sigmoid."""
+
+    def __init__(self, model):
+        self.model = model
+        dev = next(model.parameters()).device
+        named = [(n, p) for n, p in model.named_parameters() if not n.startswith(NO_GRAD_PREFIXES)]
+        self.offsets, off = {}, 0
+        for n, p in named:
+            self.offsets[n] = off
+            off += (p.numel() + 7) // 8 * 8                      # 32-byte aligned segments
+        self.n = off
+        self.p = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.g = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.pb = torch.zeros(off, device=dev, dtype=torch.bfloat16)
+        self.views, self.gviews, self.bviews = {}, {}, {}
+        with torch.no_grad():
+            for n, p in named:
+                o, k = self.offsets[n], p.numel()
+                self.p[o:o + k].copy_(p.detach().reshape(-1).float())
+                p.data = self.p[o:o + k].view(p.shape)           # the module parameter now aliases the flat buffer
+                p.grad = self.g[o:o + k].view(p.shape)
+                self.views[n], self.gviews[n] = p.data, p.grad
+                self.bviews[n] = self.pb[o:o + k].view(p.shape)
+        self.step = 0
+        self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.grad_norm = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.refresh_bf16()
+
+    def refresh_bf16(self):
+        T.cast_bf16(self.p, self.pb)
+
+    def w(self, name):          # bf16 shadow (GEMM operand)
+        return self.bviews[name]
+
+    def f(self, name):          # fp32 master
+        return self.views[name]
+
+    def gr(self, name):         # fp32 gradient
+        return self.gviews[name]
+
+    def zero_grad(self):
+        self.g.zero_()
+
+    def clip_and_step(self, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0):
+        self.step += 1
+        self.sumsq.zero_()
+        T.grad_sumsq(self.g, self.sumsq)
+        T.clip_adamw(self.p, self.g, self.m, self.v, self.sumsq, max_norm, lr, betas[0], betas[1], eps, weight_decay,
+                     self.step, self.grad_norm)
+        self.refresh_bf16()
+        self.invalidate_caches()
+
+    def invalidate_caches(self):
+        """The kernels update the flat buffer behind torch's back (no version bump): drop the inference-path
+        packed-weight caches so the next eval forward re-reads the parameters."""
+        m = self.model
+        m._packed = None
+        m.behrt_lab._packed = None
+        m.behrt_demo.bert._packed = None
+
+
+def get_state(model) -> FlatTrainState:
+    st = getattr(model, "_fame_train_state", None)
+    if st is None or st.model is not model:
+        st = FlatTrainState(model)
+        object.__setattr__(model, "_fame_train_state", st)
+    return st
+
+
+# ------------------------------------------------------------------------------------------------ demo tower
+def _demo_forward(st, model, ids, age, gender, eth, ins):
+    """BEHRTModel_Demo.forward for training (sequence length 1): returns (demo_emb f32 [B,768], saved)."""
+    pre = "behrt_demo.bert."
+    B, S = ids.shape
+    if S != 1:
+        raise NotImplementedError("training path of the demographic encoder handles the reference's length-1 input")
+    H = 768
+    eps = model.behrt_demo.bert.config.layer_norm_eps
+    dev = ids.device
+    e = pre + "embeddings."
+    esum = torch.empty((B, H), device=dev, dtype=torch.float32)
+    estats = torch.empty((B, 2), device=dev, dtype=torch.float32)
+    x32 = torch.empty((B, H), device=dev, dtype=torch.float32)
+    xb = ops.bert_embed(ids.to(torch.int64), st.f(e + "word_embeddings.weight"), st.f(e + "position_embeddings.weight"),
+                        st.f(e + "token_type_embeddings.weight")[0], st.f(e + "LayerNorm.weight"),
+                        st.f(e + "LayerNorm.bias"), eps, S, out_f32=x32, sum_out=esum, stats=estats)
+    saved = {"esum": esum, "estats": estats, "layers": [], "ids": ids.to(torch.int64).contiguous().view(-1)}
+    for i in range(12):
+        p = f"{pre}encoder.layer.{i}."
+        s = {"xb": xb}
+        v = ops.gemm_bias_act(xb, st.w(p + "attention.self.value.weight"), st.f(p + "attention.self.value.bias"))
+        t1 = ops.gemm_bias_act(v, st.w(p + "attention.output.dense.weight"), st.f(p + "attention.output.dense.bias"),
+                               residual=x32, out_dtype=torch.float32)
+        st1 = torch.empty((B, 2), device=dev, dtype=torch.float32)
+        x1b, x1f = ops.layernorm(t1, st.f(p + "attention.output.LayerNorm.weight"),
+                                 st.f(p + "attention.output.LayerNorm.bias"), eps, want_f32=True, stats=st1)
+        pa = ops.gemm_bias_act(x1b, st.w(p + "intermediate.dense.weight"), st.f(p + "intermediate.dense.bias"))
+        h = T.gelu_fwd(pa)
+        t2 = ops.gemm_bias_act(h, st.w(p + "output.dense.weight"), st.f(p + "output.dense.bias"), residual=x1f,
+                               out_dtype=torch.float32)
+        st2 = torch.empty((B, 2), device=dev, dtype=torch.float32)
+        xb, x32 = ops.layernorm(t2, st.f(p + "output.LayerNorm.weight"), st.f(p + "output.LayerNorm.bias"), eps,
+                                want_f32=True, stats=st2)
+        s.update(v=v, t1=t1, st1=st1, x1b=x1b, pre=pa, h=h, t2=t2, st2=st2)
+        saved["layers"].append(s)
+    did = [age, gender, eth, ins]
+    tabs = [st.f(f"behrt_demo.{n}_embedding.weight") for n in ("age", "gender", "ethnicity", "insurance")]
+    saved["demo_ids"] = [t.to(torch.int64).contiguous() for t in did]
+    return ops.demo_add(x32, H, saved["demo_ids"], tabs), saved
+
+
+def _lin_bwd(st, wname, bname, dy_bf16, x_bf16, colsum_src=None):
+    """Bias and weight gradients of y = x W^T + b into the flat gradient buffer."""
+    T.colsum(colsum_src if colsum_src is not None else dy_bf16, st.gr(bname))
+    T.linear_wgrad(dy_bf16, x_bf16, st.gr(wname))
+
+
+def _demo_backward(st, model, saved, ddemo):
+    pre = "behrt_demo.bert."
+    tabs_g = [st.gr(f"behrt_demo.{n}_embedding.weight") for n in ("age", "gender", "ethnicity", "insurance")]
+    T.demo_add_bwd(ddemo, saved["demo_ids"], tabs_g)
+    dx = ddemo                                                      # f32 [B,768]: gradient of the last hidden state
+    for i in reversed(range(12)):
+        p = f"{pre}encoder.layer.{i}."
+        s = saved["layers"][i]
+        dt2b, dt2f = T.layernorm_bwd(s["t2"], dx, s["st2"], st.f(p + "output.LayerNorm.weight"),
+                                     st.gr(p + "output.LayerNorm.weight"), st.gr(p + "output.LayerNorm.bias"),
+                                     want_bf16=True, want_f32=True)
+        _lin_bwd(st, p + "output.dense.weight", p + "output.dense.bias", dt2b, s["h"], colsum_src=dt2f)
+        dh = T.linear_dgrad(dt2b, st.w(p + "output.dense.weight"))
+        dpre = T.gelu_bwd(s["pre"], dh)
+        _lin_bwd(st, p + "intermediate.dense.weight", p + "intermediate.dense.bias", dpre, s["x1b"])
+        dx1 = T.linear_dgrad(dpre, st.w(p + "intermediate.dense.weight"), out_dtype=torch.float32, aux=dt2f,
+                             aux_mode=T.AUX_ADD_F32)
+        dt1b, dt1f = T.layernorm_bwd(s["t1"], dx1, s["st1"], st.f(p + "attention.output.LayerNorm.weight"),
+                                     st.gr(p + "attention.output.LayerNorm.weight"),
+                                     st.gr(p + "attention.output.LayerNorm.bias"), want_bf16=True, want_f32=True)
+        _lin_bwd(st, p + "attention.output.dense.weight", p + "attention.output.dense.bias", dt1b, s["v"], colsum_src=dt1f)
+        dv = T.linear_dgrad(dt1b, st.w(p + "attention.output.dense.weight"))
+        _lin_bwd(st, p + "attention.self.value.weight", p + "attention.self.value.bias", dv, s["xb"])
+        # one key per sequence: softmax == 1, so query / key receive exactly zero gradient (their .grad stays 0 and
+        # AdamW still applies weight decay to them, as in the reference)
+        dx = T.linear_dgrad(dv, st.w(p + "attention.self.value.weight"), out_dtype=torch.float32, aux=dt1f,
+                            aux_mode=T.AUX_ADD_F32)
+    e = pre + "embeddings."
+    _, dsum = T.layernorm_bwd(saved["esum"], dx, saved["estats"], st.f(e + "LayerNorm.weight"),
+                              st.gr(e + "LayerNorm.weight"), st.gr(e + "LayerNorm.bias"), want_bf16=False, want_f32=True)
+    T.bert_embed_bwd(dsum, saved["ids"], st.gr(e + "word_embeddings.weight"), st.gr(e + "position_embeddings.weight"),
+                     st.gr(e + "token_type_embeddings.weight")[0], 1, pad_idx=0)
+
+
+# ------------------------------------------------------------------------------------------------ lab tower
+def _lab_forward(st, model, lab):
+    pre = "behrt_lab."
+    B, L = lab.shape
+    H, nh = 768, model.behrt_lab.nhead
+    lab = lab.float().contiguous()
+    x = ops.lab_embed(lab, st.f(pre + "token_embedding.weight")[:, 0].contiguous(), st.f(pre + "token_embedding.bias"),
+                      st.f(pre + "pos_embedding"))
+    saved = {"lab": lab, "layers": []}
+    dev = lab.device
+    for i, layer in enumerate(model.behrt_lab.transformer_encoder.layers):
+        p = f"{pre}transformer_encoder.layers.{i}."
+        s = {"x": x}
+        qkv = ops.gemm_bias_act(x, st.w(p + "self_attn.in_proj_weight"), st.f(p + "self_attn.in_proj_bias"))
+        ctx = ops.attn_fwd(qkv, B, L, nh, H // nh)
+        t1 = ops.gemm_bias_act(ctx, st.w(p + "self_attn.out_proj.weight"), st.f(p + "self_attn.out_proj.bias"), residual=x)
+        st1 = torch.empty((B * L, 2), device=dev, dtype=torch.float32)
+        x1 = ops.layernorm(t1, st.f(p + "norm1.weight"), st.f(p + "norm1.bias"), layer.norm1.eps, stats=st1)
+        h = ops.gemm_bias_act(x1, st.w(p + "linear1.weight"), st.f(p + "linear1.bias"), act=ops.ACT_RELU)
+        t2 = ops.gemm_bias_act(h, st.w(p + "linear2.weight"), st.f(p + "linear2.bias"), residual=x1)
+        st2 = torch.empty((B * L, 2), device=dev, dtype=torch.float32)
+        x = ops.layernorm(t2, st.f(p + "norm2.weight"), st.f(p + "norm2.bias"), layer.norm2.eps, stats=st2)
+        s.update(qkv=qkv, ctx=ctx, t1=t1, st1=st1, x1=x1, h=h, t2=t2, st2=st2)
+        saved["layers"].append(s)
+    return ops.seq_mean(x, B, L), saved
+
+
+def _attn_backward(qkv, dctx, B, L, nh, D):
+    """dqkv [T, 3*nh*D] bf16 from dctx [T, nh*D]: five batched tensor-core products + one softmax-backward kernel."""
+    dev = qkv.device
+    W = 3 * nh * D
+    HD = nh * D
+    ldp = (L + 7) // 8 * 8
+    rows = B * nh * L
+    s = torch.empty((rows, ldp), device=dev, dtype=torch.float32)
+    dp = torch.empty((rows, ldp), device=dev, dtype=torch.float32)
+    sq = (L * W, D)                 # (b0 = sequence, b1 = head) strides inside the packed qkv tensor
+    sc = (L * HD, D)                # same inside ctx / dctx
+    ss = (nh * L * ldp, L * ldp)    # inside the [B, nh, L, ldp] score tensors
+    # S = Q K^T, dP = dO V^T      (f32 out, padded to ldp columns)
+    T.gemm_ex(qkv, qkv, s, L, ldp, D, lda=W, ldb=W, ldy=ldp, nb0=B, nb1=nh, sa=sq, sb=sq, sy=ss, b_off=HD, n_valid=L,
+              tag="attn_s")
+    T.gemm_ex(dctx, qkv, dp, L, ldp, D, lda=HD, ldb=W, ldy=ldp, nb0=B, nb1=nh, sa=sc, sb=sq, sy=ss, b_off=2 * HD,
+              n_valid=L, tag="attn_dp")
+    p, ds = T.attn_bwd_softmax(s, dp, rows, L, ldp, D ** -0.5)
+    del s, dp
+    dqkv = torch.empty((B * L, W), device=dev, dtype=torch.bfloat16)
+    # dV = P^T dO, dK = dS^T Q  (A MN-major: stored [query rows, key cols]; B MN-major: stored [query rows, d cols])
+    T.gemm_ex(p, dctx, dqkv, L, D, L, a_mn=True, b_mn=True, lda=ldp, ldb=HD, ldy=W, nb0=B, nb1=nh, sa=ss, sb=sc, sy=sq,
+              y_off=2 * HD, tag="attn_dv")
+    T.gemm_ex(ds, qkv, dqkv, L, D, L, a_mn=True, b_mn=True, lda=ldp, ldb=W, ldy=W, nb0=B, nb1=nh, sa=ss, sb=sq, sy=sq,
+              y_off=HD, tag="attn_dk")
+    # dQ = dS K  (A K-major over keys; B = K stored [key rows, d cols] -> MN-major)
+    T.gemm_ex(ds, qkv, dqkv, L, D, L, a_mn=False, b_mn=True, lda=ldp, ldb=W, ldy=W, nb0=B, nb1=nh, sa=ss, sb=sq, sy=sq,
+              b_off=HD, tag="attn_dq")
+    return dqkv
+
+
+def _lab_backward(st, model, saved, dlab):
+    pre = "behrt_lab."
+    lab = saved["lab"]
+    B, L = lab.shape
+    H, nh = 768, model.behrt_lab.nhead
+    dx = T.seq_mean_bwd(dlab, B, L)                                  # bf16 [B*L, 768]
+    for i in reversed(range(len(saved["layers"]))):
+        p = f"{pre}transformer_encoder.layers.{i}."
+        s = saved["layers"][i]
+        dt2, _ = T.layernorm_bwd(s["t2"], dx, s["st2"], st.f(p + "norm2.weight"), st.gr(p + "norm2.weight"),
+                                 st.gr(p + "norm2.bias"))
+        _lin_bwd(st, p + "linear2.weight", p + "linear2.bias", dt2, s["h"])
+        dh = T.linear_dgrad(dt2, st.w(p + "linear2.weight"), aux=s["h"], aux_mode=T.AUX_RELU_MASK_BF16)
+        _lin_bwd(st, p + "linear1.weight", p + "linear1.bias", dh, s["x1"])
+        dx1 = T.linear_dgrad(dh, st.w(p + "linear1.weight"), aux=dt2, aux_mode=T.AUX_ADD_BF16)
+        dt1, _ = T.layernorm_bwd(s["t1"], dx1, s["st1"], st.f(p + "norm1.weight"), st.gr(p + "norm1.weight"),
+                                 st.gr(p + "norm1.bias"))
+        _lin_bwd(st, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", dt1, s["ctx"])
+        dctx = T.linear_dgrad(dt1, st.w(p + "self_attn.out_proj.weight"))
+        dqkv = _attn_backward(s["qkv"], dctx, B, L, nh, H // nh)
+        _lin_bwd(st, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", dqkv, s["x"])
+        dx = T.linear_dgrad(dqkv, st.w(p + "self_attn.in_proj_weight"), aux=dt1, aux_mode=T.AUX_ADD_BF16)
+    # token embedding: Linear(1, 768).weight has shape [768, 1] -> its gradient is the [768] vector
+    T.lab_embed_bwd(dx, lab, st.gr(pre + "pos_embedding"), st.gr(pre + "token_embedding.weight").view(-1),
+                    st.gr(pre + "token_embedding.bias"))
+
+
+# ------------------------------------------------------------------------------------------------ fusion head
+_PROJ = ("demo_projector.0.", "lab_projector.0.", "text_projector.0.")
+
+
+def _fusion_pack(st):
+    f = st.f
+    return dict(
+        wp_t=torch.stack([f(p + "weight").t().contiguous() for p in _PROJ]).contiguous(),
+        bp=torch.stack([f(p + "bias") for p in _PROJ]).contiguous(), sig_w=f("sig_weights"),
+        w3_t=f("fusion_mlp.0.weight").t().contiguous(), b3=f("fusion_mlp.0.bias"), w4=f("fusion_mlp.3.weight"),
+        b4=f("fusion_mlp.3.bias"))
+
+
+def _fusion_backward(st, fo, embs, dlogits, w_mod, lambda_l1):
+    """Returns (d demo_emb, d lab_emb) f32 [B,768]; writes every head gradient into the flat buffer."""
+    B = dlogits.shape[0]
+    dev = dlogits.device
+    f, g = st.f, st.gr
+    hid = torch.relu(fo["pre_relu"])                                           # [B,512]
+    # fusion_mlp.3: dW4[3,512] = dlogits^T hid ; db4 = colsum(dlogits)
+    T.sgemm(dlogits, 1, 3, hid, 512, 1, g("fusion_mlp.3.weight"), 3, 512, B)
+    T.colsum(dlogits, g("fusion_mlp.3.bias"))
+    dhid = T.fusion_bwd_hidden(dlogits, f("fusion_mlp.3.weight"), fo["pre_relu"])
+    # fusion_mlp.0: dW3[512,768] = dhid^T gated ; db3 ; dgated[B,768] = dhid W3
+    T.sgemm(dhid, 1, 512, fo["gated"], 768, 1, g("fusion_mlp.0.weight"), 512, 768, B)
+    T.colsum(dhid, g("fusion_mlp.0.bias"))
+    dgated = torch.empty((B, 768), device=dev, dtype=torch.float32)
+    T.sgemm(dhid, 512, 1, f("fusion_mlp.0.weight"), 768, 1, dgated, B, 768, 512)
+    dproj = T.fusion_bwd_gate(dgated, fo["proj"], f("sig_weights"), w_mod, lambda_l1, g("sig_weights"))
+    demb = []
+    for m, pn in enumerate(_PROJ):
+        dpm = dproj[:, 256 * m:256 * (m + 1)]                                   # [B,256] view, row stride 768
+        # dWp[256,768] = dpm^T emb ; dbp = colsum(dpm) ; demb = dpm Wp
+        T.sgemm(dpm, 1, 768, embs[m], 768, 1, g(pn + "weight"), 256, 768, B)
+        T.colsum(dpm, g(pn + "bias"))
+        if m < 2:                                                               # the text embedding is an input
+            de = torch.empty((B, 768), device=dev, dtype=torch.float32)
+            T.sgemm(dpm, 768, 1, f(pn + "weight"), 768, 1, de, B, 768, 256)
+            demb.append(de)
+    return demb
+
+
+# ------------------------------------------------------------------------------------------------ one optimisation step
+def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, group=None, want_outputs=False):
+    """Forward + loss + backward for one batch; gradients land in the flat buffer.  Returns loss_out f32 [4] (device)
+    = (total, bce, leddi, l1) of the GLOBAL batch."""
+    st = get_state(model)
+    (ids, mask, age, gender, eth, ins, lab, text, labels) = batch
+    st.zero_grad()
+    demo, sv_d = _demo_forward(st, model, ids, age, gender, eth, ins)
+    labe, sv_l = _lab_forward(st, model, lab)
+    text = text.float().contiguous()
+    pk = _fusion_pack(st)
+    if want_outputs:
+        cls = (model.classifier_demo, model.classifier_lab, model.classifier_text)
+        pk["wc"] = torch.stack([c.weight.detach().float() for c in cls]).contiguous()
+        pk["bc"] = torch.stack([c.bias.detach().float() for c in cls]).contiguous()
+    else:
+        pk["wc"] = pk["bc"] = pk["b4"]                                        # unused (mod_logits not requested)
+    fo = ops.fusion_fwd((demo, labe, text), pk, w_mod, want_mod_logits=want_outputs, want_intermediates=True)
+    labels = labels.float().contiguous()
+    attrs = [batch[i].to(torch.int64).contiguous() for i in ATTR_IDX]
+    stats = ops.loss_stats(fo["logits"], labels, attrs, pos_weight)
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(stats, group=group)                                    # 104 int64: global-batch statistics
+    loss, dlogits = ops.loss_fwd_bwd(fo["logits"], labels, attrs, pos_weight, stats, st.f("sig_weights"), lambda_edd,
+                                     lambda_l1)
+    if group is not None:
+        import torch.distributed as dist
+        # every rank adds lambda_l1 * sign(sig_weights) below; the gradient all-reduce is a SUM -> share it out
+        lambda_l1 = lambda_l1 / dist.get_world_size(group)
+    ddemo, dlab = _fusion_backward(st, fo, (demo, labe, text), dlogits, w_mod, lambda_l1)
+    _lab_backward(st, model, sv_l, dlab)
+    _demo_backward(st, model, sv_d, ddemo)
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(st.g, group=group)                                     # gradient SUM over ranks
+    return loss, fo
+
+
+def _hyper(optimizer):
+    g = optimizer.param_groups[0]
+    return dict(lr=g["lr"], weight_decay=g.get("weight_decay", 0.01), betas=tuple(g.get("betas", (0.9, 0.999))),
+                eps=g.get("eps", 1e-8))
+
+
+def _pos_weight(criterion, device):
+    pw = getattr(criterion, "pos_weight", None)
+    if pw is None:
+        return torch.ones(3, device=device, dtype=torch.float32)
+    return pw.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def train_step(model, dataloader, optimizer, device, criterion, beta=1.0, lambda_edd=0.8, lambda_l1=0.01, target=1.0,
+               threshold=0.5, old_eddi_weights=None, group=None):
+    """Drop-in for 10_FAME.py:401-449: one pass over ``dataloader``, one optimizer step per batch; returns
+    (running_loss, running_bce_loss) as python floats.  ``optimizer`` supplies lr / weight_decay / betas / eps (a
+    torch.optim.AdamW built on model.parameters(), as the reference does); the update itself is the fused
+    clip + AdamW kernel on the flat buffers.  ``target`` and ``threshold`` are ignored, as in the reference."""
+    model.train()
+    w_mod = model.modality_weights(old_eddi_weights)
+    pw = _pos_weight(criterion, device)
+    hp = _hyper(optimizer)
+    st = get_state(model)
+    acc = torch.zeros(2, device=device, dtype=torch.float32)
+    for batch in dataloader:
+        batch = [x.to(device, non_blocking=True) for x in batch]
+        loss, _ = forward_backward(model, batch, pw, lambda_edd, lambda_l1, w_mod, group=group)
+        st.clip_and_step(hp["lr"], hp["weight_decay"], hp["betas"], hp["eps"], max_norm=1.0)
+        acc += loss[:2]                                                        # accumulate on device, sync once
+    running_loss, running_bce = acc.tolist()
+    return running_loss, running_bce
+
+
+def fame_forward_train(model, batch8, w_mod, return_modality_logits, return_gated_vector, return_intermediate):
+    """Forward of the model in training mode called directly (outside train_step): outputs only, no autograd graph
+    (gradients are produced by train.forward_backward, not by torch.autograd)."""
+    st = get_state(model)
+    ids, mask, age, gender, eth, ins, lab, text = batch8
+    with torch.no_grad():
+        demo, _ = _demo_forward(st, model, ids, age, gender, eth, ins)
+        labe, _ = _lab_forward(st, model, lab)
+        pk = _fusion_pack(st)
+        cls = (model.classifier_demo, model.classifier_lab, model.classifier_text)
+        pk["wc"] = torch.stack([c.weight.detach().float() for c in cls]).contiguous()
+        pk["bc"] = torch.stack([c.bias.detach().float() for c in cls]).contiguous()
+        o = ops.fusion_fwd((demo, labe, text.float().contiguous()), pk, w_mod, want_mod_logits=return_modality_logits,
+                           want_intermediates=return_gated_vector or return_intermediate)
+    out = {"fused_logits": o["logits"], "dynamic_weights": {"demo": w_mod[0], "lab": w_mod[1], "text": w_mod[2]},
+           "sigmoid_weights": o["sig"]}
+    if return_modality_logits:
+        out["modality_logits"] = {"demo": o["mod_logits"][0], "lab": o["mod_logits"][1], "text": o["mod_logits"][2]}
+    if return_gated_vector:
+        out["gated_vector"] = o["gated"]
+    if return_intermediate:
+        out["fusion_pre_relu"] = o["pre_relu"]
+    return out
+
+
+def demo_forward_train(module, *a):
+    raise NotImplementedError("call the parent MultimodalTransformer_EDDI_Sigmoid (or train.train_step) in training mode")
+
+
+def lab_forward_train(module, *a):
+    raise NotImplementedError("call the parent MultimodalTransformer_EDDI_Sigmoid (or train.train_step) in training mode")

@@ -67,6 +67,38 @@ typedef struct {
 } fame_gemm_args;
 int fame_gemm_bias_act(const fame_gemm_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
 
+/* K1 (general)  fame_gemm_ex:  C[b0][b1][m,n] = epi( alpha * sum_k A(m,k) B(n,k) ), same tcgen05 kernel.
+ * An operand is K-major (stored [rows = m|n, cols = k], mn_major = 0) or MN-major (stored [rows = k, cols = m|n],
+ * mn_major = 1); this covers the three products of a linear layer without any transposed copies:
+ *     forward  Y  = X W^T   : A = X (K-major),  B = W (K-major)
+ *     dgrad    dX = dY W    : A = dY (K-major), B = W (MN-major)          [autograd of the nn.Linear calls above]
+ *     wgrad    dW = dY^T X  : A = dY (MN-major), B = X (MN-major), f32 output
+ * and, with the two batch levels (b0 = sequence, b1 = head), the five products of the attention backward.
+ * aux: FAME_AUX_ADD_* adds a residual, FAME_AUX_RELU_MASK_BF16 zeroes the result where aux <= 0 (ReLU backward).
+ * Strides and leading dimensions are in elements and must be multiples of 8; N % 8 == 0. */
+enum { FAME_AUX_NONE = 0, FAME_AUX_ADD_BF16 = 1, FAME_AUX_ADD_F32 = 2, FAME_AUX_RELU_MASK_BF16 = 3 };
+typedef struct {
+    const void* ptr; /* bf16 */
+    int64_t ld;
+    int64_t stride_b0, stride_b1;
+    int32_t mn_major;
+} fame_gemm_operand;
+typedef struct {
+    fame_gemm_operand a, b;
+    const float* bias; /* [N] or NULL */
+    const void* aux;
+    int64_t ld_aux, aux_stride_b0, aux_stride_b1;
+    int32_t aux_mode;
+    void* y;
+    int64_t ldy, y_stride_b0, y_stride_b1;
+    int32_t y_dtype;
+    int32_t M, N, K, nb0, nb1;
+    int32_t act;
+    float alpha;
+    int32_t n_valid; /* 0 = N; otherwise B has only n_valid (<= N) rows and output columns beyond it are zeros */
+} fame_gemm_ex_args;
+int fame_gemm_ex(const fame_gemm_ex_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K3  fame_layernorm:  Y[r,:] = (X[r,:] - mean) * rsqrt(var + eps) * gamma + beta     (biased variance)
  * X bf16 [rows, cols] (residual already added by the producing GEMM), Y bf16.  cols % 8 == 0, cols <= 1024.
@@ -100,6 +132,8 @@ typedef struct {
     const float* beta;
     void* y; /* bf16 [tokens, hidden] */
     float* y_f32; /* optional f32 copy of the same rows, may be NULL */
+    float* sum_out; /* optional f32 pre-LayerNorm sum (saved for the backward pass), may be NULL */
+    float* stats;   /* optional [tokens][2] = {mean, rstd}, may be NULL */
     int32_t* err_flag;
     int32_t tokens, seq_len, hidden, vocab;
     float eps;
@@ -288,6 +322,53 @@ typedef struct {
     int32_t N;
 } fame_sigmoid_probs_args;
 int fame_sigmoid_probs(const fame_sigmoid_probs_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
+
+/* ============================================================================================================
+ * Backward pass and optimizer of train_step (10_FAME.py:444-447: total_loss.backward(), clip_grad_norm_(1.0),
+ * AdamW.step()).  The reference gets these from torch.autograd / torch.optim; here they are explicit kernels.
+ * Tensor-core products (dgrad / wgrad / attention backward) go through fame_gemm_ex; the entry points below take
+ * flat argument lists (device pointers, sizes, scalars) and are asynchronous on `stream` like everything else.
+ * ============================================================================================================ */
+
+/* LayerNorm backward from the saved {mean, rstd}: dx (bf16 and/or f32), dgamma/dbeta ACCUMULATED with f32 atomics. */
+int fame_layernorm_bwd(const void* x, int32_t x_dtype, const void* dy, int32_t dy_dtype, const float* stats,
+                       const float* gamma, void* dx_bf16, float* dx_f32, float* dgamma, float* dbeta, int32_t rows,
+                       int32_t cols, fame_stream_t stream);
+/* erf-GELU forward on a saved bf16 pre-activation and its backward dpre = dh * gelu'(pre); n % 8 == 0. */
+int fame_gelu_fwd(const void* pre, void* h, int64_t n, fame_stream_t stream);
+int fame_gelu_bwd(const void* pre, const void* dh, void* dpre, int64_t n, fame_stream_t stream);
+/* out[c] += sum_r x[r, c]  (bias gradients). */
+int fame_colsum(const void* x, int32_t x_dtype, int64_t ld, int32_t rows, int32_t cols, float* out, fame_stream_t stream);
+/* Backward of x.mean(dim=1) (10_FAME.py:224): dx[b*L + l, :] = dout[b, :] / L  (bf16). */
+int fame_seq_mean_bwd(const float* dout, void* dx, int32_t batch, int32_t L, int32_t cols, fame_stream_t stream);
+/* Backward of the lab token embedding (10_FAME.py:218-220): dpos written, dw / dbias accumulated. */
+int fame_lab_embed_bwd(const void* dx, const float* lab, float* dpos, float* dw, float* dbias, int32_t batch, int32_t L,
+                       int32_t hidden, fame_stream_t stream);
+/* Attention backward, softmax part: from f32 scores S = Q K^T and dP = dO V^T (rows = batch*heads*seq, leading
+ * dimension ld >= seq) produce P = softmax(scale S) and dS = scale P (dP - rowsum(P dP)) as bf16 [rows, ld]. */
+int fame_attn_bwd_softmax(const float* s, const float* dp, void* p, void* ds, int64_t rows, int32_t seq, int32_t ld,
+                          float scale, fame_stream_t stream);
+/* Scatter the gradient of the BERT embedding sum into word / position / token-type tables (padding row skipped). */
+int fame_bert_embed_bwd(const float* d_sum, const int64_t* ids, float* dword, float* dpos, float* dtype0, int32_t tokens,
+                        int32_t seq, int32_t hidden, int32_t vocab, int32_t pad_idx, fame_stream_t stream);
+/* dE_k[clamp(ids_k[b])] += dout[b] / 4 for the four demographic tables (10_FAME.py:201-205). */
+int fame_demo_add_bwd(const float* dout, const int64_t* ids0, const int64_t* ids1, const int64_t* ids2, const int64_t* ids3,
+                      float* t0, float* t1, float* t2, float* t3, int32_t n0, int32_t n1, int32_t n2, int32_t n3,
+                      int32_t batch, int32_t hidden, fame_stream_t stream);
+/* Small fp32 product with arbitrary strides, C = alpha * A B (+ C): the fusion head's backward matrices. */
+int fame_sgemm_small(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbk, int64_t sbn, float* c,
+                     int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha, int32_t accumulate, fame_stream_t stream);
+/* Fusion head backward, elementwise stages (10_FAME.py:287-296): hidden-layer ReLU mask; gate / sig_weights / L1. */
+int fame_fusion_bwd_hidden(const float* dlogits, const float* w4, const float* pre, float* dhid, int32_t B,
+                           fame_stream_t stream);
+int fame_fusion_bwd_gate(const float* dgated, const float* proj, const float* sig_w, float w0, float w1, float w2,
+                         float lambda_l1, float* dproj, float* dsig, int32_t B, fame_stream_t stream);
+/* K9: *out += sum g^2 (float64); then clip_grad_norm_(max_norm) + one AdamW step over flat f32 buffers. */
+int fame_grad_sumsq(const float* g, int64_t n, double* out, fame_stream_t stream);
+int fame_clip_adamw(float* p, const float* g, float* m, float* v, int64_t n, const double* sumsq, float max_norm, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int32_t step, float* grad_norm_out,
+                    fame_stream_t stream);
+int fame_cast_bf16(const float* x, void* y, int64_t n, fame_stream_t stream);
 
 #ifdef __cplusplus
 }

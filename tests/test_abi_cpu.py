@@ -25,7 +25,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared, "no declarations parsed"
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/fame_b200.h but not exported"
-    assert declared == set(_lib.OP_TABLE) | set(_lib.PLAIN_SYMBOLS)
+    assert declared == set(_lib.OP_TABLE) | set(_lib.PLAIN_SYMBOLS) | set(_lib.FLAT_OPS)
 
 
 def test_struct_sizes_match_header(lib):
