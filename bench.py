@@ -125,6 +125,70 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+TRAIN_B, TRAIN_L = 32, 542
+
+
+def bench_train(args, world, rank, dev, barrier):
+    """FAME training step (forward + BCE/LEDDI loss + backward + clip + AdamW), 32 patients per GPU, L = 542."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from fairmultimodal_b200 import modules, synth, train
+
+    torch.manual_seed(0)
+    demo = modules.BEHRTModel_Demo(5, 2, 5, 5)
+    lab = modules.BEHRTModel_Lab(TRAIN_L)
+    model = modules.MultimodalTransformer_EDDI_Sigmoid(768, demo, lab, dev).to(dev)
+    n_batches = 4
+    co = synth.make_cohort(TRAIN_B * n_batches, lab_tokens=TRAIN_L, chunks=0, with_tokens=False, seed=77 + rank)
+    co["text"] = np.random.default_rng(rank).standard_normal((TRAIN_B * n_batches, 768)).astype(np.float32)
+    keys = ("demo_dummy_ids", "demo_attn_mask", "age_ids", "gender_ids", "ethnicity_ids", "insurance_ids",
+            "lab_features", "text", "labels")
+    host = [[torch.from_numpy(co[k][i * TRAIN_B:(i + 1) * TRAIN_B]).pin_memory() for k in keys] for i in range(n_batches)]
+    devb = [[x.to(dev) for x in b] for b in host]
+    pw = torch.from_numpy(synth.pos_weight(co["labels"])).to(dev)
+    hp = dict(lr=1e-5, weight_decay=0.01, betas=(0.9, 0.999), eps=1e-8)
+    w = (0.33, 0.33, 0.33)
+    group = dist.group.WORLD if world > 1 else None
+    model.train()
+    out_h = torch.empty(4, dtype=torch.float32).pin_memory()
+
+    def step(i, from_host):
+        b = [x.to(dev, non_blocking=True) for x in host[i % n_batches]] if from_host else devb[i % n_batches]
+        loss = train.optimisation_step(model, b, pw, 0.8, 0.01, w, hp, group=group)
+        if from_host:
+            out_h.copy_(loss, non_blocking=True)
+
+    res = {}
+    for name, from_host in (("resident", False), ("e2e", True)):
+        for i in range(4):
+            step(i, from_host)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(args.train_steps):
+            step(i, from_host)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[name] = t.item() / args.train_steps
+    st = train.get_state(model)
+    return {
+        "metric": "FAME train patients/sec (BASELINE configs[3]: full training step, 32 patients/GPU, L=542 lab tokens, "
+                  "3 tasks, text embeddings precomputed as in 10_FAME.py:729-731)",
+        "value": world * TRAIN_B / (res["resident"] * 1e-3), "unit": "patients/s", "ms_per_step": res["resident"],
+        "e2e": {"value": world * TRAIN_B / (res["e2e"] * 1e-3), "unit": "patients/s", "ms_per_step": res["e2e"],
+                "h2d_bytes_per_step": int(sum(x.numel() * x.element_size() for x in host[0])), "d2h_bytes_per_step": 16},
+        "global_batch": world * TRAIN_B, "steps": args.train_steps, "params": int(st.n),
+        "cuda_graph": bool(train.USE_CUDA_GRAPH and (group is None or train._GRAPH_WITH_COLLECTIVES)),
+        "dropout": "off (parity configuration)", "dtype": "bf16 GEMMs, fp32 master weights / optimizer",
+        "collectives": "none" if world == 1 else "all-reduce(SUM) of 104 int64 loss statistics + flat fp32 gradient buffer",
+    }
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -206,6 +270,14 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
 
+    # ---- second metric of BASELINE.json: FAME train patients/sec (config 4a: 32 patients per GPU, L = 542 lab
+    # tokens, text embeddings precomputed as in the reference; data parallel with the statistic + gradient all-reduce)
+    train_info = None
+    if not args.skip_train:
+        del model, ids_d, mask_d
+        torch.cuda.empty_cache()
+        train_info = bench_train(args, world, rank, dev, barrier)
+
     if rank == 0:
         pk = peaks()
         by = {}
@@ -244,6 +316,8 @@ def run_ours(args):
             "kernels": kernels,
             "clocks": clocks,
         }
+        if train_info is not None:
+            line["train"] = train_info
         if cpu_v is not None:
             line["cpu_baseline"] = {"value": cpu_v, "unit": "chunks/s", "cores": cpu_threads, "kind": "port",
                                     "sample": f"{args.cpu_chunks} chunks x 512 tokens ({cpu_dt:.1f} s), fp32 oracle port "
@@ -260,6 +334,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-chunks", type=int, default=3, help="chunks timed for the cpu_baseline leg")
+    ap.add_argument("--skip-train", action="store_true", help="only the note-encoder workload")
+    ap.add_argument("--train-steps", type=int, default=20)
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -175,7 +175,7 @@ FLAT_OPS = {
     "fame_fusion_bwd_hidden": [_P, _P, _P, _P, _I32],
     "fame_fusion_bwd_gate": [_P, _P, _P, _F, _F, _F, _F, _P, _P, _I32],
     "fame_grad_sumsq": [_P, _I64, _P],
-    "fame_clip_adamw": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _I32, _P],
+    "fame_clip_adamw": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _I32, _P, _P, _P, _P],
     "fame_cast_bf16": [_P, _P, _I64],
 }
 

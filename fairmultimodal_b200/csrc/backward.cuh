@@ -158,6 +158,50 @@ colsum_kernel(const void* __restrict__ x, long long ld, int rows, int cols, floa
     atomicAdd(out + c, acc);
 }
 
+// Vectorised variant for the large bf16 activations-gradient matrices (cols % 8 == 0, ld % 8 == 0, 16-byte aligned):
+// a block covers 256 columns x a slab of rows; thread (cg, rl) streams 16-byte chunks of column group cg for rows
+// rl, rl + 8, ... (4 loads in flight), the 8 row lanes are combined through shared memory, one atomic per column.
+__global__ void __launch_bounds__(256)
+colsum_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows, int cols, float* __restrict__ out) {
+    __shared__ float red[8][256];
+    const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 256 + cg * 8;
+    const int per = (rows + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (c0 < cols) {
+        int r = r0 + rl;
+        for (; r + 24 < r1; r += 32) {
+            float f[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x + (long long)(r + 8 * u) * ld + c0)), f[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[u][j];
+        }
+        for (; r < r1; r += 8) {
+            float f[8];
+            bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x + (long long)r * ld + c0)), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = acc[j];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        atomicAdd(out + c, s);
+    }
+}
+
 // ---------------------------------------------------------------------------------------- sequence-mean backward
 // dx[b*L + l, :] = dout[b, :] / L     (bf16)
 __global__ void seq_mean_bwd_kernel(const float* __restrict__ dout, __nv_bfloat16* __restrict__ dx, int batch, int L,
@@ -373,6 +417,11 @@ sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out)
     }
 }
 
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
 struct AdamWParams {
     float* p;
     const float* g;
@@ -383,6 +432,10 @@ struct AdamWParams {
     float max_norm, lr, beta1, beta2, eps, weight_decay;
     float bc1, bc2;       // 1 - beta^step
     float* grad_norm_out; // optional: total norm written by block 0
+    // CUDA-graph friendly overrides (device memory, read at run time instead of being baked into the launch):
+    const int* step_dev;      // optimizer step count (>= 1), nullable
+    const float* hyper_dev;   // {lr, weight_decay}, nullable
+    __nv_bfloat16* p_bf16;    // optional bf16 shadow of the updated parameters (tensor-core operands), nullable
 };
 
 __global__ void __launch_bounds__(256)
@@ -390,9 +443,19 @@ clip_adamw_kernel(const AdamWParams a) {
     const float total = (float)sqrt(*a.sumsq);
     const float coef = fminf(a.max_norm / (total + 1e-6f), 1.0f);   // torch.nn.utils.clip_grad_norm_
     if (a.grad_norm_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *a.grad_norm_out = total;
-    const float step = a.lr / a.bc1;
-    const float rbc2 = rsqrtf(a.bc2);
-    const float decay = 1.0f - a.lr * a.weight_decay;
+    float lr = a.lr, wd = a.weight_decay, bc1 = a.bc1, bc2 = a.bc2;
+    if (a.hyper_dev != nullptr) {
+        lr = a.hyper_dev[0];
+        wd = a.hyper_dev[1];
+    }
+    if (a.step_dev != nullptr) {
+        const double t = (double)*a.step_dev;
+        bc1 = (float)(1.0 - pow((double)a.beta1, t));
+        bc2 = (float)(1.0 - pow((double)a.beta2, t));
+    }
+    const float step = lr / bc1;
+    const float rbc2 = rsqrtf(bc2);
+    const float decay = 1.0f - lr * wd;
     const long long n4 = a.n >> 2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 p = reinterpret_cast<float4*>(a.p)[i];
@@ -411,6 +474,12 @@ clip_adamw_kernel(const AdamWParams a) {
         reinterpret_cast<float4*>(a.p)[i] = p;
         reinterpret_cast<float4*>(a.m)[i] = m;
         reinterpret_cast<float4*>(a.v)[i] = v;
+        if (a.p_bf16 != nullptr) {
+            uint2 o;
+            o.x = pack2(p.x, p.y);
+            o.y = pack2(p.z, p.w);
+            reinterpret_cast<uint2*>(a.p_bf16)[i] = o;
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
         const long long i = (n4 << 2) + threadIdx.x;
@@ -420,6 +489,7 @@ clip_adamw_kernel(const AdamWParams a) {
         const float v = a.beta2 * a.v[i] + (1.0f - a.beta2) * g * g;
         p -= step * m / (sqrtf(v) * rbc2 + a.eps);
         a.p[i] = p; a.m[i] = m; a.v[i] = v;
+        if (a.p_bf16 != nullptr) a.p_bf16[i] = __float2bfloat16(p);
     }
 }
 

@@ -209,16 +209,14 @@ def calibrate_thresholds(model, dataloader, device):
     return thresholds_from_hist(c.hist)
 
 
-def evaluate_from_logits(logits, labels, attrs, thresholds, verbose=True, group=None):
+def evaluate_from_logits(logits, labels, attrs, thresholds, verbose=True, counts=None, rank_group=None):
     """Metric half of evaluate_model_multi (10_FAME.py:511-552) + the EDDI tail of run_experiment (887-915) on
-    device tensors.  Returns (metrics, fairness_details, eddi)."""
+    device tensors.  Returns (metrics, fairness_details, eddi).  `counts`: a precomputed (e.g. all-reduced) count
+    vector; `rank_group`: process group over which the AUROC / AP rank counting of `logits` is sharded."""
     th = [thresholds[n] if isinstance(thresholds, dict) else thresholds for n in OUTCOMES]
-    vec = ops.eval_counts(logits, labels, attrs, th)
-    if group is not None:
-        import torch.distributed as dist
-        dist.all_reduce(vec, group=group)
+    vec = counts if counts is not None else ops.eval_counts(logits, labels, attrs, th)
     c = Counts(vec)
-    ranks = rank_metrics(logits, labels, group=None)
+    ranks = rank_metrics(logits, labels, group=rank_group)
     metrics, fair, eddi = {}, {}, {}
     for o, name in enumerate(OUTCOMES):
         tp, fn, fp, tn = (int(x) for x in c.tot[o])

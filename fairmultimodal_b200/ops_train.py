@@ -152,10 +152,11 @@ def grad_sumsq(g, out):
     _flat("fame_grad_sumsq", g.data_ptr(), g.numel(), out.data_ptr())
 
 
-def clip_adamw(p, g, m, v, sumsq, max_norm, lr, beta1, beta2, eps, weight_decay, step, grad_norm_out=None):
+def clip_adamw(p, g, m, v, sumsq, max_norm, lr, beta1, beta2, eps, weight_decay, step, grad_norm_out=None,
+               step_dev=None, hyper_dev=None, p_bf16=None):
     _flat("fame_clip_adamw", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), sumsq.data_ptr(),
           float(max_norm), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
-          _p(grad_norm_out))
+          _p(grad_norm_out), _p(step_dev), _p(hyper_dev), _p(p_bf16))
 
 
 def cast_bf16(x, y):

@@ -60,6 +60,12 @@ class FlatTrainState:
         self.step = 0
         self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
         self.grad_norm = torch.zeros(1, device=dev, dtype=torch.float32)
+        # device-side step counter and {lr, weight_decay}: read by the AdamW kernel at run time, so a captured CUDA
+        # graph of the step follows the schedule without being re-captured
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.hyper_dev = torch.zeros(2, device=dev, dtype=torch.float32)
+        self._hyper_host = None
+        self.graphs = {}
         self.refresh_bf16()
 
     def refresh_bf16(self):
@@ -77,13 +83,22 @@ class FlatTrainState:
     def zero_grad(self):
         self.g.zero_()
 
+    def set_hyper(self, lr, weight_decay):
+        if self._hyper_host != (lr, weight_decay):
+            self.hyper_dev.copy_(torch.tensor([lr, weight_decay], dtype=torch.float32))
+            self._hyper_host = (lr, weight_decay)
+
     def clip_and_step(self, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0):
+        """clip_grad_norm_(max_norm) + AdamW on the flat buffers (graph-capturable: lr / weight decay / step count are
+        read from device memory).  The bf16 shadow is refreshed by the same kernel."""
+        if not torch.cuda.is_current_stream_capturing():
+            self.set_hyper(lr, weight_decay)
         self.step += 1
+        self.step_dev += 1
         self.sumsq.zero_()
         T.grad_sumsq(self.g, self.sumsq)
         T.clip_adamw(self.p, self.g, self.m, self.v, self.sumsq, max_norm, lr, betas[0], betas[1], eps, weight_decay,
-                     self.step, self.grad_norm)
-        self.refresh_bf16()
+                     0, self.grad_norm, step_dev=self.step_dev, hyper_dev=self.hyper_dev, p_bf16=self.pb)
         self.invalidate_caches()
 
     def invalidate_caches(self):
@@ -378,11 +393,54 @@ def train_step(model, dataloader, optimizer, device, criterion, beta=1.0, lambda
     acc = torch.zeros(2, device=device, dtype=torch.float32)
     for batch in dataloader:
         batch = [x.to(device, non_blocking=True) for x in batch]
-        loss, _ = forward_backward(model, batch, pw, lambda_edd, lambda_l1, w_mod, group=group)
-        st.clip_and_step(hp["lr"], hp["weight_decay"], hp["betas"], hp["eps"], max_norm=1.0)
+        loss = optimisation_step(model, batch, pw, lambda_edd, lambda_l1, w_mod, hp, group=group)
         acc += loss[:2]                                                        # accumulate on device, sync once
     running_loss, running_bce = acc.tolist()
     return running_loss, running_bce
+
+
+USE_CUDA_GRAPH = True
+
+
+def optimisation_step(model, batch, pw, lambda_edd, lambda_l1, w_mod, hp, group=None, use_graph=None):
+    """forward + loss + backward + clip + AdamW for one batch.  The ~350 kernel launches of a step are captured into
+    a CUDA graph per batch shape (first call of a shape runs eagerly, the second captures, later ones replay): at
+    32 patients per GPU the step is otherwise bound by host launch overhead, not by the GPU."""
+    st = get_state(model)
+    use_graph = USE_CUDA_GRAPH if use_graph is None else use_graph
+    if group is not None and not _GRAPH_WITH_COLLECTIVES:
+        use_graph = False
+    st.set_hyper(hp["lr"], hp["weight_decay"])
+
+    def eager(b):
+        loss, _ = forward_backward(model, b, pw, lambda_edd, lambda_l1, w_mod, group=group)
+        st.clip_and_step(hp["lr"], hp["weight_decay"], hp["betas"], hp["eps"], max_norm=1.0)
+        return loss
+
+    if not use_graph:
+        return eager(batch)
+    key = (tuple((tuple(x.shape), x.dtype) for x in batch), tuple(w_mod), lambda_edd, lambda_l1, hp["betas"], hp["eps"],
+           pw.data_ptr(), group is not None)
+    entry = st.graphs.get(key)
+    if entry is None:
+        st.graphs[key] = {"graph": None}
+        return eager(batch)
+    if entry["graph"] is None:
+        static = [torch.empty_like(x) for x in batch]
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            entry["loss"] = eager(static)
+        entry["graph"], entry["static"] = g, static
+        st.step -= 1                                          # the capture itself executed nothing
+    for s, x in zip(entry["static"], batch):
+        s.copy_(x, non_blocking=True)
+    entry["graph"].replay()
+    st.step += 1
+    return entry["loss"]
+
+
+_GRAPH_WITH_COLLECTIVES = False
 
 
 def fame_forward_train(model, batch8, w_mod, return_modality_logits, return_gated_vector, return_intermediate):

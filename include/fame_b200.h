@@ -367,7 +367,10 @@ int fame_fusion_bwd_gate(const float* dgated, const float* proj, const float* si
 int fame_grad_sumsq(const float* g, int64_t n, double* out, fame_stream_t stream);
 int fame_clip_adamw(float* p, const float* g, float* m, float* v, int64_t n, const double* sumsq, float max_norm, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int32_t step, float* grad_norm_out,
-                    fame_stream_t stream);
+                    const int32_t* step_dev, const float* hyper_dev, void* p_bf16, fame_stream_t stream);
+/* step_dev / hyper_dev = {lr, weight_decay} (device, may be NULL) override the by-value arguments at run time so that a
+ * captured CUDA graph follows the step count and learning-rate schedule; p_bf16 (may be NULL) receives a bf16 copy of
+ * the updated parameters for the tensor-core GEMMs. */
 int fame_cast_bf16(const float* x, void* y, int64_t n, fame_stream_t stream);
 
 #ifdef __cplusplus

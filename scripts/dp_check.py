@@ -1,0 +1,64 @@
+"""Data-parallel parity check (run under torchrun on N GPUs):  N ranks x B patients must reproduce the single-process
+step on the concatenated N*B batch: same global loss, same statistics (counts bit-exact), same gradients.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 scripts/dp_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fairmultimodal_b200 import modules, ops, parallel, synth, train  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+B, L = 8, 40
+keys = ("demo_dummy_ids", "demo_attn_mask", "age_ids", "gender_ids", "ethnicity_ids", "insurance_ids", "lab_features",
+        "text", "labels")
+co = synth.make_cohort(B * world, lab_tokens=L, chunks=0, with_tokens=False, seed=5)
+co["text"] = (np.random.default_rng(3).standard_normal((B * world, 768)) * 0.5).astype(np.float32)
+pw = torch.tensor([3.0, 1.2, 0.6], device=dev)
+w = (0.41, 0.27, 0.32)
+
+
+def build():
+    torch.manual_seed(0)
+    m = modules.MultimodalTransformer_EDDI_Sigmoid(768, modules.BEHRTModel_Demo(5, 2, 5, 5), modules.BEHRTModel_Lab(L), dev)
+    sd = {k: torch.from_numpy(v) for k, v in synth.synth_state_dict(synth.fame_shapes(lab_tokens=L), 4).items()}
+    m.load_state_dict(sd)
+    return m.to(dev).train()
+
+
+lo, hi = parallel.shard_range(B * world, rank, world)
+shard = [torch.from_numpy(co[k][lo:hi]).to(dev) for k in keys]
+full = [torch.from_numpy(co[k]).to(dev) for k in keys]
+
+m_dp = build()
+loss_dp, _ = train.forward_backward(m_dp, shard, pw, 0.8, 0.01, w, group=dist.group.WORLD)
+g_dp = train.get_state(m_dp).g.clone()
+m_1 = build()
+loss_1, _ = train.forward_backward(m_1, full, pw, 0.8, 0.01, w, group=None)
+g_1 = train.get_state(m_1).g.clone()
+torch.cuda.synchronize()
+dl = (loss_dp - loss_1).abs().max().item()
+rel = ((g_dp - g_1).norm() / g_1.norm()).item()
+# statistics: all-reduced shard statistics vs statistics of the whole batch
+attrs_s = [shard[i] for i in (2, 4, 5)]
+attrs_f = [full[i] for i in (2, 4, 5)]
+z = torch.randn(B * world, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+st_s = ops.loss_stats(z[lo:hi].contiguous(), shard[8], attrs_s, pw)
+dist.all_reduce(st_s)
+st_f = ops.loss_stats(z, full[8], attrs_f, pw)
+counts_equal = bool(torch.equal(st_s[78:103], st_f[78:103]))
+sums_close = int((st_s[:78] - st_f[:78]).abs().max().item())
+ok = dl < 1e-4 and rel < 2e-2 and counts_equal and sums_close <= 64
+print(f"[rank {rank}] world={world} |loss_dp - loss_1|={dl:.2e} grad rel diff={rel:.3e} counts_equal={counts_equal} "
+      f"fixed-point sum diff={sums_close} -> {'OK' if ok else 'FAIL'}", flush=True)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)

@@ -1,0 +1,100 @@
+"""Host-side data-parallel logic on CPU with the gloo backend, world_size 2 (no GPU): patient sharding with CSR
+re-basing, the SUM all-reduce of the loss statistics / evaluation counts, and variable-length all-gather.  The
+per-rank compute is stood in for by the CPU oracle (test infrastructure); the product kernels need a B200."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fairmultimodal_b200 import parallel, synth
+from oracle import fame_oracle as O
+
+
+def test_shard_ranges_cover_everything():
+    for n in (0, 1, 7, 32, 1000):
+        for w in (1, 2, 3, 8):
+            r = [parallel.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def test_chunk_balanced_patient_shards_and_rebase():
+    co = synth.make_cohort(500, lab_tokens=4, chunks="u1_16", seq_len=16, seed=2)
+    offs = co["chunk_offsets"]
+    for w in (1, 2, 4, 8):
+        sh = parallel.shard_patients_by_chunks(offs, w)
+        assert sh[0][0] == 0 and sh[-1][1] == 500 and all(sh[i][1] == sh[i + 1][0] for i in range(w - 1))
+        loads = [int(offs[b] - offs[a]) for a, b in sh]
+        assert sum(loads) == int(offs[-1])
+        assert max(loads) - min(loads) <= 2 * 16            # within two patients' worth of chunks
+        for a, b in sh:
+            local, (c0, c1) = parallel.rebase_offsets(offs, a, b)
+            assert local[0] == 0 and local[-1] == c1 - c0 and local.dtype == np.int32
+            np.testing.assert_array_equal(np.diff(local), np.diff(offs[a:b + 1]))
+    # pooling per shard == pooling of the whole cohort (no chunk ever crosses a rank)
+    cls = np.random.default_rng(0).standard_normal((int(offs[-1]), 768)).astype(np.float32)
+    full = O.pool_patient_notes(cls, offs)
+    parts = []
+    for a, b in parallel.shard_patients_by_chunks(offs, 4):
+        local, (c0, c1) = parallel.rebase_offsets(offs, a, b)
+        parts.append(O.pool_patient_notes(cls[c0:c1], local))
+    np.testing.assert_array_equal(np.concatenate(parts), full)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B = 64
+        co = synth.make_cohort(B, lab_tokens=4, chunks=0, with_tokens=False, seed=9)
+        g = torch.Generator().manual_seed(0)
+        z = torch.randn(B, 3, generator=g)
+        y = torch.from_numpy(co["labels"])
+        attrs = [torch.from_numpy(co[k]) for k in ("age_ids", "ethnicity_ids", "insurance_ids")]
+        lo, hi = parallel.shard_range(B, rank, world)
+        # (a) loss statistics: per-rank counts / sums, SUM all-reduce == statistics of the global batch
+        cnt, sums = O.loss_group_stats(z[lo:hi], y[lo:hi], [a[lo:hi] for a in attrs])
+        t_cnt, t_sum = torch.from_numpy(cnt), torch.from_numpy(sums)
+        parallel.all_reduce_sum_(t_cnt)
+        parallel.all_reduce_sum_(t_sum)
+        cnt_all, sums_all = O.loss_group_stats(z, y, attrs)
+        ok_cnt = bool((t_cnt.numpy() == cnt_all).all())
+        ok_sum = bool(np.allclose(t_sum.numpy(), sums_all, rtol=0, atol=1e-12))
+        # (b) variable-length all-gather keeps rank order
+        sizes = [parallel.shard_range(B, r, world)[1] - parallel.shard_range(B, r, world)[0] for r in range(world)]
+        zg = parallel.all_gather_rows(z[lo:hi], sizes)
+        ok_gather = bool(torch.equal(zg, z))
+        # (c) evaluation counts: summed per-rank confusion cells == global cells
+        pred = (torch.sigmoid(z[:, 0]) > 0.5).numpy().astype(int)
+        cells = np.array(O.group_rates(y[lo:hi, 0].numpy(), pred[lo:hi], np.ones(hi - lo, bool))[2])
+        tc = torch.from_numpy(cells)
+        parallel.all_reduce_sum_(tc)
+        ok_cells = tuple(tc.tolist()) == O.group_rates(y[:, 0].numpy(), pred, np.ones(B, bool))[2]
+        ret[rank] = (ok_cnt, ok_sum, ok_gather, ok_cells)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gloo_world2_statistics_allreduce():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        assert ret[r] == (True, True, True, True), (r, ret[r])

@@ -143,6 +143,35 @@ def test_train_step_matches_reference_golden(golden_dir):
         assert torch.equal(sd[k].cpu(), w0[k])
 
 
+def test_cuda_graph_step_equals_eager_steps():
+    """train_step replays a captured CUDA graph from the third batch of a shape on; same trajectory as eager."""
+    from fairmultimodal_b200 import synth, train
+    L, B = 24, 8
+    co = synth.make_cohort(B * 5, lab_tokens=L, chunks=0, with_tokens=False, seed=31)
+    co["text"] = (np.random.default_rng(2).standard_normal((B * 5, 768)) * 0.5).astype(np.float32)
+    batches = [[torch.from_numpy(co[k][i * B:(i + 1) * B]) for k in KEYS9] for i in range(5)]
+    pw = torch.tensor([3.0, 1.2, 0.6])
+    out = {}
+    for mode in (True, False):
+        train.USE_CUDA_GRAPH = mode
+        model, _ = _model(L, 12)
+        crit = torch.nn.BCEWithLogitsLoss(pos_weight=pw.cuda())
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
+        p0 = train.get_state(model).p.clone()
+        losses = train.train_step(model, batches, opt, "cuda", crit, lambda_edd=0.8, lambda_l1=0.01)
+        st = train.get_state(model)
+        assert st.step_dev.item() == 5
+        if mode:
+            assert any(e["graph"] is not None for e in st.graphs.values())
+        out[mode] = (losses, st.p - p0)
+    train.USE_CUDA_GRAPH = True
+    assert out[True][0][0] == pytest.approx(out[False][0][0], rel=3e-3)
+    # Adam turns every gradient into a step of ~lr regardless of its size, so elements whose gradient is float-atomic
+    # noise may move differently between two runs; the update as a whole must agree
+    d_g, d_e = out[True][1], out[False][1]
+    assert ((d_g - d_e).norm() / d_e.norm()).item() < 0.05
+
+
 def test_all_gradients_match_oracle_autograd():
     """Every parameter gradient of one step against torch.autograd over the fp32 CPU oracle (B = 6, L = 40)."""
     from fairmultimodal_b200 import synth, train
