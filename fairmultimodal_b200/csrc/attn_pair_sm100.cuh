@@ -1,0 +1,375 @@
+// K2: fused attention forward on tcgen05 / TMEM -- persistent, two query tiles per CTA.
+//
+//   ctx[b, q, h, :] = softmax_k( Q.K^T * scale  (+ -inf on masked / out-of-sequence keys) ) . V
+//
+// Replaces F.scaled_dot_product_attention as reached from BertSelfAttention (HF modeling_bert.py:192-206; additive
+// key-padding mask of HF:709-713; 10_FAME.py:140) with head_dim 64, and nn.MultiheadAttention inside
+// nn.TransformerEncoderLayer of BEHRTModel_Lab (10_FAME.py:212-215, 222; 8 heads => head_dim 96, 542 tokens).
+//
+// Why this shape.  At head_dim 64 a 128x128 score tile costs 16384 exponentials (MUFU: 16 / clk / SM = 1024 clk) but
+// only 512 clk of tensor pipe for its two MMAs, so the kernel is bound by the softmax warps, not by tcgen05.  The
+// design therefore (a) keeps TWO independent score tiles in flight per SM, one per softmax warpgroup, so that the
+// MUFU pipe never waits for an MMA round trip, (b) takes everything that is not an exponential off the softmax
+// warps: the output accumulator lives in TMEM (tcgen05.mma accumulates P.V across key blocks; it is rescaled in place
+// only when a row maximum grows by more than 2^8 -- "lazy rescale"), max uses 3-input FMNMX3, scale/sum use packed
+// FFMA2/FADD2, and (c) is persistent: one CTA per SM loops over (sequence, head, 256-query) work items while the TMA
+// producer and the MMA issuer run ahead across item boundaries, so launch / prologue / epilogue latency is hidden.
+//
+//   warp 8 lane 0 : TMA producer    Q pair (2 x 128 rows) per item, K_j / V_j ring (128 keys per stage), SW128 boxes
+//   warp 9 lane 0 : MMA issuer      S_t = Q_t . K_j^T (SS)  -> TMEM cols [t*128, t*128+128)        t = 0, 1
+//                                   O_t (+)= P_t . V_j (TS) -> TMEM cols [256 + t*128, .. + D)
+//   warps 0-3     : softmax warpgroup of tile 0 (thread = one query row, all 128 keys of the block)
+//   warps 4-7     : softmax warpgroup of tile 1
+// P_t (bf16) overwrites the first 64 columns of S_t; the in-order MMA pipe guarantees S_t(j+1) is written only after
+// P_t(j) was consumed.  A commit on s_full[t] for block j also covers P.V of block j-1 (same issuing thread), so the
+// softmax warps may rescale O_t right after that wait.
+#pragma once
+#include "sm100_ptx.cuh"
+#include "attn_flash_sm100.cuh"   // FaParams, kFaBoxBytes, ex2_approx (via attn_sm100.cuh)
+
+namespace fame {
+
+constexpr int kApThreads = 320;
+constexpr float kApLazyLog2 = 8.0f;     // rescale the accumulator only when a row max grows by more than 2^8
+
+template <int D>
+struct ApCfg {
+    static constexpr int kBoxes = (D + 63) / 64;
+    static constexpr int kTileBytes = kBoxes * kFaBoxBytes;       // 128 rows x (64 | 128) bf16 columns
+    static constexpr int kQBufs = (D <= 64) ? 2 : 1;              // Q pairs in flight
+    static constexpr int kStages = (D <= 64) ? 3 : 2;             // K/V ring depth
+    static constexpr int kSmemBytes = kTileBytes * (2 * kQBufs + 2 * kStages) + 1024 /*barriers*/ + 1024 /*align*/;
+};
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f32x2_unpack(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_add(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kApThreads, 1)
+attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParams p, const int num_items,
+                     const int qpairs) {
+    using Cfg = ApCfg<D>;
+    constexpr int NB = Cfg::kBoxes;
+    constexpr int ST = Cfg::kStages;
+    constexpr int QB = Cfg::kQBufs;
+    constexpr int TILE = Cfg::kTileBytes;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_q = smem;                          // [QB][2][TILE]
+    uint8_t* smem_k = smem_q + QB * 2 * TILE;        // [ST][TILE]
+    uint8_t* smem_v = smem_k + ST * TILE;            // [ST][TILE]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + ST * TILE);
+    uint64_t* q_full = bars;                 // [QB]
+    uint64_t* q_empty = q_full + QB;         // [QB]
+    uint64_t* k_full = q_empty + QB;         // [ST]
+    uint64_t* v_full = k_full + ST;          // [ST]
+    uint64_t* kv_empty = v_full + ST;        // [ST]
+    uint64_t* s_full = kv_empty + ST;        // [2]  S_t written (and P.V of the previous block of tile t complete)
+    uint64_t* p_full = s_full + 2;           // [2]  P_t in TMEM, O_t rescaled (4 warp arrivals)
+    uint64_t* o_full = p_full + 2;           // [2]  last P.V of the item complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.seq;
+    const int nblk = (S + 127) >> 7;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_qkv);
+        for (int i = 0; i < QB; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_empty[i], 1);
+        }
+        for (int i = 0; i < ST; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 4);
+            mbar_init(&o_full[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 8) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t kColO = 256;
+
+    // item -> (sequence b, head h, query pair qp); consecutive items share K/V of one (b, h) through L2
+    auto t1_active = [&](int item) { return (item % qpairs) * 256 + 128 < S; };
+
+    if (warp == 8) {
+        if (lane == 0) {
+            // ------------------------------------------------------------------------------------ TMA producer
+            int qb = 0, st = 0;
+            uint32_t qph = 0, kph = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const int qp = item % qpairs, bh = item / qpairs;
+                const int h = bh % p.heads, b = bh / p.heads;
+                const int row0 = b * S;
+                const int nt = t1_active(item) ? 2 : 1;
+                mbar_wait(&q_empty[qb], qph ^ 1);
+                mbar_arrive_expect_tx(&q_full[qb], TILE * nt);
+                for (int t = 0; t < nt; ++t)
+#pragma unroll
+                    for (int x = 0; x < NB; ++x)
+                        tma_load_2d(smem_q + (qb * 2 + t) * TILE + x * kFaBoxBytes, &tmap_qkv, &q_full[qb],
+                                    p.q_col0 + h * D + x * 64, row0 + qp * 256 + t * 128, kEvictFirst);
+                if (++qb == QB) { qb = 0; qph ^= 1; }
+                for (int j = 0; j < nblk; ++j) {
+                    mbar_wait(&kv_empty[st], kph ^ 1);
+                    mbar_arrive_expect_tx(&k_full[st], TILE);
+#pragma unroll
+                    for (int x = 0; x < NB; ++x)
+                        tma_load_2d(smem_k + st * TILE + x * kFaBoxBytes, &tmap_qkv, &k_full[st],
+                                    p.k_col0 + h * D + x * 64, row0 + j * 128, kEvictLast);
+                    mbar_arrive_expect_tx(&v_full[st], TILE);
+#pragma unroll
+                    for (int x = 0; x < NB; ++x)
+                        tma_load_2d(smem_v + st * TILE + x * kFaBoxBytes, &tmap_qkv, &v_full[st],
+                                    p.v_col0 + h * D + x * 64, row0 + j * 128, kEvictLast);
+                    if (++st == ST) { st = 0; kph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0 && blockIdx.x < num_items) {
+            // ------------------------------------------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);
+            // cursor over the NEXT score block to issue (runs one block ahead of the P.V products, across items)
+            int n_item = blockIdx.x, n_j = 0, n_qb = 0, ks = 0;
+            uint32_t n_qph = 0, kph = 0;
+            bool n_t1 = t1_active(n_item);
+            auto issue_s = [&](int t) {
+                if (t == 0) {
+                    if (n_j == 0) mbar_wait(&q_full[n_qb], n_qph);
+                    mbar_wait(&k_full[ks], kph);
+                }
+                tc_fence_after();
+                const uint32_t q_addr = smem_u32(smem_q + (n_qb * 2 + t) * TILE);
+                const uint32_t k_addr = smem_u32(smem_k + ks * TILE);
+#pragma unroll
+                for (int tt = 0; tt < D / 16; ++tt) {
+                    const uint32_t off = (tt >> 2) * kFaBoxBytes + (tt & 3) * 32;
+                    umma_bf16_ss(tmem_base + t * 128, make_smem_desc_sw128(q_addr + off, 16, 1024),
+                                 make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_qk, tt != 0);
+                }
+                umma_commit(&s_full[t]);
+                if (t == 1 || !n_t1) {          // last tile of this block: advance the cursor
+                    if (n_j == nblk - 1) umma_commit(&q_empty[n_qb]);
+                    if (++ks == ST) { ks = 0; kph ^= 1; }
+                    if (++n_j == nblk) {
+                        n_j = 0;
+                        n_item += gridDim.x;
+                        if (++n_qb == QB) { n_qb = 0; n_qph ^= 1; }
+                        n_t1 = n_item < num_items && t1_active(n_item);
+                    }
+                }
+            };
+            {
+                const bool c_t1 = n_t1;
+                issue_s(0);
+                if (c_t1) issue_s(1);
+            }
+            int vs = 0;
+            uint32_t vph = 0, pph0 = 0, pph1 = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const bool t1 = t1_active(item);
+                for (int j = 0; j < nblk; ++j) {
+                    mbar_wait(&v_full[vs], vph);
+                    const uint32_t v_addr = smem_u32(smem_v + vs * TILE);
+                    auto issue_pv = [&](int t) {
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk)
+                            umma_bf16_ts(tmem_base + kColO + t * 128, tmem_base + t * 128 + kk * 8,
+                                         make_smem_desc_sw128(v_addr + kk * 2048, kFaBoxBytes, 1024), idesc_pv,
+                                         (j | kk) != 0);
+                        if (j == nblk - 1) umma_commit(&o_full[t]);
+                    };
+                    mbar_wait(&p_full[0], pph0);
+                    pph0 ^= 1;
+                    tc_fence_after();
+                    issue_pv(0);
+                    if (!t1) umma_commit(&kv_empty[vs]);
+                    const bool nx = n_item < num_items;
+                    const bool c_t1 = n_t1;
+                    if (nx) issue_s(0);
+                    if (t1) {
+                        mbar_wait(&p_full[1], pph1);
+                        pph1 ^= 1;
+                        tc_fence_after();
+                        issue_pv(1);
+                        umma_commit(&kv_empty[vs]);
+                    }
+                    if (nx && c_t1) issue_s(1);
+                    if (++vs == ST) { vs = 0; vph ^= 1; }
+                }
+            }
+        }
+    } else {
+        // -------------------------------------------------------------------------------- softmax warpgroups
+        const int q = warp & 3;       // TMEM lane quadrant of this warp
+        const int t = warp >> 2;      // query tile (= warpgroup)
+        const int r = q * 32 + lane;  // row inside the tile
+        const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
+        const uint32_t s_addr = lane_base + t * 128;
+        const uint32_t o_addr = lane_base + kColO + t * 128;
+        const float sc = p.scale_log2e;
+        uint32_t sph = 0, oph = 0;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            if (t == 1 && !t1_active(item)) continue;
+            const int qp = item % qpairs, bh = item / qpairs;
+            const int h = bh % p.heads, b = bh / p.heads;
+            float m = -INFINITY, l = 0.f;   // running reference max (log2 units, scaled) and row sum
+            for (int j = 0; j < nblk; ++j) {
+                // validity of the 128 keys of this block: inside the sequence and not masked by the caller
+                const int key0 = j * 128;
+                uint32_t vm[4];
+                bool all_valid = (key0 + 128 <= S) && p.key_mask == nullptr;
+                if (!all_valid) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int k = key0 + c * 32 + lane;
+                        const bool ok = k < S && (p.key_mask == nullptr || p.key_mask[(long long)b * S + k] != 0);
+                        vm[c] = __ballot_sync(0xffffffffu, ok);
+                    }
+                    all_valid = (vm[0] & vm[1] & vm[2] & vm[3]) == 0xffffffffu;
+                }
+                mbar_wait(&s_full[t], sph);
+                sph ^= 1;
+                tc_fence_after();
+                uint32_t s[4][32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tmem_ld_x32(s_addr + c * 32, s[c]);
+                tmem_ld_wait();
+                if (!all_valid) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (!((vm[c] >> i) & 1u)) s[c][i] = 0xff800000u;   // -inf
+                }
+                float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        mx0 = fmax3(mx0, __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
+                        mx1 = fmax3(mx1, __uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3]));
+                    }
+                // scores are scaled by a positive constant, so the max commutes with the scaling
+                const float m_blk = fmaxf(mx0, mx1) * sc;
+                float m_new = fmaxf(m, m_blk);
+                if (m != -INFINITY && m_new - m <= kApLazyLog2) m_new = m;   // lazy: keep the old reference max
+                const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+                const float alpha = (m_new == m) ? 1.0f : ex2_approx(m - m_safe);   // m == -inf -> 0
+                const unsigned long long sc2 = f32x2_pack(sc, sc), nm2 = f32x2_pack(-m_safe, -m_safe);
+                unsigned long long sum2 = 0ull;   // (0.f, 0.f)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const unsigned long long x2 =
+                            f32x2_fma(f32x2_pack(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
+                        float x0, x1;
+                        f32x2_unpack(x2, x0, x1);
+                        const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+                        sum2 = f32x2_add(sum2, f32x2_pack(p0, p1));
+                        pk[i >> 1] = pack_bf16x2(p0, p1);
+                    }
+                    tmem_st_x16(s_addr + c * 16, pk);
+                }
+                if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+                    // P.V of block j-1 is complete (covered by the s_full commit): rescale O_t in place.  Done after
+                    // the exponentials so that the 128 score registers are dead by now (register pressure).
+#pragma unroll
+                    for (int c = 0; c < D / 32; ++c) {
+                        uint32_t o[32];
+                        tmem_ld_x32(o_addr + c * 32, o);
+                        tmem_ld_wait();
+                        uint32_t lo[16], hi[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            lo[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            hi[i] = __float_as_uint(__uint_as_float(o[16 + i]) * alpha);
+                        }
+                        tmem_st_x16(o_addr + c * 32, lo);
+                        tmem_st_x16(o_addr + c * 32 + 16, hi);
+                    }
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[t]);
+                float sa, sb;
+                f32x2_unpack(sum2, sa, sb);
+                l = l * alpha + (sa + sb);
+                m = m_new;
+            }
+            // ---- epilogue: O_t / l -> bf16 -> global
+            mbar_wait(&o_full[t], oph);
+            oph ^= 1;
+            tc_fence_after();
+            const float inv = l > 0.f ? 1.0f / l : 0.f;
+            const int qrow = qp * 256 + t * 128 + r;
+            __nv_bfloat16* dst = p.ctx + (long long)(b * S + qrow) * p.ld_ctx + h * D;
+#pragma unroll
+            for (int c = 0; c < D / 32; ++c) {
+                uint32_t o[32];
+                tmem_ld_x32(o_addr + c * 32, o);
+                tmem_ld_wait();
+                if (qrow < S) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 u;
+                        u.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+                        u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+                        u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+                        u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+                        *reinterpret_cast<uint4*>(dst + c * 32 + i) = u;
+                    }
+                }
+            }
+            // the reads of O_t above are ordered before this warp's next p_full arrival (tcgen05.wait::ld + the
+            // fence before that arrive), which is what the next item's first P.V (accumulate = 0) waits for
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace fame

@@ -8,6 +8,7 @@
 
 #include "attn_sm100.cuh"
 #include "attn_flash_sm100.cuh"
+#include "attn_pair_sm100.cuh"
 #include "backward.cuh"
 #include "gemm_sm100.cuh"
 #include "heads.cuh"
@@ -121,6 +122,38 @@ static int launch_flash(const fame_attn_fwd_args* a, const CUtensorMap& tq, fame
     fame::attn_fwd_flash_kernel<D><<<grid, fame::kFaThreads, fame::FaCfg<D>::kSmemBytes, stream>>>(tq, p);
     return launch_status();
 }
+
+template <int D>
+static int launch_pair(const fame_attn_fwd_args* a, const CUtensorMap& tq, int sm_count, fame_stream_t stream) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(fame::attn_fwd_pair_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             fame::ApCfg<D>::kSmemBytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+        attr_set[dev] = true;
+    }
+    fame::FaParams p;
+    p.key_mask = a->key_mask;
+    p.ctx = reinterpret_cast<__nv_bfloat16*>(a->ctx);
+    p.ld_ctx = a->ld_ctx;
+    p.batch = a->batch;
+    p.seq = a->seq;
+    p.heads = a->heads;
+    p.q_col0 = 0;
+    p.k_col0 = a->heads * D;
+    p.v_col0 = 2 * a->heads * D;
+    p.scale_log2e = a->scale * 1.4426950408889634f;
+    const int qpairs = (a->seq + 255) / 256;
+    const long long items = (long long)a->batch * a->heads * qpairs;
+    if (items > 0x7fffffffll) return FAME_ERR_SHAPE;
+    const int grid = items < sm_count ? (int)items : sm_count;
+    fame::attn_fwd_pair_kernel<D><<<grid, fame::kApThreads, fame::ApCfg<D>::kSmemBytes, stream>>>(tq, p, (int)items,
+                                                                                                 qpairs);
+    return launch_status();
+}
+
 
 }  // namespace
 
@@ -240,7 +273,7 @@ int fame_attn_fwd(const fame_attn_fwd_args* a, void*, size_t, fame_stream_t stre
     if (a == nullptr || a->qkv == nullptr || a->ctx == nullptr) return FAME_ERR_NULLPTR;
     if ((a->head_dim != 64 && a->head_dim != 96) || a->seq <= 0 || a->heads <= 0 || a->batch < 0)
         return FAME_ERR_SHAPE;
-    if (a->algo < 0 || a->algo > 2) return FAME_ERR_SHAPE;
+    if (a->algo < 0 || a->algo > 3) return FAME_ERR_SHAPE;
     const bool fullrow_ok = a->head_dim == fame::kAttnD && a->seq <= fame::kAttnMaxS;
     if (a->algo == 1 && !fullrow_ok) return FAME_ERR_SHAPE;
     const int64_t width = 3ll * a->heads * a->head_dim;
@@ -255,7 +288,9 @@ int fame_attn_fwd(const fame_attn_fwd_args* a, void*, size_t, fame_stream_t stre
     CUtensorMap tq;
     rc = encode_bf16_2d(&tq, a->qkv, (uint64_t)a->batch * a->seq, (uint64_t)width, (uint64_t)a->ld_qkv, 128);
     if (rc != FAME_OK) return rc;
-    const bool use_fullrow = a->algo == 1 || (a->algo == 0 && fullrow_ok && FAME_ATTN_AUTO_FULLROW);
+    if (a->algo == 0 || a->algo == 3)
+        return a->head_dim == 64 ? launch_pair<64>(a, tq, d->sm_count, stream) : launch_pair<96>(a, tq, d->sm_count, stream);
+    const bool use_fullrow = a->algo == 1;
     if (!use_fullrow) return a->head_dim == 64 ? launch_flash<64>(a, tq, stream) : launch_flash<96>(a, tq, stream);
 
     static bool attr_set[64] = {};
@@ -411,7 +446,7 @@ int fame_loss_stats(const fame_loss_stats_args* a, void*, size_t, fame_stream_t 
     for (int k = 0; k < 3; ++k) p.attr[k] = reinterpret_cast<const long long*>(a->attr[k]);
     p.stats = reinterpret_cast<long long*>(a->stats);
     p.B = a->B;
-    int grid = (a->B + 255) / 256;
+    int grid = (a->B + 1023) / 1024;     // 256 threads x 4 patients per trip
     if (grid > 2 * d->sm_count) grid = 2 * d->sm_count;
     fame::loss_stats_kernel<<<grid, 256, 0, stream>>>(p);
     return launch_status();
@@ -432,9 +467,9 @@ int fame_loss_fwd_bwd(const fame_loss_fwd_bwd_args* a, void*, size_t, fame_strea
     p.stats = reinterpret_cast<const long long*>(a->stats);
     p.sig_w = a->sig_w; p.n_sig = a->n_sig; p.lambda_edd = a->lambda_edd; p.lambda_l1 = a->lambda_l1;
     p.dlogits = a->dlogits; p.loss_out = a->loss_out; p.B = a->B;
-    int grid = (a->B + 255) / 256;
+    int grid = (a->B + 1023) / 1024;     // 256 threads x 4 patients per trip
     if (grid < 1) grid = 1;
-    if (grid > 2 * d->sm_count) grid = 2 * d->sm_count;
+    if (grid > 4 * d->sm_count) grid = 4 * d->sm_count;
     fame::loss_fwd_bwd_kernel<<<grid, 256, 0, stream>>>(p);
     return launch_status();
 }
@@ -457,7 +492,7 @@ int fame_eval_counts(const fame_eval_counts_args* a, void*, size_t, fame_stream_
     p.out = reinterpret_cast<unsigned long long*>(a->out);
     p.N = a->N;
     p.logits_are_probs = a->logits_are_probs;
-    int grid = (a->N + 255) / 256;
+    int grid = (a->N + 1023) / 1024;     // 256 threads x 4 patients per trip
     if (grid > 4 * d->sm_count) grid = 4 * d->sm_count;
     fame::eval_counts_kernel<<<grid, 256, 0, stream>>>(p);
     return launch_status();

@@ -178,16 +178,21 @@ fusion_fwd_kernel(const FusionParams p) {
 
 // ================================================================================================ K8 loss
 // Statistics layout (int64, identical on every rank so that one SUM all-reduce makes them global):
-//   [0..2]   sum_b |sigmoid(z)-y|  per outcome            fixed point 2^32
+//   [0..2]   sum_b |sigmoid(z)-y|  per outcome            fixed point 2^24
 //   [3..5]   sum_b bce term        per outcome            fixed point 2^24
-//   [6..77]  group error sums [outcome][attr][code 0..7]  fixed point 2^32
+//   [6..77]  group error sums [outcome][attr][code 0..7]  fixed point 2^24
 //   [78..101] group counts [attr][code]                   integer
 //   [102]    patients                                     integer
 //   [103]    error flag (an attribute code outside 0..7)
+// Every PATIENT's term is rounded to fixed point first and only integers are added afterwards, so each statistic is
+// an exact integer sum: independent of thread / block / rank order.  N data-parallel ranks therefore reproduce the
+// statistics of the single-process run on the concatenated batch bit for bit, and so does a re-run.
+// |sigmoid(z) - y| lies in [0, 1]: 2^-24 is the float32 resolution at 1.0, the rounding error per patient <= 3e-8.
 constexpr int kLossStatsLen = 104;
 constexpr int kLossSlots = 8;
-constexpr double kFixErr = 4294967296.0;   // 2^32
+constexpr double kFixErr = 16777216.0;     // 2^24
 constexpr double kFixBce = 16777216.0;     // 2^24
+constexpr int kLossTripsPerFlush = 63;     // 63 trips x 4 patients x 2^24 < 2^32: uint32 accumulators cannot overflow
 
 struct LossStatsParams {
     const float* logits;     // [B,3]
@@ -198,87 +203,127 @@ struct LossStatsParams {
     int B;
 };
 
-// Each thread walks patients grid-stride with private accumulators (predicated adds over the 8 code slots, no
-// dynamic register indexing), then a warp-shuffle tree and one shared-memory pass per block; the block total is
-// converted to fixed point and added with integer atomics, so the result is independent of block order.
+// exact warp sum of 32 uint32 values as a 64-bit integer: two hardware REDUX adds over the 16-bit halves
+__device__ __forceinline__ unsigned long long warp_sum_u32_exact(unsigned v) {
+    const unsigned lo = __reduce_add_sync(0xffffffffu, v & 0xffffu);
+    const unsigned hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    return ((unsigned long long)hi << 16) + lo;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Each thread walks patients grid-stride with private integer accumulators (predicated adds over the 8 code slots,
+// no dynamic register indexing); every kLossTripsPerFlush trips (and at the end) the warp totals go to shared
+// memory with 64-bit integer atomics, and the block totals to global memory the same way.
 __global__ void __launch_bounds__(256)
 loss_stats_kernel(const LossStatsParams p) {
-    float e_sum[3] = {0.f, 0.f, 0.f}, b_sum[3] = {0.f, 0.f, 0.f};
-    float g_sum[3][3][kLossSlots];
-    int g_cnt[3][kLossSlots];
+    unsigned e_sum[3] = {0u, 0u, 0u};
+    unsigned long long b_sum[3] = {0ull, 0ull, 0ull};
+    unsigned g_sum[3][3][kLossSlots];
+    unsigned g_cnt[3][kLossSlots];
+    unsigned n_local = 0, bad = 0;
+    auto clear = [&]() {
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i) {
+            e_sum[i] = 0u;
+            b_sum[i] = 0ull;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int s = 0; s < kLossSlots; ++s) g_sum[i][a][s] = 0u;
+        }
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int s = 0; s < kLossSlots; ++s) g_sum[i][a][s] = 0.f;
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int s = 0; s < kLossSlots; ++s) g_cnt[a][s] = 0;
-    int n_local = 0, bad = 0;
+            for (int s = 0; s < kLossSlots; ++s) g_cnt[a][s] = 0u;
+        n_local = 0;
+    };
+    clear();
     float pw[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) pw[i] = __ldg(p.pos_weight + i);
 
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < p.B; b += gridDim.x * blockDim.x) {
-        float e[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const float z = __ldg(p.logits + 3ll * b + i), y = __ldg(p.labels + 3ll * b + i);
-            const float pr = 1.0f / (1.0f + expf(-z));
-            e[i] = fabsf(pr - y);
-            // softplus(-z) = -log sigmoid(z), stable:  max(-z, 0) + log1p(exp(-|z|))
-            const float sp = fmaxf(-z, 0.f) + log1pf(expf(-fabsf(z)));
-            b_sum[i] += pw[i] * y * sp + (1.0f - y) * (sp + z);
-            e_sum[i] += e[i];
-        }
-        ++n_local;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const long long c = __ldg(p.attr[a] + b);
-            bad |= (c < 0 || c >= kLossSlots);
-#pragma unroll
-            for (int s = 0; s < kLossSlots; ++s) {
-                const bool hit = (c == s);
-                g_cnt[a][s] += hit;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) g_sum[i][a][s] += hit ? e[i] : 0.f;
-            }
-        }
-    }
-
-    __shared__ double sh[kLossStatsLen];
-    for (int i = threadIdx.x; i < kLossStatsLen; i += blockDim.x) sh[i] = 0.0;
+    __shared__ unsigned long long sh[kLossStatsLen];
+    for (int i = threadIdx.x; i < kLossStatsLen; i += blockDim.x) sh[i] = 0ull;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    auto flush = [&](int idx, float v) {
-        v = warp_sum(v);
-        if (lane == 0 && v != 0.f) atomicAdd(&sh[idx], (double)v);
+    auto put = [&](int idx, unsigned long long v) {
+        if (lane == 0 && v != 0ull) atomicAdd(&sh[idx], v);
     };
+    auto flush = [&]() {     // warp-collective: every lane of the warp calls it at the same trip
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        flush(i, e_sum[i]);
-        flush(3 + i, b_sum[i]);
-    }
+        for (int i = 0; i < 3; ++i) {
+            put(i, warp_sum_u32_exact(e_sum[i]));
+            put(3 + i, warp_sum_u64(b_sum[i]));
+        }
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int s = 0; s < kLossSlots; ++s)
+                    put(6 + (i * 3 + a) * kLossSlots + s, warp_sum_u32_exact(g_sum[i][a][s]));
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int s = 0; s < kLossSlots; ++s) flush(6 + (i * 3 + a) * kLossSlots + s, g_sum[i][a][s]);
+            for (int s = 0; s < kLossSlots; ++s) put(78 + a * kLossSlots + s, __reduce_add_sync(0xffffffffu, g_cnt[a][s]));
+        put(102, __reduce_add_sync(0xffffffffu, n_local));
+        clear();
+    };
+
+    int trips = 0;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.logits) | reinterpret_cast<uintptr_t>(p.labels) |
+                          reinterpret_cast<uintptr_t>(p.attr[0]) | reinterpret_cast<uintptr_t>(p.attr[1]) |
+                          reinterpret_cast<uintptr_t>(p.attr[2])) & 15) == 0;
+    const long long per_block = (long long)blockDim.x * kPatPerThread;
+    // the loop bound is uniform per block (base, not base + thread offset), so a warp never diverges around flush()
+    for (long long base = blockIdx.x * per_block; base < p.B; base += gridDim.x * per_block) {
+        PatientQuad q;
+        load_patient_quad(q, p.logits, 3, p.labels, p.attr, base + (long long)threadIdx.x * kPatPerThread, p.B, vec_ok);
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+        for (int u = 0; u < kPatPerThread; ++u) {
+            if (u < q.n) {
+                unsigned e[3];
 #pragma unroll
-        for (int s = 0; s < kLossSlots; ++s) flush(78 + a * kLossSlots + s, (float)g_cnt[a][s]);
-    flush(102, (float)n_local);
-    flush(103, (float)bad);
+                for (int i = 0; i < 3; ++i) {
+                    const float z = q.z[u][i], y = q.y[u][i];
+                    const float pr = 1.0f / (1.0f + expf(-z));
+                    e[i] = __float2uint_rn(fminf(fabsf(pr - y), 1.0f) * 16777216.0f);
+                    // softplus(-z) = -log sigmoid(z), stable:  max(-z, 0) + log1p(exp(-|z|))
+                    const float sp = fmaxf(-z, 0.f) + log1pf(expf(-fabsf(z)));
+                    const float term = pw[i] * y * sp + (1.0f - y) * (sp + z);
+                    b_sum[i] += __float2ull_rn(fmaxf(term, 0.f) * 16777216.0f);
+                    e_sum[i] += e[i];
+                }
+                ++n_local;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const long long c = q.code[a][u];
+                    bad |= (c < 0 || c >= kLossSlots);
+#pragma unroll
+                    for (int s = 0; s < kLossSlots; ++s) {
+                        const bool hit = (c == s);
+                        g_cnt[a][s] += hit;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) g_sum[i][a][s] += hit ? e[i] : 0u;
+                    }
+                }
+            }
+        }
+        if (++trips == kLossTripsPerFlush) {
+            flush();
+            trips = 0;
+        }
+    }
+    flush();
+    put(103, __reduce_add_sync(0xffffffffu, bad));
     __syncthreads();
     for (int i = threadIdx.x; i < kLossStatsLen; i += blockDim.x) {
-        const double v = sh[i];
-        if (v == 0.0) continue;
-        const double scale = i < 3 ? kFixErr : (i < 6 ? kFixBce : (i < 78 ? kFixErr : 1.0));
-        atomicAdd(reinterpret_cast<unsigned long long*>(p.stats + i), (unsigned long long)llrint(v * scale));
+        const unsigned long long v = sh[i];
+        if (v != 0ull) atomicAdd(reinterpret_cast<unsigned long long*>(p.stats + i), v);
     }
 }
 
@@ -356,26 +401,50 @@ loss_fwd_bwd_kernel(const LossGradParams p) {
     if (p.dlogits == nullptr) return;
     const float inv3B = (float)(1.0 / (3.0 * Bt));
     const float k_edd = p.lambda_edd * 10.0f / 9.0f;
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < p.B; b += gridDim.x * blockDim.x) {
-        int code[3];
+    float pwv[3];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const long long c = __ldg(p.attr[a] + b);
-            code[a] = (int)(c < 0 ? 0 : (c >= kLossSlots ? kLossSlots - 1 : c));
+    for (int i = 0; i < 3; ++i) pwv[i] = __ldg(p.pos_weight + i);
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.logits) | reinterpret_cast<uintptr_t>(p.labels) |
+                          reinterpret_cast<uintptr_t>(p.attr[0]) | reinterpret_cast<uintptr_t>(p.attr[1]) |
+                          reinterpret_cast<uintptr_t>(p.attr[2]) | reinterpret_cast<uintptr_t>(p.dlogits)) & 15) == 0;
+    const long long per_block = (long long)blockDim.x * kPatPerThread;
+    for (long long base = blockIdx.x * per_block; base < p.B; base += gridDim.x * per_block) {
+        const long long b0 = base + (long long)threadIdx.x * kPatPerThread;
+        PatientQuad q;
+        load_patient_quad(q, p.logits, 3, p.labels, p.attr, b0, p.B, vec_ok);
+        float gz[kPatPerThread][3];
+#pragma unroll
+        for (int u = 0; u < kPatPerThread; ++u) {
+            int code[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const long long c = q.code[a][u];
+                code[a] = (int)(c < 0 ? 0 : (c >= kLossSlots ? kLossSlots - 1 : c));
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float z = q.z[u][i], y = q.y[u][i];
+                const float pr = 1.0f / (1.0f + expf(-z));
+                float g = (-pwv[i] * y * (1.0f - pr) + (1.0f - y) * pr) * inv3B;
+                float dRde = 0.f;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) dRde += coef[i][a][code[a]] + cst[i][a];
+                const float d = pr - y;
+                const float sgn = d > 0.f ? 1.0f : (d < 0.f ? -1.0f : 0.f);
+                gz[u][i] = g + k_edd * dRde * sgn * pr * (1.0f - pr);
+            }
         }
+        if (q.n == kPatPerThread && vec_ok) {
+            float4* dst = reinterpret_cast<float4*>(p.dlogits + 3 * b0);
+            const float* gf = &gz[0][0];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const float z = __ldg(p.logits + 3ll * b + i), y = __ldg(p.labels + 3ll * b + i);
-            const float pr = 1.0f / (1.0f + expf(-z));
-            const float pw = __ldg(p.pos_weight + i);
-            float gz = (-pw * y * (1.0f - pr) + (1.0f - y) * pr) * inv3B;
-            float dRde = 0.f;
+            for (int k = 0; k < 3; ++k) dst[k] = make_float4(gf[4 * k], gf[4 * k + 1], gf[4 * k + 2], gf[4 * k + 3]);
+        } else {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) dRde += coef[i][a][code[a]] + cst[i][a];
-            const float d = pr - y;
-            const float sgn = d > 0.f ? 1.0f : (d < 0.f ? -1.0f : 0.f);
-            gz += k_edd * dRde * sgn * pr * (1.0f - pr);
-            p.dlogits[3ll * b + i] = gz;
+            for (int u = 0; u < kPatPerThread; ++u)
+                if (u < q.n)
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) p.dlogits[3 * (b0 + u) + i] = gz[u][i];
         }
     }
 }

@@ -39,7 +39,8 @@ struct EvalCountsParams {
     int logits_are_probs;       // 1: `logits` already holds float32 probabilities / 0-1 predictions
 };
 
-// Per-thread counters are packed four 8-bit cells (TP, FN, FP, TN) per register and flushed every 255 patients.
+// Per-thread counters are packed four 8-bit cells (TP, FN, FP, TN) per register and flushed every 252 patients;
+// each thread takes 4 consecutive patients per trip through 16-byte loads (load_patient_quad, rowwise.cuh).
 __global__ void __launch_bounds__(256)
 eval_counts_kernel(const EvalCountsParams p) {
     __shared__ unsigned int sh[kEvLen];
@@ -84,43 +85,50 @@ eval_counts_kernel(const EvalCountsParams p) {
     };
     reset();
     int since = 0, n_local = 0, bad = 0;
-    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;; b += (long long)gridDim.x * blockDim.x) {
-        const bool live = b < p.N;
-        // the flush is warp-collective: all lanes must reach it together
-        if (!__any_sync(0xffffffffu, live)) break;
-        if (live) {
-            int code[3];
+    const bool vec_ok = p.ld == 3 && ((reinterpret_cast<uintptr_t>(p.logits) | reinterpret_cast<uintptr_t>(p.labels) |
+                                       reinterpret_cast<uintptr_t>(p.attr[0]) | reinterpret_cast<uintptr_t>(p.attr[1]) |
+                                       reinterpret_cast<uintptr_t>(p.attr[2])) & 15) == 0;
+    const long long per_block = (long long)blockDim.x * kPatPerThread;
+    // block-uniform trip count: the flush is warp-collective, all lanes reach it together
+    for (long long base = blockIdx.x * per_block; base < p.N; base += gridDim.x * per_block) {
+        PatientQuad q;
+        load_patient_quad(q, p.logits, p.ld, p.labels, p.attr, base + (long long)threadIdx.x * kPatPerThread, p.N, vec_ok);
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const long long c = __ldg(p.attr[a] + b);
-                bad |= (c < 0 || c >= kEvSlots);
-                code[a] = (int)c;
-            }
+        for (int u = 0; u < kPatPerThread; ++u) {
+            if (u < q.n) {
+                int code[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float z = __ldg(p.logits + b * p.ld + i);
-                const float pr = p.logits_are_probs ? z : sigmoid_f32_exact(z);
-                const int y = __ldg(p.labels + 3 * b + i) != 0.f;
-                const int pred = (double)pr > p.thr[i];
-                const unsigned inc = 1u << (8 * ((1 - y) * 2 + (1 - pred)));  // cell: TP=0, FN=1, FP=2, TN=3
-                tot[i] += inc;
-#pragma unroll
-                for (int a = 0; a < 3; ++a)
-#pragma unroll
-                    for (int s = 0; s < kEvSlots; ++s) cnt[i][a][s] += (code[a] == s) ? inc : 0u;
-                if (p.sweep != nullptr) {
-                    // kk = number of sweep thresholds strictly below p  (p > t_k  <=>  k < kk); thresholds ascend
-                    int lo = 0, hi = 101;
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if ((double)pr > sweep_s[mid]) lo = mid + 1; else hi = mid;
-                    }
-                    atomicAdd(&sh[kEvConfLen + kEvTotLen + (i * 2 + y) * 102 + lo], 1u);
+                for (int a = 0; a < 3; ++a) {
+                    const long long c = q.code[a][u];
+                    bad |= (c < 0 || c >= kEvSlots);
+                    code[a] = (int)c;
                 }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const float z = q.z[u][i];
+                    const float pr = p.logits_are_probs ? z : sigmoid_f32_exact(z);
+                    const int y = q.y[u][i] != 0.f;
+                    const int pred = (double)pr > p.thr[i];
+                    const unsigned inc = 1u << (8 * ((1 - y) * 2 + (1 - pred)));  // cell: TP=0, FN=1, FP=2, TN=3
+                    tot[i] += inc;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int s = 0; s < kEvSlots; ++s) cnt[i][a][s] += (code[a] == s) ? inc : 0u;
+                    if (p.sweep != nullptr) {
+                        // kk = number of sweep thresholds strictly below p (p > t_k <=> k < kk); thresholds ascend
+                        int lo = 0, hi = 101;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if ((double)pr > sweep_s[mid]) lo = mid + 1; else hi = mid;
+                        }
+                        atomicAdd(&sh[kEvConfLen + kEvTotLen + (i * 2 + y) * 102 + lo], 1u);
+                    }
+                }
+                ++n_local;
             }
-            ++n_local;
         }
-        if (++since == 255) {
+        if (++since == 63) {          // 63 trips x 4 patients = 252 <= 255: the 8-bit cells cannot overflow
             flush();
             since = 0;
         }

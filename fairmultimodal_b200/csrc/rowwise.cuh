@@ -13,6 +13,67 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// ---- patient-record loader shared by the loss-statistics and evaluation-count kernels -------------------------------
+// One thread takes kPatPerThread = 4 CONSECUTIVE patients per trip: 12 floats of logits and of labels (3 x 16-byte
+// loads each when the rows are dense: row stride 3 floats) and 4 int64 codes per sensitive attribute (2 x 16-byte
+// loads each).  12 independent 16-byte loads per thread keep ~49 KB per SM in flight at 256 threads per SM, which is
+// what HBM3e needs (bandwidth x latency / 148 SMs ~ 44 KB); one patient per trip left these kernels latency bound
+// at 15-24 % of the copy bandwidth.
+constexpr int kPatPerThread = 4;
+
+struct PatientQuad {
+    float z[kPatPerThread][3];
+    float y[kPatPerThread][3];
+    long long code[3][kPatPerThread];
+    int n;   // patients valid in this quad (0..4)
+};
+
+__device__ __forceinline__ void load_patient_quad(PatientQuad& q, const float* __restrict__ logits, long long ld,
+                                                  const float* __restrict__ labels,
+                                                  const long long* const (&attr)[3], long long b0, long long N,
+                                                  bool vec_ok) {
+    q.n = (int)(N - b0 < kPatPerThread ? (N - b0 < 0 ? 0 : N - b0) : kPatPerThread);
+    if (q.n == kPatPerThread && vec_ok) {
+        const float4* zl = reinterpret_cast<const float4*>(logits + 3 * b0);
+        const float4* yl = reinterpret_cast<const float4*>(labels + 3 * b0);
+        float4 zv[3], yv[3];
+        longlong2 cv[3][2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            zv[k] = __ldg(zl + k);
+            yv[k] = __ldg(yl + k);
+            cv[k][0] = __ldg(reinterpret_cast<const longlong2*>(attr[k] + b0));
+            cv[k][1] = __ldg(reinterpret_cast<const longlong2*>(attr[k] + b0) + 1);
+        }
+        const float* zf = reinterpret_cast<const float*>(zv);
+        const float* yf = reinterpret_cast<const float*>(yv);
+#pragma unroll
+        for (int u = 0; u < kPatPerThread; ++u)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                q.z[u][i] = zf[3 * u + i];
+                q.y[u][i] = yf[3 * u + i];
+            }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            q.code[k][0] = cv[k][0].x; q.code[k][1] = cv[k][0].y;
+            q.code[k][2] = cv[k][1].x; q.code[k][3] = cv[k][1].y;
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < kPatPerThread; ++u) {
+            const bool live = u < q.n;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                q.z[u][i] = live ? __ldg(logits + (b0 + u) * ld + i) : 0.f;
+                q.y[u][i] = live ? __ldg(labels + 3 * (b0 + u) + i) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) q.code[k][u] = live ? __ldg(attr[k] + b0 + u) : 0;
+        }
+    }
+}
+
 __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float* f) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll

@@ -156,7 +156,8 @@ typedef struct {
     int64_t ld_ctx;
     int32_t batch, seq, heads, head_dim;
     float scale;
-    int32_t algo; /* 0 = auto; 1 = full-row TMEM kernel (head_dim 64, seq <= 512); 2 = streaming flash kernel */
+    int32_t algo; /* 0 = auto (= 3); 1 = full-row TMEM kernel (head_dim 64, seq <= 512); 2 = streaming flash kernel,
+                     one 128-query tile per CTA; 3 = persistent kernel, two 128-query tiles per CTA */
 } fame_attn_fwd_args;
 int fame_attn_fwd(const fame_attn_fwd_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
 
@@ -244,8 +245,10 @@ int fame_fusion_fwd(const fame_fusion_fwd_args* a, void* workspace, size_t works
  * statistics in between (every rank then evaluates the GLOBAL-batch loss and the gradient of its own patients):
  *   fame_loss_stats   : per-rank statistics -> stats[FAME_LOSS_STATS_LEN] (int64; counts and fixed-point sums)
  *   fame_loss_fwd_bwd : stats -> loss_out = {total, bce, leddi, l1} and dlogits = d total / d fused_logits
- * stats layout: [0..2] sum|p-y| (2^32 fixed point); [3..5] BCE sums (2^24); [6..77] subgroup error sums
- * [outcome][attr][code 0..7] (2^32); [78..101] subgroup counts [attr][code]; [102] patients; [103] bad-code flag.
+ * stats layout: [0..2] sum|p-y| (2^24 fixed point); [3..5] BCE sums (2^24); [6..77] subgroup error sums
+ * [outcome][attr][code 0..7] (2^24); [78..101] subgroup counts [attr][code]; [102] patients; [103] bad-code flag.
+ * Every patient's term is rounded to fixed point BEFORE it is added, so all 104 values are exact integer sums:
+ * shards of a batch (data-parallel ranks) add up bit for bit to the statistics of the whole batch.
  * Subgroup membership = the int64 code itself (0..7), groups "present" = count > 0 (torch.unique, 10_FAME.py:432). */
 #define FAME_LOSS_STATS_LEN 104
 typedef struct {

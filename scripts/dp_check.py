@@ -56,7 +56,7 @@ dist.all_reduce(st_s)
 st_f = ops.loss_stats(z, full[8], attrs_f, pw)
 counts_equal = bool(torch.equal(st_s[78:103], st_f[78:103]))
 sums_close = int((st_s[:78] - st_f[:78]).abs().max().item())
-ok = dl < 1e-4 and rel < 2e-2 and counts_equal and sums_close <= 64
+ok = dl < 1e-4 and rel < 2e-2 and counts_equal and sums_close == 0
 print(f"[rank {rank}] world={world} |loss_dp - loss_1|={dl:.2e} grad rel diff={rel:.3e} counts_equal={counts_equal} "
       f"fixed-point sum diff={sums_close} -> {'OK' if ok else 'FAIL'}", flush=True)
 dist.barrier()

@@ -116,13 +116,13 @@ def test_loss_matches_oracle(B, seed):
     s = stats.cpu().numpy()
     np.testing.assert_array_equal(s[78:102].reshape(3, 8), counts)                 # membership counts: bit-exact
     assert s[102] == B and s[103] == 0
-    np.testing.assert_allclose(s[6:78].reshape(3, 3, 8) / 2.0 ** 32, sums, atol=1e-5 * max(1, B / 100))
+    np.testing.assert_allclose(s[6:78].reshape(3, 3, 8) / 2.0 ** 24, sums, atol=1e-5 * max(1, B / 100))
     gref = z.grad
     assert (dz.cpu() - gref).abs().max().item() <= 2e-6 + 1e-3 * gref.abs().max().item()
 
 
 def test_loss_stats_shard_sum_equals_global():
-    """Virtual ranks: statistics of shards add up to the statistics of the concatenated batch (counts exactly)."""
+    """Virtual ranks: statistics of shards add up to the statistics of the concatenated batch, bit for bit."""
     from fairmultimodal_b200 import ops, synth
     co = synth.make_cohort(128, lab_tokens=4, chunks=0, with_tokens=False, seed=8)
     z = torch.randn(128, 3, device="cuda")
@@ -135,8 +135,7 @@ def test_loss_stats_shard_sum_equals_global():
         sl = slice(32 * r, 32 * (r + 1))
         acc += ops.loss_stats(z[sl], y[sl], [a[sl] for a in attrs], pw)
     f, a = full.cpu().numpy(), acc.cpu().numpy()
-    np.testing.assert_array_equal(f[78:103], a[78:103])
-    assert np.abs(f[:78] - a[:78]).max() <= 64        # fixed point 2^32: a few ulps of float rounding per shard
+    np.testing.assert_array_equal(f, a)     # per-patient fixed point + integer sums: every statistic is bit-exact
     # and the loss evaluated from either is the same to 1e-6
     l1, _ = ops.loss_fwd_bwd(z, y, attrs, pw, full, None, 0.8, 0.0)
     l2, _ = ops.loss_fwd_bwd(z, y, attrs, pw, acc, None, 0.8, 0.0)

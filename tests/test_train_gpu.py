@@ -144,7 +144,12 @@ def test_train_step_matches_reference_golden(golden_dir):
 
 
 def test_cuda_graph_step_equals_eager_steps():
-    """train_step replays a captured CUDA graph from the third batch of a shape on; same trajectory as eager."""
+    """train_step replays a captured CUDA graph from the third batch of a shape on; same trajectory as eager.
+
+    Two EAGER runs of the same five steps already differ (float-atomic summation order in the bias / LayerNorm /
+    embedding gradient kernels, amplified by Adam, which turns every gradient into a step of ~lr whatever its size:
+    measured on B200 with scripts/graph_vs_eager.py, eager-vs-eager update difference 9.4 %, graph-vs-eager 9.6 % /
+    3.0 %).  So the graph run is required to sit inside that run-to-run spread, not to be bit-identical."""
     from fairmultimodal_b200 import synth, train
     L, B = 24, 8
     co = synth.make_cohort(B * 5, lab_tokens=L, chunks=0, with_tokens=False, seed=31)
@@ -152,8 +157,8 @@ def test_cuda_graph_step_equals_eager_steps():
     batches = [[torch.from_numpy(co[k][i * B:(i + 1) * B]) for k in KEYS9] for i in range(5)]
     pw = torch.tensor([3.0, 1.2, 0.6])
     out = {}
-    for mode in (True, False):
-        train.USE_CUDA_GRAPH = mode
+    for mode in ("graph", "eager", "eager2"):
+        train.USE_CUDA_GRAPH = mode == "graph"
         model, _ = _model(L, 12)
         crit = torch.nn.BCEWithLogitsLoss(pos_weight=pw.cuda())
         opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
@@ -161,15 +166,16 @@ def test_cuda_graph_step_equals_eager_steps():
         losses = train.train_step(model, batches, opt, "cuda", crit, lambda_edd=0.8, lambda_l1=0.01)
         st = train.get_state(model)
         assert st.step_dev.item() == 5
-        if mode:
+        if mode == "graph":
             assert any(e["graph"] is not None for e in st.graphs.values())
         out[mode] = (losses, st.p - p0)
     train.USE_CUDA_GRAPH = True
-    assert out[True][0][0] == pytest.approx(out[False][0][0], rel=3e-3)
-    # Adam turns every gradient into a step of ~lr regardless of its size, so elements whose gradient is float-atomic
-    # noise may move differently between two runs; the update as a whole must agree
-    d_g, d_e = out[True][1], out[False][1]
-    assert ((d_g - d_e).norm() / d_e.norm()).item() < 0.05
+    assert out["graph"][0][0] == pytest.approx(out["eager"][0][0], rel=3e-3)
+    assert out["graph"][0][1] == pytest.approx(out["eager"][0][1], rel=3e-3)
+    d_g, d_e, d_e2 = out["graph"][1], out["eager"][1], out["eager2"][1]
+    spread = ((d_e - d_e2).norm() / d_e.norm()).item()
+    diff = min(((d_g - d_e).norm() / d_e.norm()).item(), ((d_g - d_e2).norm() / d_e.norm()).item())
+    assert diff <= 1.5 * spread + 0.02, (diff, spread)
 
 
 def test_all_gradients_match_oracle_autograd():
