@@ -108,9 +108,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = 1
-    for _ in range(args.warmup):
-        pass                                                   # warm-up is inside cpu_reference (thread pool)
+    per_step = args.ref_chunks_per_step                       # bounded sample of the 256-chunk step
+    if args.warmup > 0:
+        cpu_reference_chunks_per_s(min(args.warmup, 3))        # untimed warm-up chunks (thread pool, allocator)
     v, threads, dt = cpu_reference_chunks_per_s(per_step * args.steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "chunks/s", "n_gpus": args.gpus,
@@ -333,7 +333,9 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-chunks", type=int, default=3, help="chunks timed for the cpu_baseline leg")
+    ap.add_argument("--cpu-chunks", type=int, default=160, help="chunks timed for the cpu_baseline leg (~10-20 s)")
+    ap.add_argument("--ref-chunks-per-step", type=int, default=16,
+                    help="--impl reference: chunks per step (bounded sample of the 256-chunk step)")
     ap.add_argument("--skip-train", action="store_true", help="only the note-encoder workload")
     ap.add_argument("--train-steps", type=int, default=20)
     a = ap.parse_args()

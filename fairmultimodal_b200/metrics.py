@@ -105,6 +105,23 @@ def compute_eddi(y_true, y_pred, sensitive_labels, threshold=0.5, complete_group
     return e, {keyt(g): v for g, v in sub.items()}
 
 
+def calculate_tpr_and_fpr(y_true, y_pred, group_mask, device="cuda"):
+    """Drop-in for 10_FAME.py:84-97: (TPR, FPR) of the 0/1 predictions inside `group_mask`; 0 where a denominator
+    is 0.  The four confusion counts come from the count kernel (membership code 1 = inside the mask)."""
+    n = len(y_true)
+    lab3 = np.zeros((n, 3), np.float32)
+    lab3[:, 0] = np.asarray(y_true)
+    pr3 = np.zeros((n, 3), np.float32)
+    pr3[:, 0] = np.asarray(y_pred)
+    member = _dev(np.asarray(group_mask).astype(np.int64), torch.int64, device)
+    c = Counts(ops.eval_counts(_dev(pr3, torch.float32, device), _dev(lab3, torch.float32, device), [member] * 3,
+                               (0.5, 2.0, 2.0), logits_are_probs=True))
+    tp, fn, fp, tn = (int(v) for v in c.conf[0, 0, 1])
+    tpr = tp / (tp + fn) if (tp + fn) > 0 else 0
+    fpr = fp / (fp + tn) if (fp + tn) > 0 else 0
+    return tpr, fpr
+
+
 def print_fairness_metrics(y_true, y_pred, demographics, sensitive_attr_name, device="cuda", verbose=True):
     """Drop-in for 10_FAME.py:99-122: y_pred are 0/1 predictions."""
     n = len(y_true)

@@ -210,6 +210,19 @@ def test_compute_eddi_dropin_and_counts_vs_oracle():
     assert c.n == 3001
 
 
+def test_calculate_tpr_and_fpr_dropin():
+    """10_FAME.py:84-97 semantics: rates inside the mask, 0 where a denominator is 0 (checked against the oracle)."""
+    from fairmultimodal_b200 import metrics as M
+    from oracle import fame_oracle as O
+    rng = np.random.default_rng(4)
+    y = (rng.random(997) < 0.3).astype(np.int64)
+    pred = (rng.random(997) < 0.4).astype(np.int64)
+    for mask in (rng.random(997) < 0.5, np.zeros(997, bool), y == 0, y == 1):
+        tpr, fpr = M.calculate_tpr_and_fpr(y, pred, mask)
+        rt, rf, _ = O.group_rates(y, pred, mask)
+        assert tpr == rt and fpr == rf
+
+
 def test_rank_metrics_ties_and_large_n():
     from fairmultimodal_b200 import metrics as M
     from oracle import fame_oracle as O
