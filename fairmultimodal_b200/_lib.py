@@ -151,7 +151,7 @@ class GemmExArgs(C.Structure):
         ("y", C.c_void_p), ("ldy", C.c_int64), ("y_stride_b0", C.c_int64), ("y_stride_b1", C.c_int64),
         ("y_dtype", C.c_int32),
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("nb0", C.c_int32), ("nb1", C.c_int32),
-        ("act", C.c_int32), ("alpha", C.c_float), ("n_valid", C.c_int32),
+        ("act", C.c_int32), ("alpha", C.c_float), ("n_valid", C.c_int32), ("split_k", C.c_int32),
     ]
 
 
@@ -177,6 +177,8 @@ FLAT_OPS = {
     "fame_grad_sumsq": [_P, _I64, _P],
     "fame_clip_adamw": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _I32, _P, _P, _P, _P],
     "fame_cast_bf16": [_P, _P, _I64],
+    "fame_transpose_bf16_table": [_P, _I32, _I32],
+    "fame_wgrad_small": [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32],
 }
 
 # name -> args struct for every `int fame_<op>(const args*, void* ws, size_t ws_bytes, stream)` entry point
@@ -198,7 +200,7 @@ OP_TABLE = {
     "fame_gemm_ex": GemmExArgs,
 }
 PLAIN_SYMBOLS = ["fame_strerror", "fame_last_cuda_error", "fame_abi_version", "fame_device_check", "fame_sm_count",
-                 "fame_rank_counts_workspace_bytes"]
+                 "fame_rank_counts_workspace_bytes", "fame_fusion_fwd_workspace_bytes"]
 # C struct name -> ctypes mirror (tests compare sizeof() of both)
 STRUCT_NAMES = {
     "fame_gemm_args": GemmArgs, "fame_layernorm_args": LayerNormArgs, "fame_bert_embed_args": BertEmbedArgs,
@@ -231,6 +233,8 @@ def load() -> C.CDLL:
         getattr(lib, name).argtypes = []
     lib.fame_rank_counts_workspace_bytes.restype = C.c_size_t
     lib.fame_rank_counts_workspace_bytes.argtypes = [C.c_int32]
+    lib.fame_fusion_fwd_workspace_bytes.restype = C.c_size_t
+    lib.fame_fusion_fwd_workspace_bytes.argtypes = [C.c_int32]
     for name, struct in OP_TABLE.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int

@@ -14,8 +14,12 @@
 #include "heads.cuh"
 #include "metrics.cuh"
 #include "rowwise.cuh"
+#include "skinny_gemm.cuh"
 
 // which kernel algo == 0 (auto) picks for head_dim 64, seq <= 512: 1 = full-row TMEM kernel, 0 = flash kernel
+#ifndef FAME_USE_SKINNY_GEMM
+#define FAME_USE_SKINNY_GEMM 1
+#endif
 #ifndef FAME_ATTN_AUTO_FULLROW
 #define FAME_ATTN_AUTO_FULLROW 0  /* measured on B200, 256 x 12 heads x 512: flash 0.69 ms vs full-row 0.81 ms */
 #endif
@@ -399,7 +403,14 @@ int fame_demo_add(const fame_demo_add_args* a, void*, size_t, fame_stream_t stre
 }
 
 // ------------------------------------------------------------------------------------------------ K7
-int fame_fusion_fwd(const fame_fusion_fwd_args* a, void*, size_t, fame_stream_t stream) {
+// few patients: 3 launches whose CTAs own output columns (heads.cuh); needs room for proj / gated / pre_relu when the
+// caller does not ask for them
+static const int kFusionSmallMaxB = 1024;
+size_t fame_fusion_fwd_workspace_bytes(int32_t B) {
+    return (B > 0 && B <= kFusionSmallMaxB) ? (size_t)B * (768 + 768 + 512) * sizeof(float) : 0;
+}
+
+int fame_fusion_fwd(const fame_fusion_fwd_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream) {
     if (a == nullptr || a->logits == nullptr || a->wp_t == nullptr || a->bp == nullptr || a->sig_w == nullptr ||
         a->w3_t == nullptr || a->b3 == nullptr || a->w4 == nullptr || a->b4 == nullptr)
         return FAME_ERR_NULLPTR;
@@ -426,6 +437,20 @@ int fame_fusion_fwd(const fame_fusion_fwd_args* a, void*, size_t, fame_stream_t 
     p.wc = a->wc; p.bc = a->bc; p.proj = a->proj; p.gated = a->gated; p.pre_relu = a->pre_relu;
     p.logits = a->logits; p.mod_logits = a->mod_logits; p.sig_out = a->sig_out; p.B = a->B;
     const int grid = (a->B + fame::kFuRows - 1) / fame::kFuRows;
+    if (a->B <= kFusionSmallMaxB) {
+        float* ws = reinterpret_cast<float*>(workspace);
+        const bool need_ws = a->proj == nullptr || a->gated == nullptr || a->pre_relu == nullptr;
+        if (need_ws && (ws == nullptr || workspace_bytes < fame_fusion_fwd_workspace_bytes(a->B))) return FAME_ERR_WORKSPACE;
+        if (need_ws && !aligned16(ws)) return FAME_ERR_ALIGN;
+        float* proj = a->proj != nullptr ? a->proj : ws;
+        float* gated = a->gated != nullptr ? a->gated : ws + (size_t)a->B * 768;
+        float* pre = a->pre_relu != nullptr ? a->pre_relu : ws + (size_t)a->B * 1536;
+        if (!aligned16(proj) || !aligned16(gated) || !aligned16(pre)) return FAME_ERR_ALIGN;
+        fame::fusion_small_proj_kernel<<<dim3(24, grid), 256, 0, stream>>>(p, proj, gated);
+        fame::fusion_small_hidden_kernel<<<dim3(16, grid), 256, 0, stream>>>(p, gated, pre);
+        fame::fusion_small_logits_kernel<<<grid, 256, 0, stream>>>(p, proj, pre);
+        return launch_status();
+    }
     fame::fusion_fwd_kernel<<<grid, fame::kFuThreads, fame::kFuSmemBytes, stream>>>(p);
     return launch_status();
 }

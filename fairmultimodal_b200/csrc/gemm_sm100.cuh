@@ -50,6 +50,9 @@ struct GemmParams {
     int act;
     int y_f32;
     float alpha;                    // scales the accumulator before bias / activation
+    int split_k;                    // >= 1.  > 1: the K range is cut into split_k slices, one tile-task per slice;
+    int kb_per_split;               //        f32 output only
+    int atomic_out;                 // 1: tiles are ADDED to y with float4 atomics (split-K / accumulate mode)
 };
 
 // erf-GELU (HF "gelu", modeling_bert.py:339-342):  0.5 x (1 + erf(x / sqrt 2)).
@@ -98,7 +101,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int m_tiles = (p.M + kGemmBM - 1) / kGemmBM;
     const int n_tiles = (p.N + kGemmBN - 1) / kGemmBN;
     const int tiles_per_batch = m_tiles * n_tiles;
-    const int num_tiles = tiles_per_batch * p.nb0 * p.nb1;
+    // task = (output tile, k slice); the slice index is innermost so that the slices of one tile run concurrently
+    const int num_tiles = tiles_per_batch * p.nb0 * p.nb1 * p.split_k;
     const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
 
     if (warp == 0 && lane == 0) {
@@ -131,11 +135,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             // ------------------------------------------------ TMA producer
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int task = blockIdx.x; task < num_tiles; task += gridDim.x) {
+                const int tile = task / p.split_k, ks = task % p.split_k;
                 const int bidx = tile / tiles_per_batch, t2 = tile % tiles_per_batch;
                 const int b0 = bidx / p.nb1, b1 = bidx % p.nb1;
                 const int m_blk = t2 / n_tiles, n_blk = t2 % n_tiles;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb_lo = ks * p.kb_per_split, kb_hi = min(num_kb, kb_lo + p.kb_per_split);
+                for (int kb = kb_lo; kb < kb_hi; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], kGemmStageBytes);
                     uint8_t* sa = smem_a + stage * kGemmABytes;
@@ -168,11 +174,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int task = blockIdx.x; task < num_tiles; task += gridDim.x) {
+                const int kb_lo = (task % p.split_k) * p.kb_per_split, kb_hi = min(num_kb, kb_lo + p.kb_per_split);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kGemmBN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb_lo; kb < kb_hi; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem_a + stage * kGemmABytes);
@@ -185,7 +192,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                                     : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
                         const uint64_t bdesc = kBMn ? make_smem_desc_sw128(b_addr + k * 2048, kGemmSubTile, 1024)
                                                     : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                        umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+                        umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb != kb_lo) || (k != 0));
                     }
                     umma_commit(&empty_bar[stage]);
                     if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
@@ -205,7 +212,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int sw = r_local & 7;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int task = blockIdx.x; task < num_tiles; task += gridDim.x) {
+            const int tile = task / p.split_k;
+            const bool first_slice = (task % p.split_k) == 0;   // bias / residual are added by one slice only
             const int bidx = tile / tiles_per_batch, t2 = tile % tiles_per_batch;
             const int b0 = bidx / p.nb1, b1 = bidx % p.nb1;
             const int m_blk = t2 / n_tiles, n_blk = t2 % n_tiles;
@@ -237,7 +246,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 }
                 if (!active) continue;
-                if (p.bias != nullptr) {
+                if (p.bias != nullptr && first_slice) {
 #pragma unroll
                     for (int j = 0; j < 64; j += 4) {
                         if (col0 + j < p.N) {
@@ -253,7 +262,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                     for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.0f);
                 }
-                if (p.res_mode != kResNone && row_ok) {
+                if (p.res_mode != kResNone && row_ok && first_slice) {
                     const long long roff = (long long)b0 * p.rs_b0 + (long long)b1 * p.rs_b1 + (long long)row * p.ldr + col0;
                     if (p.res_mode == kResAddF32) {
                         const float* rp = reinterpret_cast<const float*>(p.residual) + roff;
@@ -291,10 +300,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     if (row_ok) {
                         float* yp = reinterpret_cast<float*>(p.y) + (long long)b0 * p.ys_b0 + (long long)b1 * p.ys_b1 +
                                     (long long)row * p.ldy + col0;
+                        if (p.atomic_out) {
 #pragma unroll
-                        for (int j = 0; j < 64; j += 4) {
-                            if (col0 + j < p.N)
-                                *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            for (int j = 0; j < 64; j += 4) {
+                                if (col0 + j < p.N)
+                                    atomicAdd(reinterpret_cast<float4*>(yp + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 64; j += 4) {
+                                if (col0 + j < p.N)
+                                    *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            }
                         }
                     }
                 } else {

@@ -72,16 +72,30 @@ fusion_fwd_kernel(const FusionParams p) {
         for (int r = 0; r < kFuRows; ++r) acc[r] = 0.f;
         const float* w = p.wp_t + (long long)m * 768 * 256 + t;
         const float* xm = xin + m * kFuRows * 768;
-        for (int k = 0; k < 768; k += 4) {
-            const float w0 = __ldg(w + (k + 0) * 256), w1 = __ldg(w + (k + 1) * 256), w2 = __ldg(w + (k + 2) * 256),
-                        w3 = __ldg(w + (k + 3) * 256);
+        // software-pipelined weight stream: the next 16 weights are in flight while the current 16 are consumed
+        // (a 4-deep dependent loop left the kernel latency bound: 345 us at 32 patients)
+        constexpr int KU = 16;
+        float wn[KU];
+#pragma unroll
+        for (int u = 0; u < KU; ++u) wn[u] = __ldg(w + u * 256);
+        for (int k = 0; k < 768; k += KU) {
+            float wc[KU];
+#pragma unroll
+            for (int u = 0; u < KU; ++u) wc[u] = wn[u];
+            if (k + KU < 768) {
+#pragma unroll
+                for (int u = 0; u < KU; ++u) wn[u] = __ldg(w + (k + KU + u) * 256);
+            }
 #pragma unroll
             for (int r = 0; r < kFuRows; ++r) {
-                const float4 x = *reinterpret_cast<const float4*>(xm + r * 768 + k);
-                acc[r] = fmaf(x.x, w0, acc[r]);
-                acc[r] = fmaf(x.y, w1, acc[r]);
-                acc[r] = fmaf(x.z, w2, acc[r]);
-                acc[r] = fmaf(x.w, w3, acc[r]);
+#pragma unroll
+                for (int u = 0; u < KU; u += 4) {
+                    const float4 x = *reinterpret_cast<const float4*>(xm + r * 768 + k + u);
+                    acc[r] = fmaf(x.x, wc[u], acc[r]);
+                    acc[r] = fmaf(x.y, wc[u + 1], acc[r]);
+                    acc[r] = fmaf(x.z, wc[u + 2], acc[r]);
+                    acc[r] = fmaf(x.w, wc[u + 3], acc[r]);
+                }
             }
         }
         const float b = __ldg(p.bp + m * 256 + t);
@@ -111,20 +125,37 @@ fusion_fwd_kernel(const FusionParams p) {
 #pragma unroll
         for (int r = 0; r < kFuRows; ++r) a0[r] = a1[r] = 0.f;
         const float* w = p.w3_t + t;
-        for (int k = 0; k < 768; k += 4) {
-            float wa[4], wb[4];
+        constexpr int KU = 8;
+        float wan[KU], wbn[KU];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                wa[u] = __ldg(w + (k + u) * 512);
-                wb[u] = __ldg(w + (k + u) * 512 + 256);
+        for (int u = 0; u < KU; ++u) {
+            wan[u] = __ldg(w + u * 512);
+            wbn[u] = __ldg(w + u * 512 + 256);
+        }
+        for (int k = 0; k < 768; k += KU) {
+            float wa[KU], wb[KU];
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                wa[u] = wan[u];
+                wb[u] = wbn[u];
+            }
+            if (k + KU < 768) {
+#pragma unroll
+                for (int u = 0; u < KU; ++u) {
+                    wan[u] = __ldg(w + (k + KU + u) * 512);
+                    wbn[u] = __ldg(w + (k + KU + u) * 512 + 256);
+                }
             }
 #pragma unroll
             for (int r = 0; r < kFuRows; ++r) {
-                const float4 x = *reinterpret_cast<const float4*>(g + r * 768 + k);
-                a0[r] = fmaf(x.x, wa[0], a0[r]); a0[r] = fmaf(x.y, wa[1], a0[r]);
-                a0[r] = fmaf(x.z, wa[2], a0[r]); a0[r] = fmaf(x.w, wa[3], a0[r]);
-                a1[r] = fmaf(x.x, wb[0], a1[r]); a1[r] = fmaf(x.y, wb[1], a1[r]);
-                a1[r] = fmaf(x.z, wb[2], a1[r]); a1[r] = fmaf(x.w, wb[3], a1[r]);
+#pragma unroll
+                for (int u = 0; u < KU; u += 4) {
+                    const float4 x = *reinterpret_cast<const float4*>(g + r * 768 + k + u);
+                    a0[r] = fmaf(x.x, wa[u], a0[r]); a0[r] = fmaf(x.y, wa[u + 1], a0[r]);
+                    a0[r] = fmaf(x.z, wa[u + 2], a0[r]); a0[r] = fmaf(x.w, wa[u + 3], a0[r]);
+                    a1[r] = fmaf(x.x, wb[u], a1[r]); a1[r] = fmaf(x.y, wb[u + 1], a1[r]);
+                    a1[r] = fmaf(x.z, wb[u + 2], a1[r]); a1[r] = fmaf(x.w, wb[u + 3], a1[r]);
+                }
             }
         }
         const float b0 = __ldg(p.b3 + t), b1 = __ldg(p.b3 + t + 256);
@@ -171,6 +202,127 @@ fusion_fwd_kernel(const FusionParams p) {
                     if (lane == 0)
                         p.mod_logits[((long long)m * p.B + row0 + r) * 3 + o] = c[o] + __ldg(p.bc + m * 3 + o);
                 }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K7, few patients
+// The fused kernel above gives one CTA per 8 patients: at the training batch size (32 per GPU) that is 4 CTAs, each
+// streaming all 2.75 MB of fp32 head weights through 16 KB of loads in flight -- 230-345 us of pure latency.  For small
+// batches the head is therefore split into three launches whose CTAs each own 32 OUTPUT COLUMNS (x 8 patients) and
+// whose 8 warps split the 768-long contraction, so the weight stream is spread over 24 / 16 column groups x B/8
+// row groups: same arithmetic in fp32, same outputs, ~10 us in total.
+constexpr int kFsCols = 32;      // output columns per CTA (lane = column: weight rows are read 128 bytes at a time)
+constexpr int kFsKU = 12;        // weight loads in flight per thread (96 per warp slice / 8 trips)
+
+// y[r, col] = sum_k x[r, k] * wt[k, col]   for the CTA's 8 rows and 32 columns; wt is [768][ldw] (transposed weight)
+__device__ __forceinline__ void fusion_small_tile(const float* __restrict__ xs /* smem [8][768] */,
+                                                  const float* __restrict__ wt, int ldw, int col,
+                                                  float (*red)[kFuRows][kFsCols], float (&out)[1], int warp, int lane) {
+    float acc[kFuRows];
+#pragma unroll
+    for (int r = 0; r < kFuRows; ++r) acc[r] = 0.f;
+    const int kb = warp * 96;
+    const float* w = wt + (long long)kb * ldw + col;
+    for (int k0 = 0; k0 < 96; k0 += kFsKU) {
+        float wv[kFsKU];
+#pragma unroll
+        for (int u = 0; u < kFsKU; ++u) wv[u] = __ldg(w + (long long)(k0 + u) * ldw);
+#pragma unroll
+        for (int u = 0; u < kFsKU; ++u)
+#pragma unroll
+            for (int r = 0; r < kFuRows; ++r) acc[r] = fmaf(xs[r * 768 + kb + k0 + u], wv[u], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kFuRows; ++r) red[warp][r][lane] = acc[r];
+    __syncthreads();
+    // thread (r = warp, c = lane) adds the 8 K-slices in a fixed order
+    float v = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) v += red[w8][warp][lane];
+    out[0] = v;
+}
+
+__global__ void __launch_bounds__(256)
+fusion_small_proj_kernel(const FusionParams p, float* __restrict__ proj, float* __restrict__ gated) {
+    __shared__ __align__(16) float xs[kFuRows * 768];
+    __shared__ float red[8][kFuRows][kFsCols];
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int m = blockIdx.x / 8, col_in_m = (blockIdx.x % 8) * kFsCols + lane;
+    const int row0 = blockIdx.y * kFuRows;
+    const int nrow = min(kFuRows, p.B - row0);
+    for (int i = t; i < kFuRows * 192; i += 256) {
+        const int r = i / 192, c4 = i % 192;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nrow) v = __ldg(reinterpret_cast<const float4*>(p.emb[m] + (long long)(row0 + r) * 768) + c4);
+        reinterpret_cast<float4*>(xs + r * 768)[c4] = v;
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && p.sig_out != nullptr)
+        for (int i = t; i < 768; i += 256) p.sig_out[i] = 1.0f / (1.0f + expf(-p.sig_w[i]));
+    __syncthreads();
+    float v[1];
+    fusion_small_tile(xs, p.wp_t + (long long)m * 768 * 256, 256, col_in_m, red, v, warp, lane);
+    const int r = warp;
+    if (r < nrow) {
+        const int c = m * 256 + col_in_m;
+        const float pr = fmaxf(v[0] + __ldg(p.bp + c), 0.f);
+        const float sg = 1.0f / (1.0f + expf(-__ldg(p.sig_w + c)));
+        proj[(long long)(row0 + r) * 768 + c] = pr;
+        gated[(long long)(row0 + r) * 768 + c] = (p.w_mod[m] * pr) * sg;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fusion_small_hidden_kernel(const FusionParams p, const float* __restrict__ gated, float* __restrict__ pre_relu) {
+    __shared__ __align__(16) float xs[kFuRows * 768];
+    __shared__ float red[8][kFuRows][kFsCols];
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int col = blockIdx.x * kFsCols + lane;
+    const int row0 = blockIdx.y * kFuRows;
+    const int nrow = min(kFuRows, p.B - row0);
+    for (int i = t; i < kFuRows * 192; i += 256) {
+        const int r = i / 192, c4 = i % 192;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nrow) v = *(reinterpret_cast<const float4*>(gated + (long long)(row0 + r) * 768) + c4);
+        reinterpret_cast<float4*>(xs + r * 768)[c4] = v;
+    }
+    __syncthreads();
+    float v[1];
+    fusion_small_tile(xs, p.w3_t, 512, col, red, v, warp, lane);
+    if (warp < nrow) pre_relu[(long long)(row0 + warp) * 512 + col] = v[0] + __ldg(p.b3 + col);
+}
+
+// logits (512 -> 3) and the 9 modality logits (256 -> 3 each): one warp per patient
+__global__ void __launch_bounds__(256)
+fusion_small_logits_kernel(const FusionParams p, const float* __restrict__ proj, const float* __restrict__ pre_relu) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= p.B) return;
+    float l[3] = {0.f, 0.f, 0.f};
+    for (int k = lane; k < 512; k += 32) {
+        const float h = fmaxf(pre_relu[(long long)row * 512 + k], 0.f);
+#pragma unroll
+        for (int o = 0; o < 3; ++o) l[o] = fmaf(h, __ldg(p.w4 + o * 512 + k), l[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        l[o] = warp_sum(l[o]);
+        if (lane == 0) p.logits[(long long)row * 3 + o] = l[o] + __ldg(p.b4 + o);
+    }
+    if (p.mod_logits != nullptr) {
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            float c[3] = {0.f, 0.f, 0.f};
+            for (int k = lane; k < 256; k += 32) {
+                const float x = proj[(long long)row * 768 + m * 256 + k];
+#pragma unroll
+                for (int o = 0; o < 3; ++o) c[o] = fmaf(x, __ldg(p.wc + (m * 3 + o) * 256 + k), c[o]);
+            }
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                c[o] = warp_sum(c[o]);
+                if (lane == 0) p.mod_logits[((long long)m * p.B + row) * 3 + o] = c[o] + __ldg(p.bc + m * 3 + o);
             }
         }
     }

@@ -33,15 +33,16 @@ def stop_trace():
     return t
 
 
-def _call(name, args, work=0.0, tag=""):
+def _call(name, args, work=0.0, tag="", ws=None):
     global LAUNCHES
     LAUNCHES += 1
+    wp, wb = (ws.data_ptr(), ws.numel() * ws.element_size()) if ws is not None else (0, 0)
     if _TRACE is None:
-        _lib.call(name, args, _stream())
+        _lib.call(name, args, _stream(), wp, wb)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    _lib.call(name, args, _stream())
+    _lib.call(name, args, _stream(), wp, wb)
     e1.record()
     _TRACE.append((name, tag, e0, e1, work))
 
@@ -267,7 +268,9 @@ def fusion_fwd(emb, packed, w_mod, want_mod_logits=False, want_intermediates=Fal
         out["pre_relu"] = torch.empty((B, 512), device=dev, dtype=torch.float32)
         a.proj, a.gated, a.pre_relu = out["proj"].data_ptr(), out["gated"].data_ptr(), out["pre_relu"].data_ptr()
     a.B = B
-    _call("fame_fusion_fwd", a, B * (3 * 768 * 4.0 + 3 * 4.0) + 4.0 * (3 * 768 * 256 + 768 * 512))
+    ws_bytes = 0 if want_intermediates else _lib.load().fame_fusion_fwd_workspace_bytes(B)
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8) if ws_bytes else None
+    _call("fame_fusion_fwd", a, B * (3 * 768 * 4.0 + 3 * 4.0) + 4.0 * (3 * 768 * 256 + 768 * 512), ws=ws)
     return out
 
 

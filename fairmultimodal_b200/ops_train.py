@@ -29,7 +29,7 @@ def _p(t):
 
 def gemm_ex(a, b, y, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldy=None, bias=None, aux=None,
             aux_mode=AUX_NONE, ld_aux=0, act=0, alpha=1.0, nb0=1, nb1=1, sa=(0, 0), sb=(0, 0), sy=(0, 0), saux=(0, 0),
-            n_valid=0, a_off=0, b_off=0, y_off=0, aux_off=0, tag=""):
+            n_valid=0, a_off=0, b_off=0, y_off=0, aux_off=0, tag="", split_k=0):
     """General tcgen05 GEMM (fame_gemm_ex).  a / b / y / aux are tensors (any shape); geometry is explicit:
     leading dimensions, element offsets and batch strides (b0, b1) in elements."""
     g = _lib.GemmExArgs()
@@ -44,27 +44,40 @@ def gemm_ex(a, b, y, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldy=No
     g.y = y.data_ptr() + y.element_size() * y_off
     g.ldy, g.y_stride_b0, g.y_stride_b1, g.y_dtype = ldy, sy[0], sy[1], _dt(y)
     g.M, g.N, g.K, g.nb0, g.nb1 = M, N, K, nb0, nb1
-    g.act, g.alpha, g.n_valid = act, alpha, n_valid
+    g.act, g.alpha, g.n_valid, g.split_k = act, alpha, n_valid, split_k
     ops._call("fame_gemm_ex", g, 2.0 * M * N * K * nb0 * nb1, tag)
     return y
 
 
-def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, aux=None, aux_mode=AUX_NONE):
-    """dX[T, K] = dY[T, N] @ W[N, K]  (+ aux residual gradient, or ReLU-masked by aux)."""
+SKINNY_MAX_ROWS = 32
+
+
+def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, aux=None, aux_mode=AUX_NONE, wT=None):
+    """dX[T, K] = dY[T, N] @ W[N, K]  (+ aux residual gradient, or ReLU-masked by aux).  With at most 32 rows and a
+    transposed shadow wT [K, N] available the product runs as a K-major x K-major skinny GEMM (weight streaming)."""
     T, N = dy.shape
     K = w.shape[1]
     if out is None:
         out = torch.empty((T, K), device=dy.device, dtype=out_dtype)
+    if wT is not None and T <= SKINNY_MAX_ROWS and N % 32 == 0:
+        return gemm_ex(dy, wT, out, T, K, N, lda=dy.stride(0), ldb=wT.stride(0), ldy=out.stride(0), aux=aux,
+                       aux_mode=aux_mode, ld_aux=aux.stride(0) if aux is not None else 0, tag="dgrad")
     return gemm_ex(dy, w, out, T, K, N, a_mn=False, b_mn=True, lda=dy.stride(0), ldb=w.stride(0), ldy=out.stride(0),
                    aux=aux, aux_mode=aux_mode, ld_aux=aux.stride(0) if aux is not None else 0, tag="dgrad")
 
 
-def linear_wgrad(dy, x, out):
-    """dW[N, K] = dY[T, N]^T @ X[T, K] -> f32 `out` (a view into the flat gradient buffer)."""
+def linear_wgrad(dy, x, out, accumulate=True):
+    """dW[N, K] (+)= dY[T, N]^T @ X[T, K] -> f32 `out` (a view into the flat gradient buffer).  With accumulate (the
+    training step: the buffer was zeroed by zero_grad) the token contraction is split over the SMs (split-K) and the
+    slices are added with float4 atomics; otherwise `out` is overwritten by a single-pass product."""
     T, N = dy.shape
     K = x.shape[1]
+    if T <= SKINNY_MAX_ROWS:
+        _flat("fame_wgrad_small", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0),
+              T, N, K, int(accumulate))
+        return out
     return gemm_ex(dy, x, out, N, K, T, a_mn=True, b_mn=True, lda=dy.stride(0), ldb=x.stride(0), ldy=out.stride(0),
-                   tag="wgrad")
+                   tag="wgrad", split_k=-1 if accumulate else 0)
 
 
 def layernorm_bwd(x, dy, stats, gamma, dgamma, dbeta, want_bf16=True, want_f32=False):
@@ -157,6 +170,10 @@ def clip_adamw(p, g, m, v, sumsq, max_norm, lr, beta1, beta2, eps, weight_decay,
     _flat("fame_clip_adamw", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), sumsq.data_ptr(),
           float(max_norm), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
           _p(grad_norm_out), _p(step_dev), _p(hyper_dev), _p(p_bf16))
+
+
+def transpose_bf16_table(table, n_entries, total_tiles):
+    _flat("fame_transpose_bf16_table", table.data_ptr(), n_entries, total_tiles)
 
 
 def cast_bf16(x, y):

@@ -66,10 +66,44 @@ class FlatTrainState:
         self.hyper_dev = torch.zeros(2, device=dev, dtype=torch.float32)
         self._hyper_host = None
         self.graphs = {}
+        self._build_transposed_shadows(dev)
         self.refresh_bf16()
+
+    # weights of the demographic tower whose data-gradient product runs on the <= 32-row skinny path: dX = dY . W reads
+    # W^T rows, so a transposed bf16 shadow is kept next to the plain one (one table-driven transpose launch per step)
+    _T_SUFFIXES = ("attention.self.value.weight", "attention.output.dense.weight", "intermediate.dense.weight",
+                   "output.dense.weight")
+
+    def _build_transposed_shadows(self, dev):
+        import numpy as np
+        names = [n for n in self.offsets if n.startswith("behrt_demo.bert.encoder.layer.") and n.endswith(self._T_SUFFIXES)]
+        total = sum(self.views[n].numel() for n in names)
+        self.pbT = torch.zeros(max(total, 8), device=dev, dtype=torch.bfloat16)
+        self.tviews = {}
+        rec = np.zeros(len(names), dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("rows", "<i4"), ("cols", "<i4"),
+                                                   ("tile0", "<i4"), ("tiles_x", "<i4")]))
+        off = tiles = 0
+        for i, n in enumerate(names):
+            rows, cols = self.views[n].shape
+            tv = self.pbT[off:off + rows * cols].view(cols, rows)
+            self.tviews[n] = tv
+            tx, ty = (cols + 63) // 64, (rows + 63) // 64
+            rec[i] = (self.bviews[n].data_ptr(), tv.data_ptr(), rows, cols, tiles, tx)
+            tiles += tx * ty
+            off += rows * cols
+        self._t_entries, self._t_tiles = len(names), tiles
+        self._t_table = torch.from_numpy(rec.view(np.uint8).copy()).to(dev) if names else None
+
+    def refresh_transposed(self):
+        if self._t_table is not None:
+            T.transpose_bf16_table(self._t_table, self._t_entries, self._t_tiles)
 
     def refresh_bf16(self):
         T.cast_bf16(self.p, self.pb)
+        self.refresh_transposed()
+
+    def wt(self, name):         # transposed bf16 shadow [in_features, out_features], or None
+        return self.tviews.get(name)
 
     def w(self, name):          # bf16 shadow (GEMM operand)
         return self.bviews[name]
@@ -99,6 +133,7 @@ class FlatTrainState:
         T.grad_sumsq(self.g, self.sumsq)
         T.clip_adamw(self.p, self.g, self.m, self.v, self.sumsq, max_norm, lr, betas[0], betas[1], eps, weight_decay,
                      0, self.grad_norm, step_dev=self.step_dev, hyper_dev=self.hyper_dev, p_bf16=self.pb)
+        self.refresh_transposed()
         self.invalidate_caches()
 
     def invalidate_caches(self):
@@ -163,7 +198,9 @@ def _demo_forward(st, model, ids, age, gender, eth, ins):
 def _lin_bwd(st, wname, bname, dy_bf16, x_bf16, colsum_src=None):
     """Bias and weight gradients of y = x W^T + b into the flat gradient buffer."""
     T.colsum(colsum_src if colsum_src is not None else dy_bf16, st.gr(bname))
-    T.linear_wgrad(dy_bf16, x_bf16, st.gr(wname))
+    # every weight gradient is produced exactly once per step: the <= 32-row kernel overwrites its (already zeroed)
+    # slice with plain stores, the split-K tensor-core product accumulates into it with atomics
+    T.linear_wgrad(dy_bf16, x_bf16, st.gr(wname), accumulate=dy_bf16.shape[0] > T.SKINNY_MAX_ROWS)
 
 
 def _demo_backward(st, model, saved, ddemo):
@@ -178,21 +215,22 @@ def _demo_backward(st, model, saved, ddemo):
                                      st.gr(p + "output.LayerNorm.weight"), st.gr(p + "output.LayerNorm.bias"),
                                      want_bf16=True, want_f32=True)
         _lin_bwd(st, p + "output.dense.weight", p + "output.dense.bias", dt2b, s["h"], colsum_src=dt2f)
-        dh = T.linear_dgrad(dt2b, st.w(p + "output.dense.weight"))
+        dh = T.linear_dgrad(dt2b, st.w(p + "output.dense.weight"), wT=st.wt(p + "output.dense.weight"))
         dpre = T.gelu_bwd(s["pre"], dh)
         _lin_bwd(st, p + "intermediate.dense.weight", p + "intermediate.dense.bias", dpre, s["x1b"])
         dx1 = T.linear_dgrad(dpre, st.w(p + "intermediate.dense.weight"), out_dtype=torch.float32, aux=dt2f,
-                             aux_mode=T.AUX_ADD_F32)
+                             aux_mode=T.AUX_ADD_F32, wT=st.wt(p + "intermediate.dense.weight"))
         dt1b, dt1f = T.layernorm_bwd(s["t1"], dx1, s["st1"], st.f(p + "attention.output.LayerNorm.weight"),
                                      st.gr(p + "attention.output.LayerNorm.weight"),
                                      st.gr(p + "attention.output.LayerNorm.bias"), want_bf16=True, want_f32=True)
         _lin_bwd(st, p + "attention.output.dense.weight", p + "attention.output.dense.bias", dt1b, s["v"], colsum_src=dt1f)
-        dv = T.linear_dgrad(dt1b, st.w(p + "attention.output.dense.weight"))
+        dv = T.linear_dgrad(dt1b, st.w(p + "attention.output.dense.weight"),
+                            wT=st.wt(p + "attention.output.dense.weight"))
         _lin_bwd(st, p + "attention.self.value.weight", p + "attention.self.value.bias", dv, s["xb"])
         # one key per sequence: softmax == 1, so query / key receive exactly zero gradient (their .grad stays 0 and
         # AdamW still applies weight decay to them, as in the reference)
         dx = T.linear_dgrad(dv, st.w(p + "attention.self.value.weight"), out_dtype=torch.float32, aux=dt1f,
-                            aux_mode=T.AUX_ADD_F32)
+                            aux_mode=T.AUX_ADD_F32, wT=st.wt(p + "attention.self.value.weight"))
     e = pre + "embeddings."
     _, dsum = T.layernorm_bwd(saved["esum"], dx, saved["estats"], st.f(e + "LayerNorm.weight"),
                               st.gr(e + "LayerNorm.weight"), st.gr(e + "LayerNorm.bias"), want_bf16=False, want_f32=True)

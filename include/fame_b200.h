@@ -96,6 +96,10 @@ typedef struct {
     int32_t act;
     float alpha;
     int32_t n_valid; /* 0 = N; otherwise B has only n_valid (<= N) rows and output columns beyond it are zeros */
+    int32_t split_k; /* 0 = Y is written.  != 0 = accumulate mode: Y (f32, initialised by the caller, e.g. the zeroed
+                        gradient buffer) += result through float4 atomics, with the contraction cut into n slices
+                        (n > 0) or into as many as fill the SMs (-1).  Used by the weight-gradient products, whose
+                        contraction runs over all tokens while the output has only a few tiles. */
 } fame_gemm_ex_args;
 int fame_gemm_ex(const fame_gemm_ex_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
 
@@ -239,6 +243,9 @@ typedef struct {
     int32_t B;
 } fame_fusion_fwd_args;
 int fame_fusion_fwd(const fame_fusion_fwd_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
+/* Workspace needed when proj / gated / pre_relu are not all requested (small batches run as three launches whose
+ * intermediates must live somewhere); 0 for batches that take the single fused kernel. */
+size_t fame_fusion_fwd_workspace_bytes(int32_t B);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K8 joint loss of train_step (10_FAME.py:420-444), two passes so that data-parallel ranks can SUM-all-reduce the
@@ -375,6 +382,15 @@ int fame_clip_adamw(float* p, const float* g, float* m, float* v, int64_t n, con
  * captured CUDA graph follows the step count and learning-rate schedule; p_bf16 (may be NULL) receives a bf16 copy of
  * the updated parameters for the tensor-core GEMMs. */
 int fame_cast_bf16(const float* x, void* y, int64_t n, fame_stream_t stream);
+/* Transposed bf16 shadows of a table of weight matrices in ONE launch (data-gradient products of the <= 32-row
+ * demographic tower read W^T rows).  table: device array of n_entries records
+ *   { const bf16* src [rows, cols]; bf16* dst [cols, rows]; int32 rows, cols, tile0, tiles_x; }   (32 bytes each)
+ * tile0 = index of the record's first 64x64 tile within the launch, tiles_x = ceil(cols / 64). */
+/* Weight gradient of a layer with at most 32 rows (demographic tower): dW[N,K] (+)= dY[M,N]^T . X[M,K]; bf16 operands,
+ * f32 result; accumulate = 0 overwrites dW.  Bound by the gradient write, CUDA-core FMAs (skinny_gemm.cuh). */
+int fame_wgrad_small(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, float* out, int64_t ld_out, int32_t M,
+                     int32_t N, int32_t K, int32_t accumulate, fame_stream_t stream);
+int fame_transpose_bf16_table(const void* table, int32_t n_entries, int32_t total_tiles, fame_stream_t stream);
 
 #ifdef __cplusplus
 }

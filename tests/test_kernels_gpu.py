@@ -42,6 +42,82 @@ def test_gemm(M, N, K, bias, res, act, f32):
     _close(y, ref, 1e-5 if f32 else 1e-2)        # bf16 output rounding: 2^-8 relative
 
 
+@pytest.mark.parametrize("M,N,K,bias,res,act,f32", [
+    (32, 768, 768, True, "f32", 0, True), (32, 3072, 768, True, None, 1, False), (32, 768, 3072, True, "f32", 0, True),
+    (32, 768, 768, True, None, 0, False), (17, 256, 96, False, "bf16", 2, False), (1, 8, 32, True, None, 0, True),
+    (8, 2304, 768, True, None, 0, False), (32, 3072, 768, False, "mask", 0, False),
+])
+def test_skinny_gemm(M, N, K, bias, res, act, f32):
+    """<= 32 rows: the weight-streaming mma.sync path (skinny_gemm.cuh), same epilogues as the tcgen05 kernel."""
+    from fairmultimodal_b200 import ops
+    from fairmultimodal_b200 import ops_train as T
+    torch.manual_seed(M * 7 + N + K)
+    x = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda") if bias else None
+    out_dtype = torch.float32 if f32 else torch.bfloat16
+    ref = x.float() @ w.float().t()
+    if bias:
+        ref = ref + b
+    ref = torch.nn.functional.gelu(ref) if act == 1 else torch.relu(ref) if act == 2 else ref
+    if res == "mask":
+        aux = torch.randn(M, N, device="cuda").bfloat16()
+        y = torch.empty(M, N, device="cuda", dtype=out_dtype)
+        T.gemm_ex(x, w, y, M, N, K, lda=K, ldb=K, ldy=N, bias=b, aux=aux, aux_mode=T.AUX_RELU_MASK_BF16, ld_aux=N, act=act)
+        ref = ref * (aux.float() > 0)
+    else:
+        r = None if res is None else (torch.randn(M, N, device="cuda") if res == "f32" else torch.randn(M, N, device="cuda").bfloat16())
+        y = ops.gemm_bias_act(x, w, b, r, act, out_dtype=out_dtype)
+        if r is not None:
+            ref = ref + r.float()
+    _close(y, ref, 1e-5 if f32 else 1e-2)
+
+
+def test_skinny_dgrad_through_transposed_shadow():
+    from fairmultimodal_b200 import ops_train as T
+    torch.manual_seed(3)
+    dy = (torch.randn(32, 3072, device="cuda") * 0.1).bfloat16()
+    w = (torch.randn(3072, 768, device="cuda") * 0.05).bfloat16()
+    ref = dy.float() @ w.float()
+    a = T.linear_dgrad(dy, w, out_dtype=torch.float32)                       # tcgen05, MN-major W
+    b = T.linear_dgrad(dy, w, out_dtype=torch.float32, wT=w.t().contiguous())  # skinny, K-major W^T
+    _close(a, ref, 1e-5)
+    _close(b, ref, 1e-5)
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 768, 3072), (32, 3072, 768), (5, 72, 200), (1, 8, 8), (32, 100, 36)])
+def test_wgrad_small(M, N, K):
+    from fairmultimodal_b200 import ops_train as T
+    torch.manual_seed(M + N + K)
+    dy = (torch.randn(M, N, device="cuda") * 0.1).bfloat16()
+    x = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    ref = dy.float().t() @ x.float()
+    out = torch.full((N, K), 7.0, device="cuda")
+    T.linear_wgrad(dy, x, out, accumulate=False)
+    _close(out, ref, 1e-5)
+    T.linear_wgrad(dy, x, out, accumulate=True)
+    _close(out, 2 * ref, 1e-5)
+
+
+def test_transpose_table():
+    import numpy as np
+    from fairmultimodal_b200 import ops_train as T
+    torch.manual_seed(4)
+    mats = [torch.randn(r, c, device="cuda").bfloat16() for r, c in ((768, 768), (3072, 768), (100, 72), (64, 200))]
+    outs = [torch.zeros(m.shape[1], m.shape[0], device="cuda", dtype=torch.bfloat16) for m in mats]
+    rec = np.zeros(len(mats), dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("rows", "<i4"), ("cols", "<i4"),
+                                              ("tile0", "<i4"), ("tiles_x", "<i4")]))
+    tiles = 0
+    for i, (m, o) in enumerate(zip(mats, outs)):
+        tx, ty = (m.shape[1] + 63) // 64, (m.shape[0] + 63) // 64
+        rec[i] = (m.data_ptr(), o.data_ptr(), m.shape[0], m.shape[1], tiles, tx)
+        tiles += tx * ty
+    table = torch.from_numpy(rec.view(np.uint8).copy()).cuda()
+    T.transpose_bf16_table(table, len(mats), tiles)
+    for m, o in zip(mats, outs):
+        assert torch.equal(o, m.t().contiguous())
+
+
 def test_gemm_rejects_bad_shapes():
     from fairmultimodal_b200 import _lib, ops
     x = torch.zeros(16, 12, device="cuda", dtype=torch.bfloat16)

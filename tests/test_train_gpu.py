@@ -40,9 +40,21 @@ def test_gemm_ex_operand_majors():
     ref = dy.float() @ w.float()
     assert (dx.float() - ref).abs().max() <= 1e-2 * ref.abs().max()
     dw = torch.empty(N, K, device="cuda")
-    T.linear_wgrad(dy, x, dw)
+    T.linear_wgrad(dy, x, dw, accumulate=False)
     ref = dy.float().t() @ x.float()
     assert (dw - ref).abs().max() <= 2e-3 * ref.abs().max()
+    # accumulate mode (split-K over the token contraction, float4 atomics): adds to what is already there
+    base = torch.randn(N, K, device="cuda")
+    dw2 = base.clone()
+    T.linear_wgrad(dy, x, dw2)
+    assert (dw2 - base - ref).abs().max() <= 2e-3 * ref.abs().max()
+    big_t = 20000                              # many k-blocks, few output tiles: the case split-K exists for
+    dy2 = (torch.randn(big_t, 264, device="cuda") * 0.1).bfloat16()
+    x2 = (torch.randn(big_t, 136, device="cuda") * 0.5).bfloat16()
+    dw3 = torch.zeros(264, 136, device="cuda")
+    T.linear_wgrad(dy2, x2, dw3)
+    ref3 = dy2.float().t() @ x2.float()
+    assert (dw3 - ref3).abs().max() <= 2e-3 * ref3.abs().max()
     aux = torch.randn(Tn, K, device="cuda").bfloat16()
     dxm = T.linear_dgrad(dy, w, aux=aux, aux_mode=T.AUX_RELU_MASK_BF16)
     ref = (dy.float() @ w.float()) * (aux.float() > 0)
@@ -144,38 +156,45 @@ def test_train_step_matches_reference_golden(golden_dir):
 
 
 def test_cuda_graph_step_equals_eager_steps():
-    """train_step replays a captured CUDA graph from the third batch of a shape on; same trajectory as eager.
+    """train_step replays a captured CUDA graph from the third batch of a shape on.
 
-    Two EAGER runs of the same five steps already differ (float-atomic summation order in the bias / LayerNorm /
-    embedding gradient kernels, amplified by Adam, which turns every gradient into a step of ~lr whatever its size:
-    measured on B200 with scripts/graph_vs_eager.py, eager-vs-eager update difference 9.4 %, graph-vs-eager 9.6 % /
-    3.0 %).  So the graph run is required to sit inside that run-to-run spread, not to be bit-identical."""
+    (a) lr = 0: the weights never move, so the graph run and the eager run see identical inputs at every step and
+        must produce the same losses, the same final gradient buffer and the same Adam moments up to float-atomic
+        summation order (1e-3 relative on the whole buffers): this is the capture / replay correctness check.
+    (b) lr = 1e-4: trajectories diverge chaotically (Adam turns every gradient, however small, into a step of ~lr, so
+        atomic-order noise in near-zero gradients is amplified: two EAGER runs differ by 7-9 % in the update norm,
+        scripts/graph_vs_eager.py); only the losses are compared, loosely."""
     from fairmultimodal_b200 import synth, train
     L, B = 24, 8
     co = synth.make_cohort(B * 5, lab_tokens=L, chunks=0, with_tokens=False, seed=31)
     co["text"] = (np.random.default_rng(2).standard_normal((B * 5, 768)) * 0.5).astype(np.float32)
     batches = [[torch.from_numpy(co[k][i * B:(i + 1) * B]) for k in KEYS9] for i in range(5)]
     pw = torch.tensor([3.0, 1.2, 0.6])
-    out = {}
-    for mode in ("graph", "eager", "eager2"):
-        train.USE_CUDA_GRAPH = mode == "graph"
-        model, _ = _model(L, 12)
-        crit = torch.nn.BCEWithLogitsLoss(pos_weight=pw.cuda())
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
-        p0 = train.get_state(model).p.clone()
-        losses = train.train_step(model, batches, opt, "cuda", crit, lambda_edd=0.8, lambda_l1=0.01)
-        st = train.get_state(model)
-        assert st.step_dev.item() == 5
-        if mode == "graph":
-            assert any(e["graph"] is not None for e in st.graphs.values())
-        out[mode] = (losses, st.p - p0)
-    train.USE_CUDA_GRAPH = True
-    assert out["graph"][0][0] == pytest.approx(out["eager"][0][0], rel=3e-3)
-    assert out["graph"][0][1] == pytest.approx(out["eager"][0][1], rel=3e-3)
-    d_g, d_e, d_e2 = out["graph"][1], out["eager"][1], out["eager2"][1]
-    spread = ((d_e - d_e2).norm() / d_e.norm()).item()
-    diff = min(((d_g - d_e).norm() / d_e.norm()).item(), ((d_g - d_e2).norm() / d_e.norm()).item())
-    assert diff <= 1.5 * spread + 0.02, (diff, spread)
+    try:
+        for lr in (0.0, 1e-4):
+            out = {}
+            for mode in ("graph", "eager"):
+                train.USE_CUDA_GRAPH = mode == "graph"
+                model, _ = _model(L, 12)
+                crit = torch.nn.BCEWithLogitsLoss(pos_weight=pw.cuda())
+                opt = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=0.01)
+                st = train.get_state(model)
+                p0 = st.p.clone()
+                losses = train.train_step(model, batches, opt, "cuda", crit, lambda_edd=0.8, lambda_l1=0.01)
+                assert st.step_dev.item() == 5
+                if mode == "graph":
+                    assert any(e["graph"] is not None for e in st.graphs.values())
+                out[mode] = (losses, st.g.clone(), st.m.clone(), st.v.clone(), (st.p - p0).abs().max().item())
+            g, e = out["graph"], out["eager"]
+            if lr == 0.0:
+                assert g[4] == 0.0 and e[4] == 0.0
+                assert g[0][0] == pytest.approx(e[0][0], rel=1e-5) and g[0][1] == pytest.approx(e[0][1], rel=1e-5)
+                for k in (1, 2, 3):
+                    assert ((g[k] - e[k]).norm() / e[k].norm()).item() < 1e-3
+            else:
+                assert g[0][0] == pytest.approx(e[0][0], rel=1e-2) and g[0][1] == pytest.approx(e[0][1], rel=1e-2)
+    finally:
+        train.USE_CUDA_GRAPH = True
 
 
 def test_all_gradients_match_oracle_autograd():
