@@ -176,13 +176,15 @@ def bench_train(args, world, rank, dev, barrier):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         res[name] = t.item() / args.train_steps
     st = train.get_state(model)
+    n_params = int(st.n)
+    train.release_graphs(model)            # before the process group goes away (captured NCCL kernels)
     return {
         "metric": "FAME train patients/sec (BASELINE configs[3]: full training step, 32 patients/GPU, L=542 lab tokens, "
                   "3 tasks, text embeddings precomputed as in 10_FAME.py:729-731)",
         "value": world * TRAIN_B / (res["resident"] * 1e-3), "unit": "patients/s", "ms_per_step": res["resident"],
         "e2e": {"value": world * TRAIN_B / (res["e2e"] * 1e-3), "unit": "patients/s", "ms_per_step": res["e2e"],
                 "h2d_bytes_per_step": int(sum(x.numel() * x.element_size() for x in host[0])), "d2h_bytes_per_step": 16},
-        "global_batch": world * TRAIN_B, "steps": args.train_steps, "params": int(st.n),
+        "global_batch": world * TRAIN_B, "steps": args.train_steps, "params": n_params,
         "cuda_graph": bool(train.USE_CUDA_GRAPH and (group is None or train._GRAPH_WITH_COLLECTIVES)),
         "dropout": "off (parity configuration)", "dtype": "bf16 GEMMs, fp32 master weights / optimizer",
         "collectives": "none" if world == 1 else "all-reduce(SUM) of 104 int64 loss statistics + flat fp32 gradient buffer",
@@ -324,7 +326,10 @@ def run_ours(args):
                                               "of BioClinicalBERT_FT.forward, one chunk per call as 10_FAME.py:157-169"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        from fairmultimodal_b200 import parallel
+        sys.stdout.flush()
+        barrier()
+        parallel.shutdown()
 
 
 if __name__ == "__main__":

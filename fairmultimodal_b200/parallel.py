@@ -84,3 +84,24 @@ def evaluate_sharded(logits, labels, attrs, thresholds, group=None, verbose=Fals
     local = metrics.evaluate_from_logits(g_logits, g_labels, g_attrs, thresholds, verbose=verbose, counts=vec,
                                          rank_group=group)
     return local
+
+
+def shutdown(timeout_s: float = 30.0, exit_code: int = 0):
+    """Tear the default process group down without risking a hang at exit: destroy_process_group runs in a helper
+    thread; if NCCL does not return within `timeout_s` (seen when CUDA graphs that captured its kernels were still
+    alive) the process exits anyway.  Call after every result has been printed and flushed."""
+    import os
+    import sys
+    import threading
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(timeout_s)
+    if t.is_alive():
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(exit_code)

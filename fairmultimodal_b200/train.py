@@ -94,6 +94,30 @@ class FlatTrainState:
         self._t_entries, self._t_tiles = len(names), tiles
         self._t_table = torch.from_numpy(rec.view(np.uint8).copy()).to(dev) if names else None
 
+    def grad_buckets(self):
+        """Contiguous ranges of the flat gradient buffer in the order the backward pass completes them (the fusion
+        head, the lab tower, then the demographic tower from its last layer down), for the bucketed gradient
+        all-reduce that overlaps the rest of the backward.  Keys: 'head', 'lab', ('demo', i) = ready once layer i of
+        the demographic BERT is done, 'rest' = everything before (embeddings, sig_weights)."""
+        if getattr(self, "_buckets", None) is not None:
+            return self._buckets
+        first = lambda pre: min((o for n, o in self.offsets.items() if n.startswith(pre)), default=None)
+        lab0 = first("behrt_lab.")
+        head0 = min(o for n, o in self.offsets.items()
+                    if n.startswith(("demo_projector.", "lab_projector.", "text_projector.", "fusion_mlp.")))
+        layer = [first(f"behrt_demo.bert.encoder.layer.{i}.") for i in range(12)]
+        cuts = {"head": (head0, self.n), "lab": (lab0, head0)}
+        hi = lab0
+        for i in (9, 6, 3):
+            cuts[("demo", i)] = (layer[i], hi)
+            hi = layer[i]
+        cuts["rest"] = (0, hi)
+        # sanity: the ranges tile [0, n) exactly
+        spans = sorted(cuts.values())
+        assert spans[0][0] == 0 and spans[-1][1] == self.n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        self._buckets = cuts
+        return cuts
+
     def refresh_transposed(self):
         if self._t_table is not None:
             T.transpose_bf16_table(self._t_table, self._t_entries, self._t_tiles)
@@ -143,6 +167,16 @@ class FlatTrainState:
         m._packed = None
         m.behrt_lab._packed = None
         m.behrt_demo.bert._packed = None
+
+
+def release_graphs(model):
+    """Drop the captured step graphs of `model` (they hold the NCCL kernels of the process group that was current
+    at capture time: destroy them before the process group, or destroy_process_group can block)."""
+    st = getattr(model, "_fame_train_state", None)
+    if st is not None:
+        st.graphs.clear()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
 
 
 def get_state(model) -> FlatTrainState:
@@ -203,7 +237,28 @@ def _lin_bwd(st, wname, bname, dy_bf16, x_bf16, colsum_src=None):
     T.linear_wgrad(dy_bf16, x_bf16, st.gr(wname), accumulate=dy_bf16.shape[0] > T.SKINNY_MAX_ROWS)
 
 
-def _demo_backward(st, model, saved, ddemo):
+class _GradReducer:
+    """Bucketed SUM all-reduce of the flat gradient buffer, launched asynchronously as soon as a bucket is complete
+    so that NCCL (NVLink) overlaps the remaining backward kernels; wait() before the gradient norm / AdamW."""
+
+    def __init__(self, st, group):
+        self.st, self.group, self.work = st, group, []
+
+    def ready(self, key):
+        if self.group is None:
+            return
+        import torch.distributed as dist
+        lo, hi = self.st.grad_buckets()[key]
+        if hi > lo:
+            self.work.append(dist.all_reduce(self.st.g[lo:hi], group=self.group, async_op=True))
+
+    def wait(self):
+        for w in self.work:
+            w.wait()
+        self.work = []
+
+
+def _demo_backward(st, model, saved, ddemo, reducer=None):
     pre = "behrt_demo.bert."
     tabs_g = [st.gr(f"behrt_demo.{n}_embedding.weight") for n in ("age", "gender", "ethnicity", "insurance")]
     T.demo_add_bwd(ddemo, saved["demo_ids"], tabs_g)
@@ -231,11 +286,15 @@ def _demo_backward(st, model, saved, ddemo):
         # AdamW still applies weight decay to them, as in the reference)
         dx = T.linear_dgrad(dv, st.w(p + "attention.self.value.weight"), out_dtype=torch.float32, aux=dt1f,
                             aux_mode=T.AUX_ADD_F32, wT=st.wt(p + "attention.self.value.weight"))
+        if reducer is not None and i in (9, 6, 3):
+            reducer.ready(("demo", i))
     e = pre + "embeddings."
     _, dsum = T.layernorm_bwd(saved["esum"], dx, saved["estats"], st.f(e + "LayerNorm.weight"),
                               st.gr(e + "LayerNorm.weight"), st.gr(e + "LayerNorm.bias"), want_bf16=False, want_f32=True)
     T.bert_embed_bwd(dsum, saved["ids"], st.gr(e + "word_embeddings.weight"), st.gr(e + "position_embeddings.weight"),
                      st.gr(e + "token_type_embeddings.weight")[0], 1, pad_idx=0)
+    if reducer is not None:
+        reducer.ready("rest")
 
 
 # ------------------------------------------------------------------------------------------------ lab tower
@@ -395,12 +454,15 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
         import torch.distributed as dist
         # every rank adds lambda_l1 * sign(sig_weights) below; the gradient all-reduce is a SUM -> share it out
         lambda_l1 = lambda_l1 / dist.get_world_size(group)
+    # gradient SUM over ranks, bucket by bucket as the backward completes them (sig_weights, produced here by the
+    # fusion head, lives at offset 0 and travels with the last bucket)
+    red = _GradReducer(st, group)
     ddemo, dlab = _fusion_backward(st, fo, (demo, labe, text), dlogits, w_mod, lambda_l1)
+    red.ready("head")
     _lab_backward(st, model, sv_l, dlab)
-    _demo_backward(st, model, sv_d, ddemo)
-    if group is not None:
-        import torch.distributed as dist
-        dist.all_reduce(st.g, group=group)                                     # gradient SUM over ranks
+    red.ready("lab")
+    _demo_backward(st, model, sv_d, ddemo, red)
+    red.wait()
     return loss, fo
 
 
@@ -467,7 +529,7 @@ def optimisation_step(model, batch, pw, lambda_edd, lambda_l1, w_mod, hp, group=
         static = [torch.empty_like(x) for x in batch]
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             entry["loss"] = eager(static)
         entry["graph"], entry["static"] = g, static
         st.step -= 1                                          # the capture itself executed nothing
@@ -478,7 +540,7 @@ def optimisation_step(model, batch, pw, lambda_edd, lambda_l1, w_mod, hp, group=
     return entry["loss"]
 
 
-_GRAPH_WITH_COLLECTIVES = False
+_GRAPH_WITH_COLLECTIVES = True      # NCCL collectives are captured into the step graph (thread-local capture mode)
 
 
 def fame_forward_train(model, batch8, w_mod, return_modality_logits, return_gated_vector, return_intermediate):

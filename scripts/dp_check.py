@@ -59,6 +59,30 @@ sums_close = int((st_s[:78] - st_f[:78]).abs().max().item())
 ok = dl < 1e-4 and rel < 2e-2 and counts_equal and sums_close == 0
 print(f"[rank {rank}] world={world} |loss_dp - loss_1|={dl:.2e} grad rel diff={rel:.3e} counts_equal={counts_equal} "
       f"fixed-point sum diff={sums_close} -> {'OK' if ok else 'FAIL'}", flush=True)
+# ---- optimisation steps: CUDA graph with captured NCCL collectives (bucketed, overlapped gradient all-reduce) against
+# eager steps, lr = 0 so that both see identical weights at every step
+hp = dict(lr=0.0, weight_decay=0.01, betas=(0.9, 0.999), eps=1e-8)
+res = {}
+for mode in (True, False):
+    m = build()
+    st = train.get_state(m)
+    losses = []
+    for i in range(5):
+        losses.append(train.optimisation_step(m, shard, pw, 0.8, 0.01, w, hp, group=dist.group.WORLD, use_graph=mode).clone())
+    torch.cuda.synchronize()
+    res[mode] = (torch.stack(losses), st.g.clone(), st.m.clone(),
+                 any(e.get("graph") is not None for e in st.graphs.values()))
+    train.release_graphs(m)
+dl2 = (res[True][0] - res[False][0]).abs().max().item()
+dg2 = ((res[True][1] - res[False][1]).norm() / res[False][1].norm()).item()
+dm2 = ((res[True][2] - res[False][2]).norm() / res[False][2].norm()).item()
+dl3 = (res[True][0][-1] - loss_1).abs().max().item()
+ok2 = res[True][3] and dl2 < 1e-5 and dg2 < 1e-3 and dm2 < 1e-3 and dl3 < 1e-4
+print(f"[rank {rank}] graph+NCCL vs eager: captured={res[True][3]} |dloss|={dl2:.2e} grad rel={dg2:.2e} adam-m rel={dm2:.2e} "
+      f"|loss - single process|={dl3:.2e} -> {'OK' if ok2 else 'FAIL'}", flush=True)
+ok = ok and ok2
+sys.stdout.flush()
 dist.barrier()
-dist.destroy_process_group()
+torch.cuda.synchronize()
+parallel.shutdown(exit_code=0 if ok else 1)
 sys.exit(0 if ok else 1)
