@@ -23,6 +23,11 @@
 // P_t (bf16) overwrites the first 64 columns of S_t; the in-order MMA pipe guarantees S_t(j+1) is written only after
 // P_t(j) was consumed.  A commit on s_full[t] for block j also covers P.V of block j-1 (same issuing thread), so the
 // softmax warps may rescale O_t right after that wait.
+//
+// Tried and measured slower (kept out): (1) a third, rotating score buffer with per-(tile, buffer) barriers so that a
+// tile's next score block is in TMEM before its warpgroup finishes the current one (0.50 ms vs 0.41 ms at 256 x 12 x
+// 512 x 64: the extra commits and cursor arithmetic in the single MMA-issuing thread cost more than the wait saved);
+// (2) fetching the key-mask bytes one block ahead (0.45 ms: the extra live registers spill in the softmax loop).
 #pragma once
 #include "sm100_ptx.cuh"
 #include "attn_flash_sm100.cuh"   // FaParams, kFaBoxBytes, ex2_approx (via attn_sm100.cuh)
@@ -46,25 +51,6 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
-__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void f32x2_unpack(unsigned long long v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ unsigned long long f32x2_add(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-
 template <int D>
 __global__ void __launch_bounds__(kApThreads, 1)
 attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParams p, const int num_items,

@@ -12,6 +12,17 @@
 // Epilogue: + bias[n], GELU(erf) / ReLU, + residual (bf16 or f32) or ReLU-mask by another tensor; bf16 output through
 // swizzled smem + TMA store, f32 output (small matrices, weight gradients) through direct vector stores.
 //
+// CTA pairs (cluster of 2, tcgen05 cta_group::2): the two CTAs of a pair own vertically adjacent 128-row output
+// tiles of the same n block and execute ONE 256x256x16 MMA per step, issued by the pair leader.  Each CTA stages its
+// own A tile (128 x 64) and only HALF of the B tile (128 of the 256 n rows); the tensor cores read the other half from
+// the peer's shared memory.  Per k-block a CTA therefore moves 32 KB through TMA and its MMAs read 32 KB of shared
+// memory instead of 48 + 48 KB: with single-CTA 128x256 MMAs the kernel sat at 1150-1380 TFLOP/s on every shape
+// (tensor pipe 65-80 % active) because operand staging (TMA writes + UMMA reads) saturated the 128 B/clk
+// shared-memory port; halving the L2 traffic alone (TMA multicast of B, tried first) changed nothing.
+// Barriers: both producers credit the LEADER's full barrier (cta_group::2 TMA); the leader's tcgen05.commit
+// multicasts to the empty / tmem_full barriers of both CTAs; the epilogue warps of both CTAs arrive on the leader's
+// tmem_empty barrier.
+//
 // Structure (one persistent CTA per SM, 384 threads):
 //   warp 0   : TMA producer   (one lane)  global -> smem ring, kStages x {A 128x64, B 256x64} bf16, SW128
 //   warp 1   : MMA issuer     (one lane)  tcgen05.mma 128x256x16, 4 per k-block, commit -> frees ring slot
@@ -26,9 +37,9 @@ namespace fame {
 constexpr int kGemmBM = 128;
 constexpr int kGemmBN = 256;
 constexpr int kGemmBK = 64;
-constexpr int kGemmStages = 4;
-constexpr int kGemmABytes = kGemmBM * kGemmBK * 2;  // 16 KB
-constexpr int kGemmBBytes = kGemmBN * kGemmBK * 2;  // 32 KB
+constexpr int kGemmStages = 6;
+constexpr int kGemmABytes = kGemmBM * kGemmBK * 2;        // 16 KB: this CTA's 128 rows of A
+constexpr int kGemmBBytes = (kGemmBN / 2) * kGemmBK * 2;  // 16 KB: this CTA's half (128 n rows) of the pair's B tile
 constexpr int kGemmStageBytes = kGemmABytes + kGemmBBytes;
 constexpr int kGemmCBoxBytes = 128 * 64 * 2;        // 16 KB staging box per epilogue warpgroup
 constexpr int kGemmSubTile = 64 * 64 * 2;           // 8 KB: one {64 mn x 64 k} box of an MN-major operand
@@ -78,8 +89,31 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaf(h, xc * q, h);
 }
 
+// Two elements at a time on the packed FP32 pipe (FFMA2 / FMUL2): 12 packed instructions per pair instead of 13
+// scalar ones per element.  The 3072-wide FFN1 epilogue is otherwise slower than its K = 768 main loop.
+__device__ __forceinline__ void gelu_erf_x2(float& a, float& b) {
+    constexpr float c0 = 7.978010774e-01f, c1 = -1.326614171e-01f, c2 = 1.961016096e-02f, c3 = -2.209631959e-03f,
+                    c4 = 1.854783768e-04f, c5 = -1.111321126e-05f, c6 = 4.429220439e-07f, c7 = -1.040250019e-08f,
+                    c8 = 1.080706497e-10f;
+    const float xa = fminf(fmaxf(a, -4.242640687f), 4.242640687f);
+    const float xb = fminf(fmaxf(b, -4.242640687f), 4.242640687f);
+    const unsigned long long x = f32x2_pack(xa, xb);
+    const unsigned long long u = f32x2_mul(x, x);
+    unsigned long long q = f32x2_fma(f32x2_pack(c8, c8), u, f32x2_pack(c7, c7));
+    q = f32x2_fma(q, u, f32x2_pack(c6, c6));
+    q = f32x2_fma(q, u, f32x2_pack(c5, c5));
+    q = f32x2_fma(q, u, f32x2_pack(c4, c4));
+    q = f32x2_fma(q, u, f32x2_pack(c3, c3));
+    q = f32x2_fma(q, u, f32x2_pack(c2, c2));
+    q = f32x2_fma(q, u, f32x2_pack(c1, c1));
+    q = f32x2_fma(q, u, f32x2_pack(c0, c0));
+    const unsigned long long h = f32x2_mul(f32x2_pack(a, b), f32x2_pack(0.5f, 0.5f));
+    const unsigned long long r = f32x2_fma(h, f32x2_mul(x, q), h);
+    f32x2_unpack(r, a, b);
+}
+
 template <bool kAMn, bool kBMn>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -98,9 +132,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    const uint32_t rank = cluster_ctarank();          // 0 / 1 inside the CTA pair
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int m_tiles = (p.M + kGemmBM - 1) / kGemmBM;
+    const int m_pairs = (m_tiles + 1) >> 1;           // a pair takes m blocks 2 mp and 2 mp + 1 (the second may be empty)
     const int n_tiles = (p.N + kGemmBN - 1) / kGemmBN;
-    const int tiles_per_batch = m_tiles * n_tiles;
+    const int tiles_per_batch = m_pairs * n_tiles;
     // task = (output tile, k slice); the slice index is innermost so that the slices of one tile run concurrently
     const int num_tiles = tiles_per_batch * p.nb0 * p.nb1 * p.split_k;
     const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
@@ -112,21 +149,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kGemmStages; ++i) {
-            mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&full_bar[i], 1);    // used in the leader only: its own arrive.expect_tx for both CTAs' bytes
+            mbar_init(&empty_bar[i], 1);   // one multicast tcgen05.commit of the leader per use
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 8);  // one arrival per epilogue warp
+            mbar_init(&tmem_empty[i], 16); // leader only: one arrival per epilogue warp of BOTH CTAs
         }
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
+        tmem_alloc_pair(tmem_slot, 512);   // executed by the same warp of both CTAs of the pair
+        tmem_relinquish_pair();
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();    // the peer's barriers are initialised before anything is multicast into its shared memory
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -135,46 +173,50 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             // ------------------------------------------------ TMA producer
             int stage = 0;
             uint32_t phase = 0;
-            for (int task = blockIdx.x; task < num_tiles; task += gridDim.x) {
+            for (int task = pair; task < num_tiles; task += npairs) {
                 const int tile = task / p.split_k, ks = task % p.split_k;
                 const int bidx = tile / tiles_per_batch, t2 = tile % tiles_per_batch;
                 const int b0 = bidx / p.nb1, b1 = bidx % p.nb1;
-                const int m_blk = t2 / n_tiles, n_blk = t2 % n_tiles;
+                const int m_blk = 2 * (t2 / n_tiles) + (int)rank, n_blk = t2 % n_tiles;
                 const int kb_lo = ks * p.kb_per_split, kb_hi = min(num_kb, kb_lo + p.kb_per_split);
                 for (int kb = kb_lo; kb < kb_hi; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], kGemmStageBytes);
+                    // both CTAs' loads complete on the leader's barrier, which expects the bytes of the whole pair
+                    const uint32_t fb = map_to_cta(smem_u32(&full_bar[stage]), 0);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kGemmStageBytes);
                     uint8_t* sa = smem_a + stage * kGemmABytes;
                     uint8_t* sb = smem_b + stage * kGemmBBytes;
                     if (kAMn) {
 #pragma unroll
                         for (int s = 0; s < kGemmBM / 64; ++s)
-                            tma_load_4d(sa + s * kGemmSubTile, &tmap_a, &full_bar[stage], m_blk * kGemmBM + 64 * s,
-                                        kb * kGemmBK, b1, b0, kEvictNormal);
+                            tma_load_4d_pair(sa + s * kGemmSubTile, &tmap_a, fb, m_blk * kGemmBM + 64 * s, kb * kGemmBK,
+                                             b1, b0, kEvictNormal);
                     } else {
-                        tma_load_4d(sa, &tmap_a, &full_bar[stage], kb * kGemmBK, m_blk * kGemmBM, b1, b0, kEvictNormal);
+                        tma_load_4d_pair(sa, &tmap_a, fb, kb * kGemmBK, m_blk * kGemmBM, b1, b0, kEvictNormal);
                     }
+                    // this CTA's half of the B tile: n rows [n_blk * 256 + rank * 128, + 128)
+                    const int n_row0 = n_blk * kGemmBN + (int)rank * (kGemmBN / 2);
                     if (kBMn) {
 #pragma unroll
-                        for (int s = 0; s < kGemmBN / 64; ++s)
-                            tma_load_4d(sb + s * kGemmSubTile, &tmap_b, &full_bar[stage], n_blk * kGemmBN + 64 * s,
-                                        kb * kGemmBK, b1, b0, kEvictLast);
+                        for (int s = 0; s < kGemmBN / 128; ++s)
+                            tma_load_4d_pair(sb + s * kGemmSubTile, &tmap_b, fb, n_row0 + 64 * s, kb * kGemmBK, b1, b0,
+                                             kEvictLast);
                     } else {
-                        tma_load_4d(sb, &tmap_b, &full_bar[stage], kb * kGemmBK, n_blk * kGemmBN, b1, b0, kEvictLast);
+                        tma_load_4d_pair(sb, &tmap_b, fb, kb * kGemmBK, n_row0, b1, b0, kEvictLast);
                     }
                     if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------ MMA issuer
-            constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, kGemmBN, kAMn ? 1 : 0, kBMn ? 1 : 0);
+        if (lane == 0 && rank == 0) {
+            // ------------------------------------------------ MMA issuer (pair leader only): 256 x 256 x 16 per step
+            constexpr uint32_t idesc = make_idesc_bf16(2 * kGemmBM, kGemmBN, kAMn ? 1 : 0, kBMn ? 1 : 0);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int task = blockIdx.x; task < num_tiles; task += gridDim.x) {
+            for (int task = pair; task < num_tiles; task += npairs) {
                 const int kb_lo = (task % p.split_k) * p.kb_per_split, kb_hi = min(num_kb, kb_lo + p.kb_per_split);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -192,12 +234,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                                     : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
                         const uint64_t bdesc = kBMn ? make_smem_desc_sw128(b_addr + k * 2048, kGemmSubTile, 1024)
                                                     : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                        umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb != kb_lo) || (k != 0));
+                        umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, (kb != kb_lo) || (k != 0));
                     }
-                    umma_commit(&empty_bar[stage]);
+                    umma_commit_pair(&empty_bar[stage], 3);   // frees the slot in both CTAs' producers
                     if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);
+                umma_commit_pair(&tmem_full[acc], 3);     // accumulators of both CTAs are complete
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -212,12 +254,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int sw = r_local & 7;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int task = blockIdx.x; task < num_tiles; task += gridDim.x) {
+        for (int task = pair; task < num_tiles; task += npairs) {
             const int tile = task / p.split_k;
             const bool first_slice = (task % p.split_k) == 0;   // bias / residual are added by one slice only
             const int bidx = tile / tiles_per_batch, t2 = tile % tiles_per_batch;
             const int b0 = bidx / p.nb1, b1 = bidx % p.nb1;
-            const int m_blk = t2 / n_tiles, n_blk = t2 % n_tiles;
+            const int m_blk = 2 * (t2 / n_tiles) + (int)rank, n_blk = t2 % n_tiles;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const int row = m_blk * kGemmBM + r_local;
@@ -243,7 +285,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     // accumulator fully read: hand the TMEM buffer back to the MMA warp before the math
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
                 }
                 if (!active) continue;
                 if (p.bias != nullptr && first_slice) {
@@ -257,7 +299,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
                 if (p.act == kActGelu) {
 #pragma unroll
-                    for (int j = 0; j < 64; ++j) v[j] = gelu_erf(v[j]);
+                    for (int j = 0; j < 64; j += 2) gelu_erf_x2(v[j], v[j + 1]);
                 } else if (p.act == kActRelu) {
 #pragma unroll
                     for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -342,9 +384,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();    // neither CTA leaves while the other may still signal barriers in its shared memory
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc_pair(tmem_base, 512);
     }
 }
 

@@ -108,7 +108,7 @@ class FlatTrainState:
         layer = [first(f"behrt_demo.bert.encoder.layer.{i}.") for i in range(12)]
         cuts = {"head": (head0, self.n), "lab": (lab0, head0)}
         hi = lab0
-        for i in (9, 6, 3):
+        for i in DEMO_BUCKET_LAYERS:
             cuts[("demo", i)] = (layer[i], hi)
             hi = layer[i]
         cuts["rest"] = (0, hi)
@@ -237,6 +237,11 @@ def _lin_bwd(st, wname, bname, dy_bf16, x_bf16, colsum_src=None):
     T.linear_wgrad(dy_bf16, x_bf16, st.gr(wname), accumulate=dy_bf16.shape[0] > T.SKINNY_MAX_ROWS)
 
 
+# a gradient bucket closes after each of these demographic-BERT layers (backward runs 11 -> 0); the remainder (layer 0,
+# embeddings, sig_weights: ~30 MB) is the only all-reduce that cannot overlap with backward compute
+DEMO_BUCKET_LAYERS = (10, 8, 6, 4, 2, 1)
+
+
 class _GradReducer:
     """Bucketed SUM all-reduce of the flat gradient buffer, launched asynchronously as soon as a bucket is complete
     so that NCCL (NVLink) overlaps the remaining backward kernels; wait() before the gradient norm / AdamW."""
@@ -286,7 +291,7 @@ def _demo_backward(st, model, saved, ddemo, reducer=None):
         # AdamW still applies weight decay to them, as in the reference)
         dx = T.linear_dgrad(dv, st.w(p + "attention.self.value.weight"), out_dtype=torch.float32, aux=dt1f,
                             aux_mode=T.AUX_ADD_F32, wT=st.wt(p + "attention.self.value.weight"))
-        if reducer is not None and i in (9, 6, 3):
+        if reducer is not None and i in DEMO_BUCKET_LAYERS:
             reducer.ready(("demo", i))
     e = pre + "embeddings."
     _, dsum = T.layernorm_bwd(saved["esum"], dx, saved["estats"], st.f(e + "LayerNorm.weight"),
