@@ -518,7 +518,7 @@ int fame_eval_counts(const fame_eval_counts_args* a, void*, size_t, fame_stream_
     p.N = a->N;
     p.logits_are_probs = a->logits_are_probs;
     int grid = (a->N + 1023) / 1024;     // 256 threads x 4 patients per trip
-    if (grid > 4 * d->sm_count) grid = 4 * d->sm_count;
+    if (grid > 6 * d->sm_count) grid = 6 * d->sm_count;   // 70 registers: 3 resident CTAs per SM, 2 waves
     fame::eval_counts_kernel<<<grid, 256, 0, stream>>>(p);
     return launch_status();
 }

@@ -39,112 +39,103 @@ struct EvalCountsParams {
     int logits_are_probs;       // 1: `logits` already holds float32 probabilities / 0-1 predictions
 };
 
-// Per-thread counters are packed four 8-bit cells (TP, FN, FP, TN) per register and flushed every 252 patients;
-// each thread takes 4 consecutive patients per trip through 16-byte loads (load_patient_quad, rowwise.cuh).
+// One shared-memory histogram per sensitive attribute, keyed by (subgroup code, confusion cell of outcome 0, of
+// outcome 1, of outcome 2) = 8 x 4 x 4 x 4 = 512 bins: a patient costs THREE shared-memory increments instead of 72
+// predicated register adds (3 outcomes x 3 attributes x 8 code slots), and the kernel needs ~40 registers instead of
+// 163, so 6+ CTAs per SM hide the load latency.  The 288 + 12 confusion counts are folded out of the 3 x 512 bins once
+// per block.  Each thread takes 4 consecutive patients per trip through 16-byte loads (load_patient_quad, rowwise.cuh).
+constexpr int kEvBins = kEvSlots * 64;
+
 __global__ void __launch_bounds__(256)
 eval_counts_kernel(const EvalCountsParams p) {
-    __shared__ unsigned int sh[kEvLen];
-    for (int i = threadIdx.x; i < kEvLen; i += blockDim.x) sh[i] = 0u;
+    __shared__ unsigned int hist[3][kEvBins];
+    __shared__ unsigned int sw_hist[kEvHistLen];
     __shared__ double sweep_s[101];
+    __shared__ unsigned int s_misc[2];   // patients, bad-code flag
+    for (int i = threadIdx.x; i < 3 * kEvBins; i += blockDim.x) (&hist[0][0])[i] = 0u;
+    for (int i = threadIdx.x; i < kEvHistLen; i += blockDim.x) sw_hist[i] = 0u;
+    if (threadIdx.x < 2) s_misc[threadIdx.x] = 0u;
     if (p.sweep != nullptr)
         for (int i = threadIdx.x; i < 101; i += blockDim.x) sweep_s[i] = p.sweep[i];
     __syncthreads();
 
-    unsigned int cnt[3][3][kEvSlots];
-    unsigned int tot[3];
     const int lane = threadIdx.x & 31;
-    auto reset = [&]() {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            tot[i] = 0u;
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int s = 0; s < kEvSlots; ++s) cnt[i][a][s] = 0u;
-        }
-    };
-    auto flush = [&]() {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const unsigned v = __reduce_add_sync(0xffffffffu, (tot[i] >> (8 * c)) & 0xffu);
-                if (lane == 0 && v) atomicAdd(&sh[kEvConfLen + i * 4 + c], v);
-            }
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int s = 0; s < kEvSlots; ++s)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const unsigned v = __reduce_add_sync(0xffffffffu, (cnt[i][a][s] >> (8 * c)) & 0xffu);
-                        if (lane == 0 && v) atomicAdd(&sh[((i * 3 + a) * kEvSlots + s) * 4 + c], v);
-                    }
-        }
-        reset();
-    };
-    reset();
-    int since = 0, n_local = 0, bad = 0;
+    unsigned n_local = 0, bad = 0;
     const bool vec_ok = p.ld == 3 && ((reinterpret_cast<uintptr_t>(p.logits) | reinterpret_cast<uintptr_t>(p.labels) |
                                        reinterpret_cast<uintptr_t>(p.attr[0]) | reinterpret_cast<uintptr_t>(p.attr[1]) |
                                        reinterpret_cast<uintptr_t>(p.attr[2])) & 15) == 0;
     const long long per_block = (long long)blockDim.x * kPatPerThread;
-    // block-uniform trip count: the flush is warp-collective, all lanes reach it together
     for (long long base = blockIdx.x * per_block; base < p.N; base += gridDim.x * per_block) {
         PatientQuad q;
         load_patient_quad(q, p.logits, p.ld, p.labels, p.attr, base + (long long)threadIdx.x * kPatPerThread, p.N, vec_ok);
 #pragma unroll
         for (int u = 0; u < kPatPerThread; ++u) {
             if (u < q.n) {
-                int code[3];
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const long long c = q.code[a][u];
-                    bad |= (c < 0 || c >= kEvSlots);
-                    code[a] = (int)c;
-                }
+                unsigned cells = 0;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const float z = q.z[u][i];
                     const float pr = p.logits_are_probs ? z : sigmoid_f32_exact(z);
                     const int y = q.y[u][i] != 0.f;
                     const int pred = (double)pr > p.thr[i];
-                    const unsigned inc = 1u << (8 * ((1 - y) * 2 + (1 - pred)));  // cell: TP=0, FN=1, FP=2, TN=3
-                    tot[i] += inc;
-#pragma unroll
-                    for (int a = 0; a < 3; ++a)
-#pragma unroll
-                        for (int s = 0; s < kEvSlots; ++s) cnt[i][a][s] += (code[a] == s) ? inc : 0u;
+                    cells |= (unsigned)((1 - y) * 2 + (1 - pred)) << (2 * i);   // cell: TP=0, FN=1, FP=2, TN=3
                     if (p.sweep != nullptr) {
-                        // kk = number of sweep thresholds strictly below p (p > t_k <=> k < kk); thresholds ascend
-                        int lo = 0, hi = 101;
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if ((double)pr > sweep_s[mid]) lo = mid + 1; else hi = mid;
-                        }
-                        atomicAdd(&sh[kEvConfLen + kEvTotLen + (i * 2 + y) * 102 + lo], 1u);
+                        // kk = number of sweep thresholds strictly below p (p > t_k <=> k < kk); thresholds ascend.
+                        // Start from the bin a uniform grid would give and walk (at most a step or two).
+                        int kk = min(101, max(0, (int)(pr * 100.0f)));
+                        while (kk < 101 && (double)pr > sweep_s[kk]) ++kk;
+                        while (kk > 0 && !((double)pr > sweep_s[kk - 1])) --kk;
+                        atomicAdd(&sw_hist[(i * 2 + y) * 102 + kk], 1u);
                     }
+                }
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const long long c = q.code[a][u];
+                    bad |= (c < 0 || c >= kEvSlots);
+                    atomicAdd(&hist[a][(((int)c & (kEvSlots - 1)) << 6) | cells], 1u);
                 }
                 ++n_local;
             }
         }
-        if (++since == 63) {          // 63 trips x 4 patients = 252 <= 255: the 8-bit cells cannot overflow
-            flush();
-            since = 0;
-        }
     }
-    flush();
     {
-        const unsigned v = __reduce_add_sync(0xffffffffu, (unsigned)n_local);
-        const unsigned e = __reduce_or_sync(0xffffffffu, (unsigned)bad);
+        const unsigned v = __reduce_add_sync(0xffffffffu, n_local);
+        const unsigned e = __reduce_or_sync(0xffffffffu, bad);
         if (lane == 0) {
-            atomicAdd(&sh[kEvLen - 2], v);
-            if (e) atomicOr(&sh[kEvLen - 1], 1u);
+            atomicAdd(&s_misc[0], v);
+            if (e) atomicOr(&s_misc[1], 1u);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kEvLen; i += blockDim.x)
-        if (sh[i]) atomicAdd(p.out + i, (unsigned long long)sh[i]);
+    // fold the bins: conf[i][a][code][cell] = sum over the cells of the other two outcomes; tot[i][cell] from attr 0
+    for (int idx = threadIdx.x; idx < kEvConfLen + kEvTotLen; idx += blockDim.x) {
+        unsigned long long sum = 0ull;
+        if (idx < kEvConfLen) {
+            const int cell = idx & 3, code = (idx >> 2) & 7, ia = idx >> 5, a = ia % 3, i = ia / 3;
+            for (int o = 0; o < 16; ++o) {
+                // spread the 4 bits of o over the two outcome positions other than i
+                const int lo = o & 3, hi = o >> 2;
+                const int c0 = i == 0 ? cell : lo, c1 = i == 1 ? cell : (i == 0 ? lo : hi), c2 = i == 2 ? cell : hi;
+                sum += hist[a][(code << 6) | c0 | (c1 << 2) | (c2 << 4)];
+            }
+        } else {
+            const int t = idx - kEvConfLen, cell = t & 3, i = t >> 2;
+            for (int code = 0; code < kEvSlots; ++code)
+                for (int o = 0; o < 16; ++o) {
+                    const int lo = o & 3, hi = o >> 2;
+                    const int c0 = i == 0 ? cell : lo, c1 = i == 1 ? cell : (i == 0 ? lo : hi), c2 = i == 2 ? cell : hi;
+                    sum += hist[0][(code << 6) | c0 | (c1 << 2) | (c2 << 4)];
+                }
+        }
+        if (sum) atomicAdd(p.out + idx, sum);
+    }
+    if (p.sweep != nullptr)
+        for (int i = threadIdx.x; i < kEvHistLen; i += blockDim.x)
+            if (sw_hist[i]) atomicAdd(p.out + kEvConfLen + kEvTotLen + i, (unsigned long long)sw_hist[i]);
+    if (threadIdx.x == 0) {
+        if (s_misc[0]) atomicAdd(p.out + kEvLen - 2, (unsigned long long)s_misc[0]);
+        if (s_misc[1]) atomicOr(p.out + kEvLen - 1, 1ull);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ rank counts
