@@ -59,7 +59,7 @@ class AttnFwdArgs(C.Structure):
         ("key_mask", C.c_void_p),
         ("ctx", C.c_void_p), ("ld_ctx", C.c_int64),
         ("batch", C.c_int32), ("seq", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
-        ("scale", C.c_float), ("algo", C.c_int32),
+        ("scale", C.c_float), ("algo", C.c_int32), ("lse", C.c_void_p),
     ]
 
 
@@ -179,6 +179,8 @@ FLAT_OPS = {
     "fame_cast_bf16": [_P, _P, _I64],
     "fame_transpose_bf16_table": [_P, _I32, _I32],
     "fame_wgrad_small": [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32],
+    "fame_attn_delta": [_P, _P, _I64, _P, _I32, _I32, _I32, _I32],
+    "fame_attn_bwd_pds": [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _F],
 }
 
 # name -> args struct for every `int fame_<op>(const args*, void* ws, size_t ws_bytes, stream)` entry point

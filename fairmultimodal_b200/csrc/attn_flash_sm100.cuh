@@ -37,6 +37,7 @@ struct FaParams {
     int batch, seq, heads;
     int q_col0, k_col0, v_col0;  // first column of Q / K / V of head 0 inside the packed tensor
     float scale_log2e;
+    float* lse;               // optional [batch, heads, seq]: row log-sum-exp in log2 units of the scaled scores
 };
 
 template <int D>

@@ -327,6 +327,9 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
             tc_fence_after();
             const float inv = l > 0.f ? 1.0f / l : 0.f;
             const int qrow = qp * 256 + t * 128 + r;
+            // saved for the backward pass: P = 2^(s * scale_log2e - lse); +inf for an all-masked row (P = 0)
+            if (p.lse != nullptr && qrow < S)
+                p.lse[((long long)b * p.heads + h) * S + qrow] = l > 0.f ? m + log2f(l) : INFINITY;
             __nv_bfloat16* dst = p.ctx + (long long)(b * S + qrow) * p.ld_ctx + h * D;
 #pragma unroll
             for (int c = 0; c < D / 32; ++c) {

@@ -9,6 +9,7 @@
 #include "attn_sm100.cuh"
 #include "attn_flash_sm100.cuh"
 #include "attn_pair_sm100.cuh"
+#include "attn_bwd_sm100.cuh"
 #include "backward.cuh"
 #include "gemm_sm100.cuh"
 #include "heads.cuh"
@@ -122,6 +123,7 @@ static int launch_flash(const fame_attn_fwd_args* a, const CUtensorMap& tq, fame
     p.k_col0 = a->heads * D;
     p.v_col0 = 2 * a->heads * D;
     p.scale_log2e = a->scale * 1.4426950408889634f;
+    p.lse = nullptr;
     dim3 grid((a->seq + 127) / 128, a->heads, a->batch);
     fame::attn_fwd_flash_kernel<D><<<grid, fame::kFaThreads, fame::FaCfg<D>::kSmemBytes, stream>>>(tq, p);
     return launch_status();
@@ -149,12 +151,35 @@ static int launch_pair(const fame_attn_fwd_args* a, const CUtensorMap& tq, int s
     p.k_col0 = a->heads * D;
     p.v_col0 = 2 * a->heads * D;
     p.scale_log2e = a->scale * 1.4426950408889634f;
+    p.lse = a->lse;
     const int qpairs = (a->seq + 255) / 256;
     const long long items = (long long)a->batch * a->heads * qpairs;
     if (items > 0x7fffffffll) return FAME_ERR_SHAPE;
     const int grid = items < sm_count ? (int)items : sm_count;
     fame::attn_fwd_pair_kernel<D><<<grid, fame::kApThreads, fame::ApCfg<D>::kSmemBytes, stream>>>(tq, p, (int)items,
                                                                                                  qpairs);
+    return launch_status();
+}
+
+
+template <int D>
+static int launch_attn_bwd_pds(const CUtensorMap& tq, const CUtensorMap& tdo, const fame::AbParams& p, int sm_count,
+                               fame_stream_t stream) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(fame::attn_bwd_pds_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             fame::AbCfg<D>::kSmemBytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+        attr_set[dev] = true;
+    }
+    const int qtiles = (p.seq + 127) / 128;
+    const long long items = (long long)p.batch * p.heads * qtiles;
+    if (items > 0x7fffffffll) return FAME_ERR_SHAPE;
+    const int grid = items < sm_count ? (int)items : sm_count;
+    fame::attn_bwd_pds_kernel<D><<<grid, fame::kAbThreads, fame::AbCfg<D>::kSmemBytes, stream>>>(tq, tdo, p, (int)items,
+                                                                                                qtiles);
     return launch_status();
 }
 
@@ -278,6 +303,7 @@ int fame_attn_fwd(const fame_attn_fwd_args* a, void*, size_t, fame_stream_t stre
     if ((a->head_dim != 64 && a->head_dim != 96) || a->seq <= 0 || a->heads <= 0 || a->batch < 0)
         return FAME_ERR_SHAPE;
     if (a->algo < 0 || a->algo > 3) return FAME_ERR_SHAPE;
+    if (a->lse != nullptr && a->algo != 0 && a->algo != 3) return FAME_ERR_SHAPE;   // only the persistent kernel saves it
     const bool fullrow_ok = a->head_dim == fame::kAttnD && a->seq <= fame::kAttnMaxS;
     if (a->algo == 1 && !fullrow_ok) return FAME_ERR_SHAPE;
     const int64_t width = 3ll * a->heads * a->head_dim;
@@ -369,15 +395,26 @@ int fame_seq_mean(const fame_seq_mean_args* a, void*, size_t, fame_stream_t stre
     int rc = device_info(&d);
     if (rc != FAME_OK) return rc;
     if (a->batch == 0) return FAME_OK;
-    // enough blocks to cover the SMs twice; splitting L needs a zeroed output and float atomics
+    if (a->cols > 1024) return FAME_ERR_SHAPE;
+    // enough blocks to cover the SMs; the row splits of one sequence form a thread-block cluster (<= 8, portable) and
+    // are combined in rank order through distributed shared memory (deterministic, no atomics, no memset)
     int splits = 1;
-    while (a->batch * splits < 2 * d->sm_count && splits * 8 <= a->L) splits *= 2;
-    if (splits > 1) {
-        cudaError_t e = cudaMemsetAsync(a->out, 0, sizeof(float) * (size_t)a->batch * a->cols, stream);
-        if (e != cudaSuccess) return cuda_fail(e);
-    }
-    fame::seq_mean_kernel<<<dim3(a->batch, splits), 128, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(a->x), a->out, a->L, a->cols, splits);
+    while (a->batch * splits < d->sm_count && splits < 8 && splits * 8 <= a->L) splits *= 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(a->batch, splits);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 1;
+    attr.val.clusterDim.y = splits;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fame::seq_mean_kernel, reinterpret_cast<const __nv_bfloat16*>(a->x), a->out,
+                                       (int)a->L, (int)a->cols, splits);
+    if (e != cudaSuccess) return cuda_fail(e);
     return launch_status();
 }
 

@@ -328,17 +328,28 @@ lab_embed_kernel(const float* __restrict__ lab, const float* __restrict__ w_tok,
 
 // ---------------------------------------------------------------------------------------- K6 sequence mean
 // out[b, :] = mean_l x[b*L + l, :]  (BEHRTModel_Lab.forward, 10_FAME.py:224).  bf16 in, f32 out.
-// grid = (batch, splits): block (b, s) sums rows l = s, s + splits, ...; splits > 1 accumulates with atomicAdd
-// into a zero-initialised output (used only when batch alone cannot fill the GPU).
+// grid = (batch, splits), launched as thread-block clusters (1, splits, 1): block (b, s) sums rows l = s, s + splits,
+// ...; the partial rows meet in the distributed shared memory of the cluster and rank 0 adds them IN RANK ORDER, so
+// the result does not depend on block timing.  (Float atomics here made the whole training step irreproducible: the
+// 1e-7 jitter of this mean reaches the loss gradient and the demographic tower -- a 12-layer post-LN BERT fed a
+// constant token -- amplifies it to 1e-3 in its weight gradients.)  cols <= 1024, cols % 8 == 0.
+__device__ __forceinline__ float ld_shared_cluster_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 __global__ void __launch_bounds__(128)
 seq_mean_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int L, int cols, int splits) {
+    __shared__ float part[1024];
     const int b = blockIdx.x, sp = blockIdx.y;
     const __nv_bfloat16* xb = x + (long long)b * L * cols;
     const float inv = 1.0f / (float)L;
-    for (int c0 = threadIdx.x * 8; c0 < cols; c0 += blockDim.x * 8) {
-        float acc[8];
+    const int c0 = threadIdx.x * 8;           // 128 threads x 8 columns cover cols <= 1024
+    float acc[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (c0 < cols) {
         int l = sp;
         for (; l + 3 * splits < L; l += 4 * splits) {
             float f[4][8];
@@ -356,15 +367,37 @@ seq_mean_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, in
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] += f[j];
         }
-        float* o = out + (long long)b * cols + c0;
-        if (splits == 1) {
+    }
+    if (splits == 1) {
+        if (c0 < cols) {
+            float* o = out + (long long)b * cols + c0;
             *reinterpret_cast<float4*>(o) = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
             *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(o + j, acc[j] * inv);
         }
+        return;
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[c0 + j] = acc[j];
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (sp == 0 && c0 < cols) {
+        float tot[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tot[j] = acc[j];
+        for (int r = 1; r < splits; ++r) {
+            uint32_t remote;
+            const uint32_t local = static_cast<uint32_t>(__cvta_generic_to_shared(&part[c0]));
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tot[j] += ld_shared_cluster_f32(remote + 4 * j);
+        }
+        float* o = out + (long long)b * cols + c0;
+        *reinterpret_cast<float4*>(o) = make_float4(tot[0] * inv, tot[1] * inv, tot[2] * inv, tot[3] * inv);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(tot[4] * inv, tot[5] * inv, tot[6] * inv, tot[7] * inv);
+    }
+    // nobody leaves while rank 0 may still read its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------- K4c demographic add

@@ -146,8 +146,9 @@ def bert_embed(ids, word, pos, type_emb, gamma, beta, eps, seq_len, err_flag=Non
     return out
 
 
-def attn_fwd(qkv, batch, seq, heads, head_dim, key_mask=None, scale=None, out=None, algo=0):
-    """qkv bf16 [batch*seq, 3*heads*head_dim] -> ctx bf16 [batch*seq, heads*head_dim]."""
+def attn_fwd(qkv, batch, seq, heads, head_dim, key_mask=None, scale=None, out=None, algo=0, lse=None):
+    """qkv bf16 [batch*seq, 3*heads*head_dim] -> ctx bf16 [batch*seq, heads*head_dim].  lse (optional f32
+    [batch, heads, seq]) receives the row log-sum-exp the backward pass needs."""
     _cuda(qkv, "qkv", torch.bfloat16)
     if out is None:
         out = torch.empty((batch * seq, heads * head_dim), device=qkv.device, dtype=torch.bfloat16)
@@ -164,6 +165,7 @@ def attn_fwd(qkv, batch, seq, heads, head_dim, key_mask=None, scale=None, out=No
     a.batch, a.seq, a.heads, a.head_dim = batch, seq, heads, head_dim
     a.scale = float(scale) if scale is not None else head_dim ** -0.5
     a.algo = algo
+    a.lse = _cuda(lse, "lse", torch.float32).data_ptr() if lse is not None else None
     _call("fame_attn_fwd", a, 4.0 * batch * heads * seq * seq * head_dim)
     return out
 

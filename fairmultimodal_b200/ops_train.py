@@ -126,6 +126,23 @@ def attn_bwd_softmax(s, dp, rows, seq, ld, scale):
     return p, ds
 
 
+def attn_delta(dctx, ctx, batch, seq, heads, head_dim):
+    """delta f32 [batch, heads, seq] = rowsum(dO * O) per (token, head)."""
+    delta = torch.empty((batch, heads, seq), device=ctx.device, dtype=torch.float32)
+    _flat("fame_attn_delta", dctx.data_ptr(), ctx.data_ptr(), ctx.stride(0), delta.data_ptr(), batch, seq, heads, head_dim)
+    return delta
+
+
+def attn_bwd_pds(qkv, dctx, lse, delta, batch, seq, heads, head_dim, ldp, scale):
+    """P and dS (bf16 [batch*heads*seq, ldp]) from the packed qkv, dO, the forward's lse and delta; scores stay in TMEM."""
+    rows = batch * heads * seq
+    p = torch.empty((rows, ldp), device=qkv.device, dtype=torch.bfloat16)
+    ds = torch.empty((rows, ldp), device=qkv.device, dtype=torch.bfloat16)
+    _flat("fame_attn_bwd_pds", qkv.data_ptr(), qkv.stride(0), dctx.data_ptr(), dctx.stride(0), lse.data_ptr(),
+          delta.data_ptr(), p.data_ptr(), ds.data_ptr(), ldp, batch, seq, heads, head_dim, float(scale))
+    return p, ds
+
+
 def bert_embed_bwd(d_sum, ids, dword, dpos, dtype0, seq, pad_idx=0):
     tokens, hidden = d_sum.shape
     _flat("fame_bert_embed_bwd", d_sum.data_ptr(), ids.data_ptr(), dword.data_ptr(), dpos.data_ptr(), dtype0.data_ptr(),

@@ -316,7 +316,8 @@ def _lab_forward(st, model, lab):
         p = f"{pre}transformer_encoder.layers.{i}."
         s = {"x": x}
         qkv = ops.gemm_bias_act(x, st.w(p + "self_attn.in_proj_weight"), st.f(p + "self_attn.in_proj_bias"))
-        ctx = ops.attn_fwd(qkv, B, L, nh, H // nh)
+        lse = torch.empty((B, nh, L), device=dev, dtype=torch.float32)       # saved for the attention backward
+        ctx = ops.attn_fwd(qkv, B, L, nh, H // nh, lse=lse)
         t1 = ops.gemm_bias_act(ctx, st.w(p + "self_attn.out_proj.weight"), st.f(p + "self_attn.out_proj.bias"), residual=x)
         st1 = torch.empty((B * L, 2), device=dev, dtype=torch.float32)
         x1 = ops.layernorm(t1, st.f(p + "norm1.weight"), st.f(p + "norm1.bias"), layer.norm1.eps, stats=st1)
@@ -324,30 +325,24 @@ def _lab_forward(st, model, lab):
         t2 = ops.gemm_bias_act(h, st.w(p + "linear2.weight"), st.f(p + "linear2.bias"), residual=x1)
         st2 = torch.empty((B * L, 2), device=dev, dtype=torch.float32)
         x = ops.layernorm(t2, st.f(p + "norm2.weight"), st.f(p + "norm2.bias"), layer.norm2.eps, stats=st2)
-        s.update(qkv=qkv, ctx=ctx, t1=t1, st1=st1, x1=x1, h=h, t2=t2, st2=st2)
+        s.update(qkv=qkv, ctx=ctx, lse=lse, t1=t1, st1=st1, x1=x1, h=h, t2=t2, st2=st2)
         saved["layers"].append(s)
     return ops.seq_mean(x, B, L), saved
 
 
-def _attn_backward(qkv, dctx, B, L, nh, D):
-    """dqkv [T, 3*nh*D] bf16 from dctx [T, nh*D]: five batched tensor-core products + one softmax-backward kernel."""
+def _attn_backward(qkv, dctx, ctx, lse, B, L, nh, D):
+    """dqkv [T, 3*nh*D] bf16 from dctx [T, nh*D]: P and dS come out of one kernel that keeps both score products
+    (Q K^T and dO V^T) in TMEM and recomputes the softmax from the forward's row log-sum-exp; three batched tensor-core
+    products turn them into dV, dK, dQ."""
     dev = qkv.device
     W = 3 * nh * D
     HD = nh * D
     ldp = (L + 7) // 8 * 8
-    rows = B * nh * L
-    s = torch.empty((rows, ldp), device=dev, dtype=torch.float32)
-    dp = torch.empty((rows, ldp), device=dev, dtype=torch.float32)
     sq = (L * W, D)                 # (b0 = sequence, b1 = head) strides inside the packed qkv tensor
     sc = (L * HD, D)                # same inside ctx / dctx
-    ss = (nh * L * ldp, L * ldp)    # inside the [B, nh, L, ldp] score tensors
-    # S = Q K^T, dP = dO V^T      (f32 out, padded to ldp columns)
-    T.gemm_ex(qkv, qkv, s, L, ldp, D, lda=W, ldb=W, ldy=ldp, nb0=B, nb1=nh, sa=sq, sb=sq, sy=ss, b_off=HD, n_valid=L,
-              tag="attn_s")
-    T.gemm_ex(dctx, qkv, dp, L, ldp, D, lda=HD, ldb=W, ldy=ldp, nb0=B, nb1=nh, sa=sc, sb=sq, sy=ss, b_off=2 * HD,
-              n_valid=L, tag="attn_dp")
-    p, ds = T.attn_bwd_softmax(s, dp, rows, L, ldp, D ** -0.5)
-    del s, dp
+    ss = (nh * L * ldp, L * ldp)    # inside the [B, nh, L, ldp] probability / score-gradient tensors
+    delta = T.attn_delta(dctx, ctx, B, L, nh, D)
+    p, ds = T.attn_bwd_pds(qkv, dctx, lse, delta, B, L, nh, D, ldp, D ** -0.5)
     dqkv = torch.empty((B * L, W), device=dev, dtype=torch.bfloat16)
     # dV = P^T dO, dK = dS^T Q  (A MN-major: stored [query rows, key cols]; B MN-major: stored [query rows, d cols])
     T.gemm_ex(p, dctx, dqkv, L, D, L, a_mn=True, b_mn=True, lda=ldp, ldb=HD, ldy=W, nb0=B, nb1=nh, sa=ss, sb=sc, sy=sq,
@@ -379,7 +374,7 @@ def _lab_backward(st, model, saved, dlab):
                                  st.gr(p + "norm1.bias"))
         _lin_bwd(st, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", dt1, s["ctx"])
         dctx = T.linear_dgrad(dt1, st.w(p + "self_attn.out_proj.weight"))
-        dqkv = _attn_backward(s["qkv"], dctx, B, L, nh, H // nh)
+        dqkv = _attn_backward(s["qkv"], dctx, s["ctx"], s["lse"], B, L, nh, H // nh)
         _lin_bwd(st, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", dqkv, s["x"])
         dx = T.linear_dgrad(dqkv, st.w(p + "self_attn.in_proj_weight"), aux=dt1, aux_mode=T.AUX_ADD_BF16)
     # token embedding: Linear(1, 768).weight has shape [768, 1] -> its gradient is the [768] vector

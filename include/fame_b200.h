@@ -162,6 +162,8 @@ typedef struct {
     float scale;
     int32_t algo; /* 0 = auto (= 3); 1 = full-row TMEM kernel (head_dim 64, seq <= 512); 2 = streaming flash kernel,
                      one 128-query tile per CTA; 3 = persistent kernel, two 128-query tiles per CTA */
+    float* lse;   /* optional f32 [batch, heads, seq]: log2-domain log-sum-exp of each row of scaled scores, saved for
+                     fame_attn_bwd_pds (P = 2^(s * scale * log2 e - lse)); algo 0 / 3 only; may be NULL */
 } fame_attn_fwd_args;
 int fame_attn_fwd(const fame_attn_fwd_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
 
@@ -390,6 +392,16 @@ int fame_cast_bf16(const float* x, void* y, int64_t n, fame_stream_t stream);
  * f32 result; accumulate = 0 overwrites dW.  Bound by the gradient write, CUDA-core FMAs (skinny_gemm.cuh). */
 int fame_wgrad_small(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, float* out, int64_t ld_out, int32_t M,
                      int32_t N, int32_t K, int32_t accumulate, fame_stream_t stream);
+/* Attention backward, first half (autograd of the sdpa call inside nn.MultiheadAttention, 10_FAME.py:214,445):
+ * P = softmax(Q K^T scale) and dS = scale P (dO V^T - delta) per (sequence, head), both bf16 [batch, heads, seq, ldp]
+ * (columns >= seq zero), from the packed qkv tensor, dO = dctx, the forward's lse and delta = rowsum(dO * O)
+ * (fame_attn_delta).  Both score products stay in TMEM.  The three products dV = P^T dO, dK = dS^T Q, dQ = dS K follow
+ * through fame_gemm_ex.  head_dim 64 or 96; ldp % 8 == 0, ldp >= seq. */
+int fame_attn_delta(const void* dctx, const void* ctx, int64_t ld, float* delta, int32_t batch, int32_t seq,
+                    int32_t heads, int32_t head_dim, fame_stream_t stream);
+int fame_attn_bwd_pds(const void* qkv, int64_t ld_qkv, const void* dctx, int64_t ld_dctx, const float* lse,
+                      const float* delta, void* p, void* ds, int64_t ldp, int32_t batch, int32_t seq, int32_t heads,
+                      int32_t head_dim, float scale, fame_stream_t stream);
 int fame_transpose_bf16_table(const void* table, int32_t n_entries, int32_t total_tiles, fame_stream_t stream);
 
 #ifdef __cplusplus

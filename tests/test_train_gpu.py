@@ -64,18 +64,35 @@ def test_gemm_ex_operand_majors():
     assert (small - ref).abs().max() <= 2e-3 * ref.abs().max()
 
 
-def test_attention_backward_matches_autograd():
-    from fairmultimodal_b200 import train
-    torch.manual_seed(1)
-    B, L, nh, D = 3, 77, 8, 96
-    qkv = torch.randn(B * L, 3 * nh * D, device="cuda").bfloat16()
+@pytest.mark.parametrize("B,L,nh,D,mag", [(3, 77, 8, 96, 1.0), (2, 542, 8, 96, 1.0), (40, 542, 8, 96, 1.0),
+                                         (3, 300, 12, 64, 1.0), (2, 128, 8, 96, 2.5), (1, 12, 8, 96, 1.0)])
+def test_attention_backward_matches_autograd(B, L, nh, D, mag):
+    """Fused P / dS kernel (scores in TMEM, softmax recomputed from the forward's lse) + dV / dK / dQ products against
+    torch.autograd of the same attention; also the saved lse and the probabilities themselves."""
+    from fairmultimodal_b200 import ops, train
+    from fairmultimodal_b200 import ops_train as T
+    torch.manual_seed(B + L)
+    qkv = (torch.randn(B * L, 3 * nh * D, device="cuda") * mag).bfloat16()
     dctx = (torch.randn(B * L, nh * D, device="cuda") * 0.1).bfloat16()
-    dqkv = train._attn_backward(qkv, dctx, B, L, nh, D)
+    lse = torch.empty(B, nh, L, device="cuda")
+    ctx_k = ops.attn_fwd(qkv, B, L, nh, D, lse=lse)
+    dqkv = train._attn_backward(qkv, dctx, ctx_k, lse, B, L, nh, D)
     q = qkv.float().clone().requires_grad_(True)
     qq, kk, vv = q.view(B, L, 3, nh, D).permute(2, 0, 3, 1, 4)
-    ctx = (torch.softmax(qq @ kk.transpose(-1, -2) * D ** -0.5, -1) @ vv).permute(0, 2, 1, 3).reshape(B * L, nh * D)
+    sc = qq @ kk.transpose(-1, -2) * D ** -0.5
+    prob = torch.softmax(sc, -1)
+    ctx = (prob @ vv).permute(0, 2, 1, 3).reshape(B * L, nh * D)
     ctx.backward(dctx.float())
     assert (dqkv.float() - q.grad).abs().max() <= 3e-2 * q.grad.abs().max()
+    ref_lse = torch.logsumexp(sc.detach(), -1) * 1.4426950408889634          # natural log -> log2 units
+    assert (lse - ref_lse).abs().max() <= 2e-2
+    ldp = (L + 7) // 8 * 8
+    delta = T.attn_delta(dctx, ctx_k, B, L, nh, D)
+    p, ds = T.attn_bwd_pds(qkv, dctx, lse, delta, B, L, nh, D, ldp, D ** -0.5)
+    p = p.view(B, nh, L, ldp).float()
+    assert (p[..., :L] - prob.detach()).abs().max() <= 2e-2
+    assert p[..., L:].abs().max().item() == 0 if ldp > L else True
+    assert torch.isfinite(ds.float()).all()
 
 
 def test_layernorm_backward():
