@@ -210,6 +210,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.only_train:
+        info = bench_train(args, world, rank, dev, barrier)
+        if rank == 0:
+            print(json.dumps({"train": info}), flush=True)
+        if world > 1:
+            from fairmultimodal_b200 import parallel
+            sys.stdout.flush()
+            barrier()
+            parallel.shutdown()
+        return
+
     # random-init BERT-base (vocab 28 996), deterministic in the seed; every rank holds a replica
     sd = {k: torch.from_numpy(v) for k, v in
           synth.synth_state_dict(synth.bert_shapes("BioBert.", synth.VOCAB), WSEED).items()}
@@ -343,6 +354,7 @@ if __name__ == "__main__":
                     help="--impl reference: chunks per step (bounded sample of the 256-chunk step)")
     ap.add_argument("--skip-train", action="store_true", help="only the note-encoder workload")
     ap.add_argument("--train-steps", type=int, default=20)
+    ap.add_argument("--only-train", action="store_true", help="diagnostic: print only the training-step object")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

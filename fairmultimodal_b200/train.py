@@ -95,10 +95,13 @@ class FlatTrainState:
         self._t_table = torch.from_numpy(rec.view(np.uint8).copy()).to(dev) if names else None
 
     def grad_buckets(self):
-        """Contiguous ranges of the flat gradient buffer in the order the backward pass completes them (the fusion
-        head, the lab tower, then the demographic tower from its last layer down), for the bucketed gradient
-        all-reduce that overlaps the rest of the backward.  Keys: 'head', 'lab', ('demo', i) = ready once layer i of
-        the demographic BERT is done, 'rest' = everything before (embeddings, sig_weights)."""
+        """Ranges of the flat gradient buffer in the order the backward pass completes them (the fusion head, the
+        demographic tower from its last layer down, then the lab tower), for the bucketed gradient all-reduce that
+        overlaps the rest of the backward.  Keys: 'head', 'lab', ('demo', i) = ready once layer i of the demographic
+        BERT is done, 'rest' = everything before (embeddings, sig_weights).  Each value is a LIST of (lo, hi) ranges:
+        the query / key projections of the demographic BERT are left out -- with its length-1 sequences the softmax
+        is identically 1, their gradient is exactly zero on every rank (never written), and summing
+        57 MB of zeros over NVLink would be 15 % of the traffic."""
         if getattr(self, "_buckets", None) is not None:
             return self._buckets
         first = lambda pre: min((o for n, o in self.offsets.items() if n.startswith(pre)), default=None)
@@ -106,14 +109,35 @@ class FlatTrainState:
         head0 = min(o for n, o in self.offsets.items()
                     if n.startswith(("demo_projector.", "lab_projector.", "text_projector.", "fusion_mlp.")))
         layer = [first(f"behrt_demo.bert.encoder.layer.{i}.") for i in range(12)]
-        cuts = {"head": (head0, self.n), "lab": (lab0, head0)}
+        # exactly-zero gradient ranges: [query.weight, value.weight) of every demographic layer (q.w, q.b, k.w, k.b)
+        zero = []
+        for i in range(12):
+            pre = f"behrt_demo.bert.encoder.layer.{i}.attention.self."
+            lo, hi = self.offsets[pre + "query.weight"], self.offsets[pre + "value.weight"]
+            names = [n for n, o in self.offsets.items() if lo <= o < hi]
+            assert all(n.startswith((pre + "query.", pre + "key.")) for n in names), names
+            zero.append((lo, hi))
+
+        def minus_zero(lo, hi):
+            out, cur = [], lo
+            for zl, zh in zero:
+                if zh <= cur or zl >= hi:
+                    continue
+                if zl > cur:
+                    out.append((cur, zl))
+                cur = max(cur, zh)
+            if cur < hi:
+                out.append((cur, hi))
+            return out
+
+        cuts = {"head": [(head0, self.n)], "lab": [(lab0, head0)]}
         hi = lab0
         for i in DEMO_BUCKET_LAYERS:
-            cuts[("demo", i)] = (layer[i], hi)
+            cuts[("demo", i)] = minus_zero(layer[i], hi)
             hi = layer[i]
-        cuts["rest"] = (0, hi)
-        # sanity: the ranges tile [0, n) exactly
-        spans = sorted(cuts.values())
+        cuts["rest"] = minus_zero(0, hi)
+        # sanity: together with the zero ranges the buckets tile [0, n) exactly
+        spans = sorted([r for v in cuts.values() for r in v] + zero)
         assert spans[0][0] == 0 and spans[-1][1] == self.n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         self._buckets = cuts
         return cuts
@@ -237,8 +261,8 @@ def _lin_bwd(st, wname, bname, dy_bf16, x_bf16, colsum_src=None):
     T.linear_wgrad(dy_bf16, x_bf16, st.gr(wname), accumulate=dy_bf16.shape[0] > T.SKINNY_MAX_ROWS)
 
 
-# a gradient bucket closes after each of these demographic-BERT layers (backward runs 11 -> 0); the remainder (layer 0,
-# embeddings, sig_weights: ~30 MB) is the only all-reduce that cannot overlap with backward compute
+# a gradient bucket closes after each of these demographic-BERT layers (backward runs 11 -> 0); the lab tower runs its
+# backward after the demographic one, so only its own 46 MB bucket is reduced with nothing left to overlap
 DEMO_BUCKET_LAYERS = (10, 8, 6, 4, 2, 1)
 
 
@@ -253,9 +277,9 @@ class _GradReducer:
         if self.group is None:
             return
         import torch.distributed as dist
-        lo, hi = self.st.grad_buckets()[key]
-        if hi > lo:
-            self.work.append(dist.all_reduce(self.st.g[lo:hi], group=self.group, async_op=True))
+        for lo, hi in self.st.grad_buckets()[key]:
+            if hi > lo:
+                self.work.append(dist.all_reduce(self.st.g[lo:hi], group=self.group, async_op=True))
 
     def wait(self):
         for w in self.work:
@@ -459,9 +483,11 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
     red = _GradReducer(st, group)
     ddemo, dlab = _fusion_backward(st, fo, (demo, labe, text), dlogits, w_mod, lambda_l1)
     red.ready("head")
+    # the demographic tower first: it owns 88 % of the gradient bytes and its backward at 32 patients is weight
+    # streaming (HBM / latency bound), so its buckets travel over NVLink underneath the tensor-core-bound lab backward
+    _demo_backward(st, model, sv_d, ddemo, red)
     _lab_backward(st, model, sv_l, dlab)
     red.ready("lab")
-    _demo_backward(st, model, sv_d, ddemo, red)
     red.wait()
     return loss, fo
 
