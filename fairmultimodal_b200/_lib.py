@@ -59,7 +59,7 @@ class AttnFwdArgs(C.Structure):
         ("key_mask", C.c_void_p),
         ("ctx", C.c_void_p), ("ld_ctx", C.c_int64),
         ("batch", C.c_int32), ("seq", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
-        ("scale", C.c_float), ("algo", C.c_int32), ("lse", C.c_void_p),
+        ("scale", C.c_float), ("algo", C.c_int32), ("lse", C.c_void_p), ("kv_len", C.c_void_p),
     ]
 
 
@@ -162,6 +162,7 @@ EVAL_COUNTS_LEN = 914
 _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 # flat-argument entry points (backward pass / optimizer): name -> argument types, the stream is appended
 FLAT_OPS = {
+    "fame_mask_kv_len": [_P, _I32, _I32, _P],
     "fame_layernorm_bwd": [_P, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32],
     "fame_gelu_fwd": [_P, _P, _I64],
     "fame_gelu_bwd": [_P, _P, _P, _I64],

@@ -176,9 +176,11 @@ class BertModelB200(nn.Module):
         pk = self._pack()
         eps = c.layer_norm_eps
         H, nh = c.hidden_size, c.num_attention_heads
-        mask = None
+        mask = kv_len = None
         if attention_mask is not None:
             mask = (attention_mask != 0).to(torch.uint8).contiguous()
+            if S > 128:
+                kv_len = ops.mask_kv_len(mask)      # once per batch: the 12 layers skip all-padding key blocks
         e = pk["emb"]
         x = ops.bert_embed(input_ids.to(torch.int64), e["word"], e["pos"], e["type0"], e["g"], e["b"], eps, S)
         for l in pk["layers"]:
@@ -188,7 +190,7 @@ class BertModelB200(nn.Module):
                 ctx = ops.gemm_bias_act(x, l["wqkv"][2 * H:], l["bqkv"][2 * H:])
             else:
                 qkv = ops.gemm_bias_act(x, l["wqkv"], l["bqkv"])
-                ctx = ops.attn_fwd(qkv, B, S, nh, H // nh, key_mask=mask)
+                ctx = ops.attn_fwd(qkv, B, S, nh, H // nh, key_mask=mask, kv_len=kv_len)
             t = ops.gemm_bias_act(ctx, l["wo"], l["bo"], residual=x)
             x = ops.layernorm(t, l["ln1"][0], l["ln1"][1], eps, out=t)
             h = ops.gemm_bias_act(x, l["w1"], l["b1"], act=ops.ACT_GELU_ERF)

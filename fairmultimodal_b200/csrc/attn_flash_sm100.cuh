@@ -38,6 +38,7 @@ struct FaParams {
     int q_col0, k_col0, v_col0;  // first column of Q / K / V of head 0 inside the packed tensor
     float scale_log2e;
     float* lse;               // optional [batch, heads, seq]: row log-sum-exp in log2 units of the scaled scores
+    const int* kv_len;        // optional [batch]: 1 + last attended key (pair kernel: skips fully masked key blocks)
 };
 
 template <int D>

@@ -110,6 +110,13 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
 
     // item -> (sequence b, head h, query pair qp); consecutive items share K/V of one (b, h) through L2
     auto t1_active = [&](int item) { return (item % qpairs) * 256 + 128 < S; };
+    // key blocks of an item: all of them, or only those that hold an attended key of its sequence (p.kv_len); at
+    // least one, so that an all-masked sequence still produces its zero rows
+    auto nblk_of = [&](int item) {
+        if (p.kv_len == nullptr) return nblk;
+        const int len = __ldg(p.kv_len + (item / qpairs) / p.heads);
+        return max(1, min(nblk, (len + 127) >> 7));
+    };
 
     if (warp == 8) {
         if (lane == 0) {
@@ -129,7 +136,8 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
                         tma_load_2d(smem_q + (qb * 2 + t) * TILE + x * kFaBoxBytes, &tmap_qkv, &q_full[qb],
                                     p.q_col0 + h * D + x * 64, row0 + qp * 256 + t * 128, kEvictFirst);
                 if (++qb == QB) { qb = 0; qph ^= 1; }
-                for (int j = 0; j < nblk; ++j) {
+                const int nb_item = nblk_of(item);
+                for (int j = 0; j < nb_item; ++j) {
                     mbar_wait(&kv_empty[st], kph ^ 1);
                     mbar_arrive_expect_tx(&k_full[st], TILE);
 #pragma unroll
@@ -154,6 +162,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
             int n_item = blockIdx.x, n_j = 0, n_qb = 0, ks = 0;
             uint32_t n_qph = 0, kph = 0;
             bool n_t1 = t1_active(n_item);
+            int n_nblk = nblk_of(n_item);
             auto issue_s = [&](int t) {
                 if (t == 0) {
                     if (n_j == 0) mbar_wait(&q_full[n_qb], n_qph);
@@ -170,13 +179,14 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
                 }
                 umma_commit(&s_full[t]);
                 if (t == 1 || !n_t1) {          // last tile of this block: advance the cursor
-                    if (n_j == nblk - 1) umma_commit(&q_empty[n_qb]);
+                    if (n_j == n_nblk - 1) umma_commit(&q_empty[n_qb]);
                     if (++ks == ST) { ks = 0; kph ^= 1; }
-                    if (++n_j == nblk) {
+                    if (++n_j == n_nblk) {
                         n_j = 0;
                         n_item += gridDim.x;
                         if (++n_qb == QB) { n_qb = 0; n_qph ^= 1; }
                         n_t1 = n_item < num_items && t1_active(n_item);
+                        if (n_item < num_items) n_nblk = nblk_of(n_item);
                     }
                 }
             };
@@ -189,7 +199,8 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
             uint32_t vph = 0, pph0 = 0, pph1 = 0;
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
                 const bool t1 = t1_active(item);
-                for (int j = 0; j < nblk; ++j) {
+                const int nb_item = nblk_of(item);
+                for (int j = 0; j < nb_item; ++j) {
                     mbar_wait(&v_full[vs], vph);
                     const uint32_t v_addr = smem_u32(smem_v + vs * TILE);
                     auto issue_pv = [&](int t) {
@@ -198,7 +209,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
                             umma_bf16_ts(tmem_base + kColO + t * 128, tmem_base + t * 128 + kk * 8,
                                          make_smem_desc_sw128(v_addr + kk * 2048, kFaBoxBytes, 1024), idesc_pv,
                                          (j | kk) != 0);
-                        if (j == nblk - 1) umma_commit(&o_full[t]);
+                        if (j == nb_item - 1) umma_commit(&o_full[t]);
                     };
                     mbar_wait(&p_full[0], pph0);
                     pph0 ^= 1;
@@ -235,7 +246,8 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
             const int qp = item % qpairs, bh = item / qpairs;
             const int h = bh % p.heads, b = bh / p.heads;
             float m = -INFINITY, l = 0.f;   // running reference max (log2 units, scaled) and row sum
-            for (int j = 0; j < nblk; ++j) {
+            const int nb_item = nblk_of(item);
+            for (int j = 0; j < nb_item; ++j) {
                 // validity of the 128 keys of this block: inside the sequence and not masked by the caller
                 const int key0 = j * 128;
                 uint32_t vm[4];

@@ -152,6 +152,7 @@ static int launch_pair(const fame_attn_fwd_args* a, const CUtensorMap& tq, int s
     p.v_col0 = 2 * a->heads * D;
     p.scale_log2e = a->scale * 1.4426950408889634f;
     p.lse = a->lse;
+    p.kv_len = a->kv_len;
     const int qpairs = (a->seq + 255) / 256;
     const long long items = (long long)a->batch * a->heads * qpairs;
     if (items > 0x7fffffffll) return FAME_ERR_SHAPE;
@@ -263,6 +264,22 @@ int fame_layernorm(const fame_layernorm_args* a, void*, size_t, fame_stream_t st
     int rc = device_info(&d);
     if (rc != FAME_OK) return rc;
     if (a->rows == 0) return FAME_OK;
+    if (a->x_dtype == FAME_DT_BF16 && a->y != nullptr && a->y_f32 == nullptr) {
+        // bf16 -> bf16: two rows per warp, packed registers (rowwise.cuh)
+        const int per_block = 2 * fame::kLn2WarpsPerBlock;
+        const int grid2 = (a->rows + per_block - 1) / per_block;
+        if (a->cols <= 768)
+            fame::layernorm_bf16_rows2_kernel<3><<<grid2, fame::kLn2WarpsPerBlock * 32, 0, stream>>>(
+                reinterpret_cast<const __nv_bfloat16*>(a->x), a->ldx, a->gamma, a->beta,
+                reinterpret_cast<__nv_bfloat16*>(a->y), a->ldy, reinterpret_cast<float2*>(a->stats), a->rows, a->cols,
+                a->eps);
+        else
+            fame::layernorm_bf16_rows2_kernel<4><<<grid2, fame::kLn2WarpsPerBlock * 32, 0, stream>>>(
+                reinterpret_cast<const __nv_bfloat16*>(a->x), a->ldx, a->gamma, a->beta,
+                reinterpret_cast<__nv_bfloat16*>(a->y), a->ldy, reinterpret_cast<float2*>(a->stats), a->rows, a->cols,
+                a->eps);
+        return launch_status();
+    }
     const int grid = (a->rows + fame::kLnWarpsPerBlock - 1) / fame::kLnWarpsPerBlock;
     if (a->x_dtype == FAME_DT_F32)
         fame::layernorm_kernel<true><<<grid, fame::kLnWarpsPerBlock * 32, 0, stream>>>(
@@ -304,6 +321,7 @@ int fame_attn_fwd(const fame_attn_fwd_args* a, void*, size_t, fame_stream_t stre
         return FAME_ERR_SHAPE;
     if (a->algo < 0 || a->algo > 3) return FAME_ERR_SHAPE;
     if (a->lse != nullptr && a->algo != 0 && a->algo != 3) return FAME_ERR_SHAPE;   // only the persistent kernel saves it
+    if (a->kv_len != nullptr && a->algo != 0 && a->algo != 3) return FAME_ERR_SHAPE;
     const bool fullrow_ok = a->head_dim == fame::kAttnD && a->seq <= fame::kAttnMaxS;
     if (a->algo == 1 && !fullrow_ok) return FAME_ERR_SHAPE;
     const int64_t width = 3ll * a->heads * a->head_dim;
@@ -342,6 +360,17 @@ int fame_attn_fwd(const fame_attn_fwd_args* a, void*, size_t, fame_stream_t stre
     p.scale_log2e = a->scale * 1.4426950408889634f;
     dim3 grid((a->seq + fame::kAttnBQ - 1) / fame::kAttnBQ, a->heads, a->batch);
     fame::attn_fwd_d64_kernel<<<grid, fame::kAttnThreads, fame::kAttnSmemBytes, stream>>>(tq, p);
+    return launch_status();
+}
+
+int fame_mask_kv_len(const uint8_t* key_mask, int32_t batch, int32_t seq, int32_t* kv_len, fame_stream_t stream) {
+    if (key_mask == nullptr || kv_len == nullptr) return FAME_ERR_NULLPTR;
+    if (batch < 0 || seq <= 0) return FAME_ERR_SHAPE;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    if (batch == 0) return FAME_OK;
+    fame::mask_kv_len_kernel<<<(batch + 7) / 8, 256, 0, stream>>>(key_mask, batch, seq, kv_len);
     return launch_status();
 }
 

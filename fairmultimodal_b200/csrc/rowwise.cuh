@@ -174,6 +174,131 @@ layernorm_kernel(const void* __restrict__ x, long long ldx, const float* __restr
     }
 }
 
+// bf16 -> bf16 fast path (the 24 LayerNorms of a note-encoder step: 201 MB in, 201 MB out each, HBM bound).
+// A warp owns TWO rows at a time and keeps them as packed bf16 (12 + 12 registers at 768 columns) instead of 32 + 32
+// floats: ~40 registers per thread => 48 resident warps per SM x 2 rows x 1.5 KB = 147 KB of loads in flight per SM
+// (the one-row kernel above had 32 warps x 1.5 KB = 49 KB, below what 6.5 TB/s x ~1.5 us of loaded latency needs),
+// and the two rows' shuffle reductions interleave.  Two-pass variance on the register copy, as above.
+constexpr int kLn2WarpsPerBlock = 8;
+
+// volatile: each pass re-expands the packed row copy; without it the compiler keeps all 48 expanded floats alive
+// across the reductions and spills them
+__device__ __forceinline__ float bf16_lo(uint32_t w) {
+    float f;
+    asm volatile("shl.b32 %0, %1, 16;" : "=f"(f) : "r"(w));
+    return f;
+}
+__device__ __forceinline__ float bf16_hi(uint32_t w) {
+    float f;
+    asm volatile("and.b32 %0, %1, 0xffff0000;" : "=f"(f) : "r"(w));
+    return f;
+}
+__device__ __forceinline__ float sum8(const uint4& u) {
+    return ((bf16_lo(u.x) + bf16_hi(u.x)) + (bf16_lo(u.y) + bf16_hi(u.y))) +
+           ((bf16_lo(u.z) + bf16_hi(u.z)) + (bf16_lo(u.w) + bf16_hi(u.w)));
+}
+__device__ __forceinline__ float sq(float d) { return d * d; }
+__device__ __forceinline__ float sqdev8(const uint4& u, float m) {
+    return ((sq(bf16_lo(u.x) - m) + sq(bf16_hi(u.x) - m)) + (sq(bf16_lo(u.y) - m) + sq(bf16_hi(u.y) - m))) +
+           ((sq(bf16_lo(u.z) - m) + sq(bf16_hi(u.z) - m)) + (sq(bf16_lo(u.w) - m) + sq(bf16_hi(u.w) - m)));
+}
+__device__ __forceinline__ uint32_t ln_out2(uint32_t w, float m, float rs, float g0, float g1, float b0, float b1) {
+    return pack_bf16x2((bf16_lo(w) - m) * rs * g0 + b0, (bf16_hi(w) - m) * rs * g1 + b1);
+}
+
+template <int CH>   // chunks of 8 columns per lane: cols <= CH * 256
+__global__ void __launch_bounds__(kLn2WarpsPerBlock * 32, 5)
+layernorm_bf16_rows2_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, long long ldy,
+                            float2* __restrict__ stats, int rows, int cols, float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = (blockIdx.x * kLn2WarpsPerBlock + warp) * 2;
+    if (row0 >= rows) return;
+    const bool two = row0 + 1 < rows;
+    const int nchunks = cols >> 3;
+    const uint4* xa = reinterpret_cast<const uint4*>(x + (long long)row0 * ldx);
+    const uint4* xb = reinterpret_cast<const uint4*>(x + (long long)(row0 + (two ? 1 : 0)) * ldx);
+    uint4 ra[CH], rb[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        const int ch = lane + 32 * i;
+        if (ch < nchunks) {
+            ra[i] = ld_nc_na(xa + ch);
+            rb[i] = ld_nc_na(xb + ch);
+        } else {
+            ra[i] = make_uint4(0, 0, 0, 0);
+            rb[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        sa += sum8(ra[i]);
+        sb += sum8(rb[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    const float inv_n = 1.0f / (float)cols;
+    const float ma = sa * inv_n, mb = sb * inv_n;
+    float qa = 0.f, qb = 0.f;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        if (lane + 32 * i < nchunks) {      // the zero padding of absent chunks must not enter the variance
+            qa += sqdev8(ra[i], ma);
+            qb += sqdev8(rb[i], mb);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        qa += __shfl_xor_sync(0xffffffffu, qa, o);
+        qb += __shfl_xor_sync(0xffffffffu, qb, o);
+    }
+    const float rsa = rsqrtf(qa * inv_n + eps), rsb = rsqrtf(qb * inv_n + eps);
+    if (stats != nullptr && lane == 0) {
+        stats[row0] = make_float2(ma, rsa);
+        if (two) stats[row0 + 1] = make_float2(mb, rsb);
+    }
+    uint4* ya = reinterpret_cast<uint4*>(y + (long long)row0 * ldy);
+    uint4* yb = reinterpret_cast<uint4*>(y + (long long)(row0 + 1) * ldy);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        const int ch = lane + 32 * i;
+        if (ch < nchunks) {
+            const float4 g0 = ld_nc_f4_pinned(reinterpret_cast<const float4*>(gamma) + 2 * ch);
+            const float4 b0 = ld_nc_f4_pinned(reinterpret_cast<const float4*>(beta) + 2 * ch);
+            uint4 oa, ob;
+            oa.x = ln_out2(ra[i].x, ma, rsa, g0.x, g0.y, b0.x, b0.y);
+            oa.y = ln_out2(ra[i].y, ma, rsa, g0.z, g0.w, b0.z, b0.w);
+            ob.x = ln_out2(rb[i].x, mb, rsb, g0.x, g0.y, b0.x, b0.y);
+            ob.y = ln_out2(rb[i].y, mb, rsb, g0.z, g0.w, b0.z, b0.w);
+            const float4 g1 = ld_nc_f4_pinned(reinterpret_cast<const float4*>(gamma) + 2 * ch + 1);
+            const float4 b1 = ld_nc_f4_pinned(reinterpret_cast<const float4*>(beta) + 2 * ch + 1);
+            oa.z = ln_out2(ra[i].z, ma, rsa, g1.x, g1.y, b1.x, b1.y);
+            oa.w = ln_out2(ra[i].w, ma, rsa, g1.z, g1.w, b1.z, b1.w);
+            ob.z = ln_out2(rb[i].z, mb, rsb, g1.x, g1.y, b1.x, b1.y);
+            ob.w = ln_out2(rb[i].w, mb, rsb, g1.z, g1.w, b1.z, b1.w);
+            ya[ch] = oa;
+            if (two) yb[ch] = ob;
+        }
+    }
+}
+
+// kv_len[b] = 1 + index of the last non-zero byte of key_mask[b, :]  (0 for an all-zero row); warp per sequence
+__global__ void __launch_bounds__(256)
+mask_kv_len_kernel(const uint8_t* __restrict__ key_mask, int batch, int seq, int* __restrict__ kv_len) {
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= batch) return;
+    int last = 0;
+    for (int k = lane; k < seq; k += 32)
+        if (key_mask[(long long)b * seq + k] != 0) last = k + 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    if (lane == 0) kv_len[b] = last;
+}
+
 // ---------------------------------------------------------------------------------------- K4 BERT embedding
 // hidden % 128 == 0, hidden <= 1024: lane l owns float4 chunks l, l+32, ... (hidden/128 of them).
 constexpr int kEmbMaxChunks = 8;

@@ -47,6 +47,19 @@ def _call(name, args, work=0.0, tag="", ws=None):
     _TRACE.append((name, tag, e0, e1, work))
 
 
+def _call_flat(name, work, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    if _TRACE is None:
+        _lib.call_flat(name, _stream(), *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.call_flat(name, _stream(), *args)
+    e1.record()
+    _TRACE.append((name, "", e0, e1, work))
+
+
 def _cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
     if not t.is_cuda:
         raise _lib.FameError(f"{name} must be a CUDA tensor (fairmultimodal_b200 has no CPU path)")
@@ -146,9 +159,21 @@ def bert_embed(ids, word, pos, type_emb, gamma, beta, eps, seq_len, err_flag=Non
     return out
 
 
-def attn_fwd(qkv, batch, seq, heads, head_dim, key_mask=None, scale=None, out=None, algo=0, lse=None):
+def mask_kv_len(key_mask):
+    """uint8 [batch, seq] key mask -> int32 [batch]: 1 + index of the last attended key (0 if none)."""
+    _cuda(key_mask, "key_mask", torch.uint8)
+    if not key_mask.is_contiguous() or key_mask.dim() != 2:
+        raise _lib.FameError("key_mask must be contiguous uint8 [batch, seq]")
+    batch, seq = key_mask.shape
+    out = torch.empty(batch, device=key_mask.device, dtype=torch.int32)
+    _call_flat("fame_mask_kv_len", 1.0 * batch * seq, key_mask.data_ptr(), batch, seq, out.data_ptr())
+    return out
+
+
+def attn_fwd(qkv, batch, seq, heads, head_dim, key_mask=None, scale=None, out=None, algo=0, lse=None, kv_len=None):
     """qkv bf16 [batch*seq, 3*heads*head_dim] -> ctx bf16 [batch*seq, heads*head_dim].  lse (optional f32
-    [batch, heads, seq]) receives the row log-sum-exp the backward pass needs."""
+    [batch, heads, seq]) receives the row log-sum-exp the backward pass needs.  kv_len (optional int32 [batch], from
+    mask_kv_len(key_mask)) lets the kernel skip key blocks that hold only masked keys; the result does not change."""
     _cuda(qkv, "qkv", torch.bfloat16)
     if out is None:
         out = torch.empty((batch * seq, heads * head_dim), device=qkv.device, dtype=torch.bfloat16)
@@ -166,6 +191,12 @@ def attn_fwd(qkv, batch, seq, heads, head_dim, key_mask=None, scale=None, out=No
     a.scale = float(scale) if scale is not None else head_dim ** -0.5
     a.algo = algo
     a.lse = _cuda(lse, "lse", torch.float32).data_ptr() if lse is not None else None
+    if kv_len is not None:
+        if key_mask is None or kv_len.numel() != batch:
+            raise _lib.FameError("kv_len needs key_mask and must be int32 [batch]")
+        a.kv_len = _cuda(kv_len, "kv_len", torch.int32).data_ptr()
+    else:
+        a.kv_len = None
     _call("fame_attn_fwd", a, 4.0 * batch * heads * seq * seq * head_dim)
     return out
 

@@ -164,8 +164,17 @@ typedef struct {
                      one 128-query tile per CTA; 3 = persistent kernel, two 128-query tiles per CTA */
     float* lse;   /* optional f32 [batch, heads, seq]: log2-domain log-sum-exp of each row of scaled scores, saved for
                      fame_attn_bwd_pds (P = 2^(s * scale * log2 e - lse)); algo 0 / 3 only; may be NULL */
+    const int32_t* kv_len; /* optional int32 [batch] from fame_mask_kv_len: 1 + index of the last attended key of each
+                     sequence.  Key blocks (128 keys) that lie entirely beyond it hold only masked keys (probability
+                     exactly 0) and are not loaded, multiplied or exponentiated; results are identical with and
+                     without it.  algo 0 / 3 only; may be NULL */
 } fame_attn_fwd_args;
 int fame_attn_fwd(const fame_attn_fwd_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
+
+/* fame_mask_kv_len: kv_len[b] = 1 + max{k : key_mask[b, k] != 0} (0 when the row is all zero).  key_mask uint8
+ * [batch, seq] as handed to fame_attn_fwd (the reference's attention_mask, HF:709-713), computed once per batch and
+ * shared by the 12 layers. */
+int fame_mask_kv_len(const uint8_t* key_mask, int32_t batch, int32_t seq, int32_t* kv_len, fame_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K5  fame_segment_mean:  out[p,:] = mean_{c in [offsets[p], offsets[p+1])} x[c*ldx : c*ldx+cols]; zeros if empty.

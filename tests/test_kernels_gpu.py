@@ -152,6 +152,50 @@ def test_attention(H, D, B, S, masked, algo):
     _close(ctx, ref, 2e-2)
 
 
+@pytest.mark.parametrize("H,D,B,S", [(12, 64, 40, 512), (8, 96, 7, 542), (12, 64, 3, 700), (12, 64, 200, 512)])
+def test_attention_kv_len_skips_only_masked_blocks(H, D, B, S):
+    """Key blocks beyond the last attended key are skipped: the context is bit-identical to the unskipped kernel
+    (masked keys have probability exactly 0 either way), for prefix masks, masks with holes and all-masked rows."""
+    from fairmultimodal_b200 import ops
+    torch.manual_seed(S + B)
+    qkv = torch.randn(B * S, 3 * H * D, device="cuda").bfloat16()
+    lens = torch.randint(1, S + 1, (B,), device="cuda")
+    lens[0] = S
+    lens[1] = 1
+    mask = (torch.arange(S, device="cuda")[None, :] < lens[:, None])
+    mask[2, : S // 2 : 3] = False                       # holes inside the attended prefix
+    if B > 4:
+        mask[3] = False                                  # nothing attended at all
+    mask = mask.to(torch.uint8).contiguous()
+    kv_len = ops.mask_kv_len(mask)
+    last = torch.where(mask.bool(), torch.arange(1, S + 1, device="cuda")[None, :], 0).max(dim=1).values
+    assert torch.equal(kv_len.long(), last)              # integer indexing: bit-exact
+    lse0 = torch.empty(B, H, S, device="cuda")
+    lse1 = torch.empty(B, H, S, device="cuda")
+    full = ops.attn_fwd(qkv, B, S, H, D, key_mask=mask, lse=lse0)
+    skip = ops.attn_fwd(qkv, B, S, H, D, key_mask=mask, kv_len=kv_len, lse=lse1)
+    assert torch.equal(full, skip)
+    assert torch.equal(lse0, lse1)
+
+
+@pytest.mark.parametrize("rows,cols", [(1003, 768), (1, 768), (16, 8), (130, 1024), (257, 520)])
+def test_layernorm_bf16_fast_path(rows, cols):
+    """bf16 -> bf16 LayerNorm (two rows per warp): odd row counts, narrow and 1024-wide rows, in place, statistics."""
+    from fairmultimodal_b200 import ops
+    torch.manual_seed(rows + cols)
+    x = (torch.randn(rows, cols, device="cuda") * 2 + 0.5).bfloat16()
+    g, b = torch.randn(cols, device="cuda"), torch.randn(cols, device="cuda")
+    ref = torch.nn.functional.layer_norm(x.float(), (cols,), g, b, 1e-12)
+    stats = torch.empty(rows, 2, device="cuda")
+    _close(ops.layernorm(x, g, b, 1e-12, stats=stats), ref, 1e-2)
+    xf = x.float()
+    assert torch.allclose(stats[:, 0], xf.mean(1), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(stats[:, 1], (xf.var(1, unbiased=False) + 1e-12).rsqrt(), rtol=1e-4)
+    y = x.clone()
+    ops.layernorm(y, g, b, 1e-12, out=y)                 # in place, as the note encoder calls it
+    _close(y, ref, 1e-2)
+
+
 def test_layernorm_and_embed():
     from fairmultimodal_b200 import ops
     torch.manual_seed(0)
