@@ -203,6 +203,7 @@ OP_TABLE = {
     "fame_gemm_ex": GemmExArgs,
 }
 PLAIN_SYMBOLS = ["fame_strerror", "fame_last_cuda_error", "fame_abi_version", "fame_device_check", "fame_sm_count",
+                 "fame_set_sm_budget",
                  "fame_rank_counts_workspace_bytes", "fame_fusion_fwd_workspace_bytes"]
 # C struct name -> ctypes mirror (tests compare sizeof() of both)
 STRUCT_NAMES = {
@@ -234,6 +235,8 @@ def load() -> C.CDLL:
     for name in ("fame_last_cuda_error", "fame_abi_version", "fame_device_check", "fame_sm_count"):
         getattr(lib, name).restype = C.c_int
         getattr(lib, name).argtypes = []
+    lib.fame_set_sm_budget.restype = C.c_int
+    lib.fame_set_sm_budget.argtypes = [C.c_int]
     lib.fame_rank_counts_workspace_bytes.restype = C.c_size_t
     lib.fame_rank_counts_workspace_bytes.argtypes = [C.c_int32]
     lib.fame_fusion_fwd_workspace_bytes.restype = C.c_size_t

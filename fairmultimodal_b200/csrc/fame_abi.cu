@@ -27,6 +27,13 @@
 
 namespace {
 
+// SMs the persistent tensor-core kernels (GEMM, attention forward / backward) may occupy; 0 = all of them.
+static int g_sm_budget = 0;
+static inline int persistent_sms(int sm_count) {
+    return (g_sm_budget > 0 && g_sm_budget < sm_count) ? g_sm_budget : sm_count;
+}
+
+
 thread_local int g_last_cuda_error = 0;
 
 int cuda_fail(cudaError_t e) {
@@ -156,7 +163,8 @@ static int launch_pair(const fame_attn_fwd_args* a, const CUtensorMap& tq, int s
     const int qpairs = (a->seq + 255) / 256;
     const long long items = (long long)a->batch * a->heads * qpairs;
     if (items > 0x7fffffffll) return FAME_ERR_SHAPE;
-    const int grid = items < sm_count ? (int)items : sm_count;
+    const int sms = persistent_sms(sm_count);
+    const int grid = items < sms ? (int)items : sms;
     fame::attn_fwd_pair_kernel<D><<<grid, fame::kApThreads, fame::ApCfg<D>::kSmemBytes, stream>>>(tq, p, (int)items,
                                                                                                  qpairs);
     return launch_status();
@@ -178,7 +186,8 @@ static int launch_attn_bwd_pds(const CUtensorMap& tq, const CUtensorMap& tdo, co
     const int qtiles = (p.seq + 127) / 128;
     const long long items = (long long)p.batch * p.heads * qtiles;
     if (items > 0x7fffffffll) return FAME_ERR_SHAPE;
-    const int grid = items < sm_count ? (int)items : sm_count;
+    const int sms = persistent_sms(sm_count);
+    const int grid = items < sms ? (int)items : sms;
     fame::attn_bwd_pds_kernel<D><<<grid, fame::kAbThreads, fame::AbCfg<D>::kSmemBytes, stream>>>(tq, tdo, p, (int)items,
                                                                                                 qtiles);
     return launch_status();
@@ -208,6 +217,12 @@ int fame_abi_version(void) { return 1; }
 int fame_device_check(void) {
     DeviceInfo* d = nullptr;
     return device_info(&d);
+}
+
+int fame_set_sm_budget(int sms) {
+    if (sms < 0) return FAME_ERR_SHAPE;
+    g_sm_budget = sms;
+    return FAME_OK;
 }
 
 int fame_sm_count(void) {

@@ -60,6 +60,11 @@ def _call_flat(name, work, *args):
     _TRACE.append((name, "", e0, e1, work))
 
 
+def set_sm_budget(sms: int) -> None:
+    """SMs that persistent tensor-core kernels launched from now on may occupy (0 = all)."""
+    _lib.check(_lib.load().fame_set_sm_budget(int(sms)), "fame_set_sm_budget")
+
+
 def _cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
     if not t.is_cuda:
         raise _lib.FameError(f"{name} must be a CUDA tensor (fairmultimodal_b200 has no CPU path)")

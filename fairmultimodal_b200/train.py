@@ -27,8 +27,64 @@ import torch
 from . import ops
 from . import ops_train as T
 
+import os
+
+TWO_STREAMS = os.environ.get("FAME_TWO_STREAMS", "1") != "0"   # demographic and lab towers on concurrent streams
+# SMs left free by the lab tower's persistent kernels while the demographic stream (and NCCL) runs beside it
+RESERVED_SMS = int(os.environ.get("FAME_RESERVED_SMS", "16"))
+RESERVED_SMS_DP = int(os.environ.get("FAME_RESERVED_SMS_DP", "32"))   # data parallel: the NCCL kernels need SMs too
+
 NO_GRAD_PREFIXES = ("classifier_demo.", "classifier_lab.", "classifier_text.", "behrt_demo.bert.pooler.")
 ATTR_IDX = (2, 4, 5)          # age_ids, ethnicity_ids, insurance_ids inside the 9-tensor batch (10_FAME.py:431)
+
+
+# regions of the flat buffers in layout order: never reduced | demo layers 11 .. 1 | demo layer 0 | rest | lab | head
+_R_NORED, _R_DEMO11, _R_REST, _R_LAB, _R_HEAD = 0, 1, 13, 14, 15
+
+
+def _r_demo(i):
+    return _R_DEMO11 + (11 - i)
+
+
+
+def _layout_key(name):
+    """Region of the flat buffers a parameter lives in (see FlatTrainState.__init__)."""
+    if name.startswith("behrt_demo.bert.encoder.layer."):
+        i = int(name.split(".")[4])
+        if ".attention.self.query." in name or ".attention.self.key." in name:
+            return _R_NORED
+        return _r_demo(i)
+    if name.startswith("behrt_lab."):
+        return _R_LAB
+    if name.startswith(("demo_projector.", "lab_projector.", "text_projector.", "fusion_mlp.")):
+        return _R_HEAD
+    return _R_REST
+
+
+def plan_layout(named_sizes):
+    """[(name, numel)] sorted by region -> (offsets {name: first element}, regions {region: (lo, hi)}, total)."""
+    offsets, region, off = {}, {}, 0
+    for n, k in named_sizes:
+        offsets[n] = off
+        r = _layout_key(n)
+        lo, _ = region.get(r, (off, off))
+        off += (k + 7) // 8 * 8                                  # 32-byte aligned segments
+        region[r] = (lo, off)
+    return offsets, region, off
+
+
+def plan_buckets(region, total):
+    """Contiguous all-reduce buckets over the regions of plan_layout (see FlatTrainState.grad_buckets)."""
+    assert _R_LAB in region and _R_HEAD in region and _R_REST in region
+    cuts, lo = {}, region[_r_demo(11)][0]
+    for i in DEMO_BUCKET_LAYERS:
+        cuts[("demo", i)] = (lo, region[_r_demo(i)][1])
+        lo = region[_r_demo(i)][1]
+    cuts["tail"] = (lo, region[_R_HEAD][1])
+    # sanity: together with the never-reduced region the buckets tile [0, total) exactly
+    spans = sorted(list(cuts.values()) + [region.get(_R_NORED, (0, 0))])
+    assert spans[0][0] == 0 and spans[-1][1] == total and all(a[1] == b[0] for a, b in zip(spans, spans[1:])), spans
+    return cuts
 
 
 class FlatTrainState:
@@ -38,11 +94,13 @@ class FlatTrainState:
         self.model = model
         dev = next(model.parameters()).device
         named = [(n, p) for n, p in model.named_parameters() if not n.startswith(NO_GRAD_PREFIXES)]
-        self.offsets, off = {}, 0
-        for n, p in named:
-            self.offsets[n] = off
-            off += (p.numel() + 7) // 8 * 8                      # 32-byte aligned segments
-        self.n = off
+        # Layout = the order in which the backward completes gradients, so that every all-reduce bucket is ONE
+        # contiguous range:  [never reduced | rest | demo layers 0..11 | lab | head].  "Never reduced": query / key
+        # projections of the demographic BERT -- with its length-1 sequences the softmax is identically 1, their
+        # gradient is exactly zero on every rank (never written); 57 MB that need not cross NVLink.
+        named.sort(key=lambda np_: _layout_key(np_[0]))          # stable: module order inside each region
+        self.offsets, self.region, self.n = plan_layout([(n, p.numel()) for n, p in named])
+        off = self.n
         self.p = torch.zeros(off, device=dev, dtype=torch.float32)
         self.g = torch.zeros(off, device=dev, dtype=torch.float32)
         self.m = torch.zeros(off, device=dev, dtype=torch.float32)
@@ -95,52 +153,26 @@ class FlatTrainState:
         self._t_table = torch.from_numpy(rec.view(np.uint8).copy()).to(dev) if names else None
 
     def grad_buckets(self):
-        """Ranges of the flat gradient buffer in the order the backward pass completes them (the fusion head, the
-        demographic tower from its last layer down, then the lab tower), for the bucketed gradient all-reduce that
-        overlaps the rest of the backward.  Keys: 'head', 'lab', ('demo', i) = ready once layer i of the demographic
-        BERT is done, 'rest' = everything before (embeddings, sig_weights).  Each value is a LIST of (lo, hi) ranges:
-        the query / key projections of the demographic BERT are left out -- with its length-1 sequences the softmax
-        is identically 1, their gradient is exactly zero on every rank (never written), and summing
-        57 MB of zeros over NVLink would be 15 % of the traffic."""
+        """Contiguous ranges (lo, hi) of the flat gradient buffer, keyed by the backward event that completes them:
+        ('demo', i) closes once layer i of the demographic BERT is done (its backward runs 11 -> 0 on the side stream),
+        'tail' = the last demographic layers + embeddings + sig_weights + lab tower + fusion head, complete when both
+        tower streams have joined.  Few large buckets: an NCCL all-reduce of 335 MB takes 0.88 ms on 8 B200s in one
+        piece and 1.67 ms in eight, and every call costs 40-70 us of latency."""
         if getattr(self, "_buckets", None) is not None:
             return self._buckets
-        first = lambda pre: min((o for n, o in self.offsets.items() if n.startswith(pre)), default=None)
-        lab0 = first("behrt_lab.")
-        head0 = min(o for n, o in self.offsets.items()
-                    if n.startswith(("demo_projector.", "lab_projector.", "text_projector.", "fusion_mlp.")))
-        layer = [first(f"behrt_demo.bert.encoder.layer.{i}.") for i in range(12)]
-        # exactly-zero gradient ranges: [query.weight, value.weight) of every demographic layer (q.w, q.b, k.w, k.b)
-        zero = []
-        for i in range(12):
-            pre = f"behrt_demo.bert.encoder.layer.{i}.attention.self."
-            lo, hi = self.offsets[pre + "query.weight"], self.offsets[pre + "value.weight"]
-            names = [n for n, o in self.offsets.items() if lo <= o < hi]
-            assert all(n.startswith((pre + "query.", pre + "key.")) for n in names), names
-            zero.append((lo, hi))
-
-        def minus_zero(lo, hi):
-            out, cur = [], lo
-            for zl, zh in zero:
-                if zh <= cur or zl >= hi:
-                    continue
-                if zl > cur:
-                    out.append((cur, zl))
-                cur = max(cur, zh)
-            if cur < hi:
-                out.append((cur, hi))
-            return out
-
-        cuts = {"head": [(head0, self.n)], "lab": [(lab0, head0)]}
-        hi = lab0
-        for i in DEMO_BUCKET_LAYERS:
-            cuts[("demo", i)] = minus_zero(layer[i], hi)
-            hi = layer[i]
-        cuts["rest"] = minus_zero(0, hi)
-        # sanity: together with the zero ranges the buckets tile [0, n) exactly
-        spans = sorted([r for v in cuts.values() for r in v] + zero)
-        assert spans[0][0] == 0 and spans[-1][1] == self.n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        cuts = plan_buckets(self.region, self.n)
         self._buckets = cuts
         return cuts
+
+    def side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.p.device, priority=-1)   # short kernels first when an SM frees
+        return self._side
+
+    def post_stream(self):
+        if getattr(self, "_post", None) is None:
+            self._post = torch.cuda.Stream(device=self.p.device, priority=-1)
+        return self._post
 
     def refresh_transposed(self):
         if self._t_table is not None:
@@ -177,8 +209,10 @@ class FlatTrainState:
             self.set_hyper(lr, weight_decay)
         self.step += 1
         self.step_dev += 1
-        self.sumsq.zero_()
-        T.grad_sumsq(self.g, self.sumsq)
+        if not getattr(self, "sumsq_valid", False):       # forward_backward already summed it bucket by bucket
+            self.sumsq.zero_()
+            T.grad_sumsq(self.g, self.sumsq)
+        self.sumsq_valid = False
         T.clip_adamw(self.p, self.g, self.m, self.v, self.sumsq, max_norm, lr, betas[0], betas[1], eps, weight_decay,
                      0, self.grad_norm, step_dev=self.step_dev, hyper_dev=self.hyper_dev, p_bf16=self.pb)
         self.refresh_transposed()
@@ -261,30 +295,44 @@ def _lin_bwd(st, wname, bname, dy_bf16, x_bf16, colsum_src=None):
     T.linear_wgrad(dy_bf16, x_bf16, st.gr(wname), accumulate=dy_bf16.shape[0] > T.SKINNY_MAX_ROWS)
 
 
-# a gradient bucket closes after each of these demographic-BERT layers (backward runs 11 -> 0); the lab tower runs its
-# backward after the demographic one, so only its own 46 MB bucket is reduced with nothing left to overlap
-DEMO_BUCKET_LAYERS = (10, 8, 6, 4, 2, 1)
+# a gradient bucket closes after each of these demographic-BERT layers (backward runs 11 -> 0, on the side stream next
+# to the lab backward): 94 MB + 113 MB that cross NVLink under the lab backward; 'tail' (71 MB) is the exposed rest
+DEMO_BUCKET_LAYERS = (7, 1)
 
 
 class _GradReducer:
-    """Bucketed SUM all-reduce of the flat gradient buffer, launched asynchronously as soon as a bucket is complete
-    so that NCCL (NVLink) overlaps the remaining backward kernels; wait() before the gradient norm / AdamW."""
+    """Per bucket, as soon as the backward has completed it: SUM all-reduce over the ranks (asynchronous, NCCL over
+    NVLink, overlapping the remaining backward kernels) and then the bucket's contribution to the squared gradient
+    norm, on a third stream that follows the collective -- so that after the last bucket only its own all-reduce and
+    13 us of norm are left before AdamW.  finish() joins everything into the current stream."""
 
     def __init__(self, st, group):
-        self.st, self.group, self.work = st, group, []
+        self.st, self.group = st, group
+        self.post = st.post_stream()
+        self.used = False
 
     def ready(self, key):
-        if self.group is None:
+        lo, hi = self.st.grad_buckets()[key]
+        if hi <= lo:
             return
-        import torch.distributed as dist
-        for lo, hi in self.st.grad_buckets()[key]:
-            if hi > lo:
-                self.work.append(dist.all_reduce(self.st.g[lo:hi], group=self.group, async_op=True))
+        cur = torch.cuda.current_stream()
+        g = self.st.g[lo:hi]
+        if self.group is not None:
+            import torch.distributed as dist
+            work = dist.all_reduce(g, group=self.group, async_op=True)
+            with torch.cuda.stream(self.post):
+                work.wait()
+                T.grad_sumsq(g, self.st.sumsq)
+        else:
+            self.post.wait_stream(cur)
+            with torch.cuda.stream(self.post):
+                T.grad_sumsq(g, self.st.sumsq)
+        self.used = True
 
-    def wait(self):
-        for w in self.work:
-            w.wait()
-        self.work = []
+    def finish(self):
+        if self.used:
+            torch.cuda.current_stream().wait_stream(self.post)
+        self.st.sumsq_valid = True
 
 
 def _demo_backward(st, model, saved, ddemo, reducer=None):
@@ -322,8 +370,6 @@ def _demo_backward(st, model, saved, ddemo, reducer=None):
                               st.gr(e + "LayerNorm.weight"), st.gr(e + "LayerNorm.bias"), want_bf16=False, want_f32=True)
     T.bert_embed_bwd(dsum, saved["ids"], st.gr(e + "word_embeddings.weight"), st.gr(e + "position_embeddings.weight"),
                      st.gr(e + "token_type_embeddings.weight")[0], 1, pad_idx=0)
-    if reducer is not None:
-        reducer.ready("rest")
 
 
 # ------------------------------------------------------------------------------------------------ lab tower
@@ -448,6 +494,12 @@ def _fusion_backward(st, fo, embs, dlogits, w_mod, lambda_l1):
     return demb
 
 
+def _lab_budget(group=None):
+    from . import _lib
+    r = RESERVED_SMS if group is None else RESERVED_SMS_DP
+    return max(2, _lib.load().fame_sm_count() - r) if r > 0 else 0
+
+
 # ------------------------------------------------------------------------------------------------ one optimisation step
 def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, group=None, want_outputs=False):
     """Forward + loss + backward for one batch; gradients land in the flat buffer.  Returns loss_out f32 [4] (device)
@@ -455,8 +507,24 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
     st = get_state(model)
     (ids, mask, age, gender, eth, ins, lab, text, labels) = batch
     st.zero_grad()
-    demo, sv_d = _demo_forward(st, model, ids, age, gender, eth, ins)
-    labe, sv_l = _lab_forward(st, model, lab)
+    st.sumsq.zero_()
+    st.post_stream().wait_stream(torch.cuda.current_stream())
+    # The two towers are independent until the fusion head.  At 32 patients the demographic tower is ~270 launches of
+    # 3-9 us (weight streaming, latency bound) and the lab tower a chain of tensor-core kernels, so they run on two
+    # streams (two branches of the captured graph) and the short kernels fill the gaps between the long ones.
+    main = torch.cuda.current_stream()
+    side = st.side_stream() if TWO_STREAMS else None
+    if side is not None:
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            demo, sv_d = _demo_forward(st, model, ids, age, gender, eth, ins)
+        ops.set_sm_budget(_lab_budget(group))
+        labe, sv_l = _lab_forward(st, model, lab)
+        ops.set_sm_budget(0)
+        main.wait_stream(side)
+    else:
+        demo, sv_d = _demo_forward(st, model, ids, age, gender, eth, ins)
+        labe, sv_l = _lab_forward(st, model, lab)
     text = text.float().contiguous()
     pk = _fusion_pack(st)
     if want_outputs:
@@ -479,16 +547,27 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
         # every rank adds lambda_l1 * sign(sig_weights) below; the gradient all-reduce is a SUM -> share it out
         lambda_l1 = lambda_l1 / dist.get_world_size(group)
     # gradient SUM over ranks, bucket by bucket as the backward completes them (sig_weights, produced here by the
-    # fusion head, lives at offset 0 and travels with the last bucket)
+    # fusion head, lives in the 'rest' region and travels with the last demographic bucket)
     red = _GradReducer(st, group)
     ddemo, dlab = _fusion_backward(st, fo, (demo, labe, text), dlogits, w_mod, lambda_l1)
-    red.ready("head")
-    # the demographic tower first: it owns 88 % of the gradient bytes and its backward at 32 patients is weight
-    # streaming (HBM / latency bound), so its buckets travel over NVLink underneath the tensor-core-bound lab backward
-    _demo_backward(st, model, sv_d, ddemo, red)
-    _lab_backward(st, model, sv_l, dlab)
-    red.ready("lab")
-    red.wait()
+    # the demographic tower owns 88 % of the gradient bytes: its buckets cross NVLink while the tensor-core-bound lab
+    # backward runs (side stream, or simply first when single-stream)
+    if side is not None:
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _demo_backward(st, model, sv_d, ddemo, red)
+        ops.set_sm_budget(_lab_budget(group))
+        _lab_backward(st, model, sv_l, dlab)
+        ops.set_sm_budget(0)
+        main.wait_stream(side)
+    else:
+        _demo_backward(st, model, sv_d, ddemo, red)
+        _lab_backward(st, model, sv_l, dlab)
+    red.ready("tail")
+    red.finish()
+    # tensors that crossed streams (allocated on one, read on the other) stay referenced until both branches have been
+    # enqueued and joined: the caching allocator may hand a freed block back to its own stream immediately
+    del sv_d, sv_l, ddemo, dlab, demo, labe
     return loss, fo
 
 

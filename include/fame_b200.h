@@ -43,6 +43,10 @@ int fame_last_cuda_error(void); /* cudaError_t of the last FAME_ERR_CUDA on this
 int fame_abi_version(void);
 int fame_device_check(void); /* FAME_OK iff the current device is compute capability 10.x */
 int fame_sm_count(void);
+/* SMs the persistent tensor-core kernels (GEMM, attention) launched AFTER this call may occupy; 0 = all.  The
+ * data-parallel training step leaves a few SMs to the latency-bound demographic-tower stream and to the NCCL
+ * all-reduce kernels that run concurrently with the lab tower.  Host-side state, not a device setting. */
+int fame_set_sm_budget(int sms);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K1  fame_gemm_bias_act:  Y[M,N] = act(X[M,K] . W[N,K]^T + bias[N]) (+ residual[M,N])

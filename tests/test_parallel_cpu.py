@@ -98,3 +98,36 @@ def test_gloo_world2_statistics_allreduce():
     assert len(ret) == world
     for r in range(world):
         assert ret[r] == (True, True, True, True), (r, ret[r])
+
+
+def test_flat_layout_and_gradient_buckets():
+    """Flat-buffer layout of the training state: the all-reduce buckets are contiguous, follow the order in which
+    the backward completes them, tile the buffer together with the never-reduced (exactly-zero gradient) region, and
+    that region holds precisely the query / key projections of the demographic BERT."""
+    from fairmultimodal_b200 import synth, train
+    shapes = synth.fame_shapes(lab_tokens=542)
+    names = [(n, int(np.prod(s))) for n, s in shapes.items() if not n.startswith(train.NO_GRAD_PREFIXES)]
+    names.sort(key=lambda x: train._layout_key(x[0]))
+    offsets, region, total = train.plan_layout(names)
+    assert total >= sum(k for _, k in names) and all(o % 8 == 0 for o in offsets.values())
+    cuts = train.plan_buckets(region, total)
+    lo, hi = region[train._R_NORED]
+    nored = [n for n, o in offsets.items() if lo <= o < hi]
+    assert len(nored) == 48 and all(".attention.self.query." in n or ".attention.self.key." in n for n in nored)
+    assert hi - lo == 12 * 2 * (768 * 768 + 768)
+    def bucket_of(name):
+        o = offsets[name]
+        return [k for k, (a, b) in cuts.items() if a <= o < b]
+    assert bucket_of("fusion_mlp.0.weight") == ["tail"] and bucket_of("text_projector.0.bias") == ["tail"]
+    assert bucket_of("behrt_lab.pos_embedding") == ["tail"]
+    assert bucket_of("sig_weights") == ["tail"] and bucket_of("behrt_demo.age_embedding.weight") == ["tail"]
+    assert bucket_of("behrt_demo.bert.encoder.layer.0.intermediate.dense.weight") == ["tail"]
+    first, second = train.DEMO_BUCKET_LAYERS
+    assert bucket_of(f"behrt_demo.bert.encoder.layer.{first}.output.dense.weight") == [("demo", first)]
+    assert bucket_of("behrt_demo.bert.encoder.layer.11.attention.self.value.weight") == [("demo", first)]
+    assert bucket_of(f"behrt_demo.bert.encoder.layer.{first - 1}.output.dense.bias") == [("demo", second)]
+    assert bucket_of(f"behrt_demo.bert.encoder.layer.{second}.attention.output.LayerNorm.weight") == [("demo", second)]
+    # buckets are listed in the order the backward closes them, each starting where the previous one ended
+    spans = list(cuts.values())
+    assert spans[0][0] == region[train._R_NORED][1] and spans[-1][1] == total
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
