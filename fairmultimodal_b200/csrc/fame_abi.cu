@@ -552,9 +552,19 @@ int fame_loss_stats(const fame_loss_stats_args* a, void*, size_t, fame_stream_t 
     for (int k = 0; k < 3; ++k) p.attr[k] = reinterpret_cast<const long long*>(a->attr[k]);
     p.stats = reinterpret_cast<long long*>(a->stats);
     p.B = a->B;
-    int grid = (a->B + 1023) / 1024;     // 256 threads x 4 patients per trip
-    if (grid > 2 * d->sm_count) grid = 2 * d->sm_count;
-    fame::loss_stats_kernel<<<grid, 256, 0, stream>>>(p);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(fame::loss_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             fame::kLsSmemBytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+        attr_set[dev] = true;
+    }
+    const int per_block = fame::kLsThreads * fame::kPatPerThread;   // patients per block per trip
+    int grid = (a->B + per_block - 1) / per_block;
+    if (grid > 4 * d->sm_count) grid = 4 * d->sm_count;             // 4 resident CTAs per SM (50 KB of bins each)
+    fame::loss_stats_kernel<<<grid, fame::kLsThreads, fame::kLsSmemBytes, stream>>>(p);
     return launch_status();
 }
 

@@ -369,75 +369,71 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 
 // (A variant that groups lanes by subgroup code with match.any / REDUX and keeps the sums in shared memory was
 // measured SLOWER at scale -- 14.7 % vs 26.5 % of the copy bandwidth at 32 M patients: the warp collectives cost more
-// than the predicated adds they replace.  At real batch sizes, 32 - 2048 patients, either is launch latency.)
-// Each thread walks patients grid-stride with private integer accumulators (predicated adds over the 8 code slots,
-// no dynamic register indexing); every kLossTripsPerFlush trips (and at the end) the warp totals go to shared
-// memory with 64-bit integer atomics, and the block totals to global memory the same way.
-__global__ void __launch_bounds__(256)
+// than the predicated adds they replace.  The variant with all 96 subgroup accumulators in registers -- predicated
+// adds over the 8 code slots -- needed 225 registers: one CTA per SM, 14.7 % of the copy bandwidth after the
+// deterministic fixed-point change.)
+// Subgroup accumulators are THREAD-PRIVATE COLUMNS OF SHARED MEMORY: bins[bin][thread], bin = outcome x attribute x
+// code (72 fixed-point sums) + attribute x code (24 counts).  The code indexes the bin directly (what registers cannot
+// do), the column index is the thread, so there are no atomics and no bank conflicts (bank = thread % 32), a patient
+// costs 12 read-modify-writes, and the kernel needs ~64 registers: 4 CTAs of 128 threads per SM with 16 patients in
+// flight per thread.  Every kLossTripsPerFlush trips (uint32 bins cannot overflow before that) and at the end, 96
+// threads add up one bin each across the 128 columns (rotated start => conflict-free) into 64-bit block totals.
+constexpr int kLsThreads = 128;
+constexpr int kLsBins = 96;
+constexpr int kLsSmemBytes = kLsBins * kLsThreads * 4 + kLossStatsLen * 8;
+
+__global__ void __launch_bounds__(kLsThreads, 4)
 loss_stats_kernel(const LossStatsParams p) {
+    extern __shared__ __align__(16) unsigned char ls_smem[];
+    unsigned (*bins)[kLsThreads] = reinterpret_cast<unsigned (*)[kLsThreads]>(ls_smem);
+    unsigned long long* sh = reinterpret_cast<unsigned long long*>(ls_smem + kLsBins * kLsThreads * 4);
+    const int tid = threadIdx.x, lane = tid & 31;
     unsigned e_sum[3] = {0u, 0u, 0u};
     unsigned long long b_sum[3] = {0ull, 0ull, 0ull};
-    unsigned g_sum[3][3][kLossSlots];
-    unsigned g_cnt[3][kLossSlots];
     unsigned n_local = 0, bad = 0;
-    auto clear = [&]() {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            e_sum[i] = 0u;
-            b_sum[i] = 0ull;
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int s = 0; s < kLossSlots; ++s) g_sum[i][a][s] = 0u;
-        }
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int s = 0; s < kLossSlots; ++s) g_cnt[a][s] = 0u;
-        n_local = 0;
-    };
-    clear();
     float pw[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) pw[i] = __ldg(p.pos_weight + i);
-
-    __shared__ unsigned long long sh[kLossStatsLen];
-    for (int i = threadIdx.x; i < kLossStatsLen; i += blockDim.x) sh[i] = 0ull;
+#pragma unroll 8
+    for (int b = 0; b < kLsBins; ++b) bins[b][tid] = 0u;
+    for (int i = tid; i < kLossStatsLen; i += kLsThreads) sh[i] = 0ull;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
+
     auto put = [&](int idx, unsigned long long v) {
         if (lane == 0 && v != 0ull) atomicAdd(&sh[idx], v);
     };
-    auto flush = [&]() {     // warp-collective: every lane of the warp calls it at the same trip
+    auto flush = [&]() {     // block-collective: the trip count is uniform over the block
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             put(i, warp_sum_u32_exact(e_sum[i]));
             put(3 + i, warp_sum_u64(b_sum[i]));
+            e_sum[i] = 0u;
+            b_sum[i] = 0ull;
         }
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int s = 0; s < kLossSlots; ++s)
-                    put(6 + (i * 3 + a) * kLossSlots + s, warp_sum_u32_exact(g_sum[i][a][s]));
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int s = 0; s < kLossSlots; ++s) put(78 + a * kLossSlots + s, __reduce_add_sync(0xffffffffu, g_cnt[a][s]));
         put(102, __reduce_add_sync(0xffffffffu, n_local));
-        clear();
+        n_local = 0;
+        __syncthreads();
+        if (tid < kLsBins) {
+            unsigned long long tot = 0ull;
+#pragma unroll 8
+            for (int j = 0; j < kLsThreads; ++j) tot += bins[tid][(j + tid) & (kLsThreads - 1)];
+            // bins 0..71 = [outcome][attr][code] sums -> stats[6 + ...]; bins 72..95 = [attr][code] counts -> stats[78 + ...]
+            if (tot != 0ull) atomicAdd(&sh[6 + tid], tot);
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int b = 0; b < kLsBins; ++b) bins[b][tid] = 0u;
     };
 
     int trips = 0;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.logits) | reinterpret_cast<uintptr_t>(p.labels) |
                           reinterpret_cast<uintptr_t>(p.attr[0]) | reinterpret_cast<uintptr_t>(p.attr[1]) |
                           reinterpret_cast<uintptr_t>(p.attr[2])) & 15) == 0;
-    const long long per_block = (long long)blockDim.x * kPatPerThread;
-    // the loop bound is uniform per block (base, not base + thread offset), so a warp never diverges around flush()
+    const long long per_block = (long long)kLsThreads * kPatPerThread;
+    // the loop bound is uniform per block (base, not base + thread offset), so the block never diverges around flush()
     for (long long base = blockIdx.x * per_block; base < p.B; base += gridDim.x * per_block) {
         PatientQuad q;
-        load_patient_quad(q, p.logits, 3, p.labels, p.attr, base + (long long)threadIdx.x * kPatPerThread, p.B, vec_ok);
+        load_patient_quad(q, p.logits, 3, p.labels, p.attr, base + (long long)tid * kPatPerThread, p.B, vec_ok);
 #pragma unroll
         for (int u = 0; u < kPatPerThread; ++u) {
             if (u < q.n) {
@@ -457,13 +453,13 @@ loss_stats_kernel(const LossStatsParams p) {
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
                     const long long c = q.code[a][u];
-                    bad |= (c < 0 || c >= kLossSlots);
+                    if (c < 0 || c >= kLossSlots) {
+                        bad = 1;
+                    } else {
+                        const int s = a * kLossSlots + (int)c;
+                        bins[72 + s][tid] += 1u;
 #pragma unroll
-                    for (int s = 0; s < kLossSlots; ++s) {
-                        const bool hit = (c == s);
-                        g_cnt[a][s] += hit;
-#pragma unroll
-                        for (int i = 0; i < 3; ++i) g_sum[i][a][s] += hit ? e[i] : 0u;
+                        for (int i = 0; i < 3; ++i) bins[i * 24 + s][tid] += e[i];
                     }
                 }
             }
@@ -476,7 +472,7 @@ loss_stats_kernel(const LossStatsParams p) {
     flush();
     put(103, __reduce_add_sync(0xffffffffu, bad));
     __syncthreads();
-    for (int i = threadIdx.x; i < kLossStatsLen; i += blockDim.x) {
+    for (int i = tid; i < kLossStatsLen; i += kLsThreads) {
         const unsigned long long v = sh[i];
         if (v != 0ull) atomicAdd(reinterpret_cast<unsigned long long*>(p.stats + i), v);
     }
