@@ -140,6 +140,8 @@ def bench_train(args, world, rank, dev, barrier):
     demo = modules.BEHRTModel_Demo(5, 2, 5, 5)
     lab = modules.BEHRTModel_Lab(TRAIN_L)
     model = modules.MultimodalTransformer_EDDI_Sigmoid(768, demo, lab, dev).to(dev)
+    if args.no_dropout:
+        modules.set_dropout(model, 0.0)
     n_batches = 4
     co = synth.make_cohort(TRAIN_B * n_batches, lab_tokens=TRAIN_L, chunks=0, with_tokens=False, seed=77 + rank)
     co["text"] = np.random.default_rng(rank).standard_normal((TRAIN_B * n_batches, 768)).astype(np.float32)
@@ -186,7 +188,8 @@ def bench_train(args, world, rank, dev, barrier):
                 "h2d_bytes_per_step": int(sum(x.numel() * x.element_size() for x in host[0])), "d2h_bytes_per_step": 16},
         "global_batch": world * TRAIN_B, "steps": args.train_steps, "params": n_params,
         "cuda_graph": bool(train.USE_CUDA_GRAPH and (group is None or train._GRAPH_WITH_COLLECTIVES)),
-        "dropout": "off (parity configuration)", "dtype": "bf16 GEMMs, fp32 master weights / optimizer",
+        "dropout": "off (parity configuration)" if args.no_dropout else
+                   "0.1 at every site of the reference's train() mode (masks from an in-kernel counter hash)", "dtype": "bf16 GEMMs, fp32 master weights / optimizer",
         "collectives": "none" if world == 1 else "all-reduce(SUM) of 104 int64 loss statistics + flat fp32 gradient buffer",
     }
 
@@ -354,6 +357,7 @@ if __name__ == "__main__":
                     help="--impl reference: chunks per step (bounded sample of the 256-chunk step)")
     ap.add_argument("--skip-train", action="store_true", help="only the note-encoder workload")
     ap.add_argument("--train-steps", type=int, default=20)
+    ap.add_argument("--no-dropout", action="store_true", help="training step with every dropout probability 0")
     ap.add_argument("--only-train", action="store_true", help="diagnostic: print only the training-step object")
     a = ap.parse_args()
     if a.impl == "reference":

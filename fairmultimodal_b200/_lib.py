@@ -20,6 +20,10 @@ class FameError(RuntimeError):
     pass
 
 
+class DropoutCfg(C.Structure):
+    _fields_ = [("step", C.c_void_p), ("seed", C.c_uint32), ("thresh16", C.c_uint32), ("group_shift", C.c_int32)]
+
+
 class GemmArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("ldx", C.c_int64),
@@ -29,7 +33,7 @@ class GemmArgs(C.Structure):
         ("y", C.c_void_p), ("ldy", C.c_int64),
         ("y_dtype", C.c_int32),
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
-        ("act", C.c_int32),
+        ("act", C.c_int32), ("drop", DropoutCfg),
     ]
 
 
@@ -60,6 +64,7 @@ class AttnFwdArgs(C.Structure):
         ("ctx", C.c_void_p), ("ld_ctx", C.c_int64),
         ("batch", C.c_int32), ("seq", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
         ("scale", C.c_float), ("algo", C.c_int32), ("lse", C.c_void_p), ("kv_len", C.c_void_p),
+        ("drop", DropoutCfg),
     ]
 
 
@@ -152,6 +157,7 @@ class GemmExArgs(C.Structure):
         ("y_dtype", C.c_int32),
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("nb0", C.c_int32), ("nb1", C.c_int32),
         ("act", C.c_int32), ("alpha", C.c_float), ("n_valid", C.c_int32), ("split_k", C.c_int32),
+        ("drop", DropoutCfg),
     ]
 
 
@@ -163,7 +169,8 @@ _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 # flat-argument entry points (backward pass / optimizer): name -> argument types, the stream is appended
 FLAT_OPS = {
     "fame_mask_kv_len": [_P, _I32, _I32, _P],
-    "fame_layernorm_bwd": [_P, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32],
+    "fame_layernorm_bwd": [_P, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P],
+    "fame_dropout_apply": [_P, _I32, _I64, _I32, _I32, _P],
     "fame_gelu_fwd": [_P, _P, _I64],
     "fame_gelu_bwd": [_P, _P, _P, _I64],
     "fame_colsum": [_P, _I32, _I64, _I32, _I32, _P],
@@ -181,7 +188,7 @@ FLAT_OPS = {
     "fame_transpose_bf16_table": [_P, _I32, _I32],
     "fame_wgrad_small": [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32],
     "fame_attn_delta": [_P, _P, _I64, _P, _I32, _I32, _I32, _I32],
-    "fame_attn_bwd_pds": [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _F],
+    "fame_attn_bwd_pds": [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _F, _P],
 }
 
 # name -> args struct for every `int fame_<op>(const args*, void* ws, size_t ws_bytes, stream)` entry point

@@ -77,7 +77,8 @@ class BertModelB200(nn.Module):
         self.config = types.SimpleNamespace(
             vocab_size=vocab_size, hidden_size=hidden_size, num_hidden_layers=num_hidden_layers,
             num_attention_heads=num_attention_heads, intermediate_size=intermediate_size,
-            max_position_embeddings=max_position_embeddings, layer_norm_eps=layer_norm_eps)
+            max_position_embeddings=max_position_embeddings, layer_norm_eps=layer_norm_eps,
+            hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)      # BertConfig defaults (training only)
         self.embeddings = _Embeddings(vocab_size, hidden_size, max_position_embeddings, layer_norm_eps)
         self.encoder = _Encoder(hidden_size, intermediate_size, num_hidden_layers, layer_norm_eps)
         self.pooler = _Dense(hidden_size, hidden_size)       # computed-but-unused in the reference; kept for keys

@@ -17,6 +17,7 @@
 //   warps 0-3     : warpgroup of even key blocks (thread = one query row)
 //   warps 4-7     : warpgroup of odd key blocks
 #pragma once
+#include "dropout.cuh"
 #include "sm100_ptx.cuh"
 #include "attn_flash_sm100.cuh"   // kFaBoxBytes, ex2_approx (via attn_sm100.cuh)
 
@@ -42,9 +43,13 @@ struct AbParams {
     int batch, seq, heads;
     int q_col0, k_col0, v_col0;   // first column of Q / K / V of head 0 inside the packed qkv tensor
     float scale, scale_log2e;
+    DropCfg drop;                 // dropout of the attention probabilities in the forward (kDrop instantiation only)
 };
 
-template <int D>
+// kDrop: the forward dropped entries of P (mask m, scale c = 1 / (1 - p)):  O = (m c P) V.  Then
+//   dV = (m c P)^T dO   -> the P written here is m c P;     dP = m c (dO V^T);
+//   dS = scale P (dP - delta),  delta = rowsum(dO * O) = sum_k P_k dP_k  still holds.
+template <int D, bool kDrop = false>
 __global__ void __launch_bounds__(kAbThreads, 1)
 attn_bwd_pds_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                     const AbParams p, const int num_items, const int qtiles) {
@@ -178,6 +183,8 @@ attn_bwd_pds_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             const long long orow = (long long)bh * S + qrow;       // row of P / dS and of lse / delta
             const float lse = row_ok ? __ldg(p.lse + orow) : INFINITY;   // +inf -> P = 0 for rows outside the sequence
             const float dl = row_ok ? __ldg(p.delta + orow) : 0.f;
+            const uint32_t drop_rs = kDrop ? drop_row_seed(drop_site_seed(p.drop), (uint32_t)orow) : 0u;
+            const float drop_inv = kDrop ? drop_inv_keep(p.drop.thresh16) : 1.0f;
             for (int j = 0; j < nblk; ++j) {
                 if (((g0 + j) & 1) != w) continue;
                 mbar_wait(&sd_full[w], fph);
@@ -204,8 +211,21 @@ attn_bwd_pds_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
                         float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2e, -lse));
                         if (kc + i >= S) p0 = 0.f;          // keys beyond the sequence (rows of the next one / padding)
                         if (kc + i + 1 >= S) p1 = 0.f;
-                        const float d0 = p.scale * p0 * (__uint_as_float(dp[i]) - dl);
-                        const float d1 = p.scale * p1 * (__uint_as_float(dp[i + 1]) - dl);
+                        float dp0 = __uint_as_float(dp[i]), dp1 = __uint_as_float(dp[i + 1]);
+                        float m0 = 1.f, m1 = 1.f;
+                        if (kDrop) {
+                            const uint32_t bits = drop_pair_bits(drop_rs, (uint32_t)(kc + i) >> 1);
+                            m0 = (bits & 0xffffu) >= p.drop.thresh16 ? drop_inv : 0.f;
+                            m1 = (bits >> 16) >= p.drop.thresh16 ? drop_inv : 0.f;
+                            dp0 *= m0;
+                            dp1 *= m1;
+                        }
+                        const float d0 = p.scale * p0 * (dp0 - dl);
+                        const float d1 = p.scale * p1 * (dp1 - dl);
+                        if (kDrop) {
+                            p0 *= m0;
+                            p1 *= m1;
+                        }
                         pk[i >> 1] = pack_bf16x2(p0, p1);
                         dk[i >> 1] = pack_bf16x2(d0, d1);
                     }

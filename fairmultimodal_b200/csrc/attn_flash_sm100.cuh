@@ -15,6 +15,7 @@
 // head_dim 96 rows (192 B) do not fit one 128-byte swizzle atom: every tile is loaded as two 64-column boxes
 // (the second box is only half used; its extra columns are never addressed by an MMA).
 #pragma once
+#include "dropout.cuh"
 #include "sm100_ptx.cuh"
 
 namespace fame {
@@ -39,6 +40,7 @@ struct FaParams {
     float scale_log2e;
     float* lse;               // optional [batch, heads, seq]: row log-sum-exp in log2 units of the scaled scores
     const int* kv_len;        // optional [batch]: 1 + last attended key (pair kernel: skips fully masked key blocks)
+    DropCfg drop;             // dropout of the attention probabilities (pair kernel, kDrop instantiation only)
 };
 
 template <int D>

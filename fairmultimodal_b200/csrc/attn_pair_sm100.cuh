@@ -51,7 +51,12 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
-template <int D>
+// kDrop: dropout of the attention probabilities (training; torch's F.multi_head_attention_forward applies
+// dropout_p to softmax(QK^T) before the product with V, and HF's sdpa path passes dropout_p the same way, HF:205).
+// The row sum l (softmax denominator) and the saved log-sum-exp use the UNDROPPED exponentials; dropped entries of P
+// are zeroed before P.V and the 1 / (1 - p) scale is folded into the final 1 / l.  Mask row = (sequence, head, query),
+// mask column = key (dropout.cuh); attn_bwd_pds_kernel<D, true> regenerates the same bits.
+template <int D, bool kDrop = false>
 __global__ void __launch_bounds__(kApThreads, 1)
 attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParams p, const int num_items,
                      const int qpairs) {
@@ -241,10 +246,12 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
         const uint32_t o_addr = lane_base + kColO + t * 128;
         const float sc = p.scale_log2e;
         uint32_t sph = 0, oph = 0;
+        const uint32_t drop_site = kDrop ? drop_site_seed(p.drop) : 0u;
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
             if (t == 1 && !t1_active(item)) continue;
             const int qp = item % qpairs, bh = item / qpairs;
             const int h = bh % p.heads, b = bh / p.heads;
+            const uint32_t drop_rs = kDrop ? drop_row_seed(drop_site, (uint32_t)(bh * S + qp * 256 + t * 128 + r)) : 0u;
             float m = -INFINITY, l = 0.f;   // running reference max (log2 units, scaled) and row sum
             const int nb_item = nblk_of(item);
             for (int j = 0; j < nb_item; ++j) {
@@ -300,8 +307,13 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
                             f32x2_fma(f32x2_pack(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
                         float x0, x1;
                         f32x2_unpack(x2, x0, x1);
-                        const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+                        float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
                         sum2 = f32x2_add(sum2, f32x2_pack(p0, p1));
+                        if (kDrop) {
+                            const uint32_t bits = drop_pair_bits(drop_rs, (uint32_t)(key0 + c * 32 + i) >> 1);
+                            p0 = (bits & 0xffffu) >= p.drop.thresh16 ? p0 : 0.f;
+                            p1 = (bits >> 16) >= p.drop.thresh16 ? p1 : 0.f;
+                        }
                         pk[i >> 1] = pack_bf16x2(p0, p1);
                     }
                     tmem_st_x16(s_addr + c * 16, pk);
@@ -337,7 +349,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
             mbar_wait(&o_full[t], oph);
             oph ^= 1;
             tc_fence_after();
-            const float inv = l > 0.f ? 1.0f / l : 0.f;
+            const float inv = (l > 0.f ? 1.0f / l : 0.f) * (kDrop ? drop_inv_keep(p.drop.thresh16) : 1.0f);
             const int qrow = qp * 256 + t * 128 + r;
             // saved for the backward pass: P = 2^(s * scale_log2e - lse); +inf for an all-masked row (P = 0)
             if (p.lse != nullptr && qrow < S)

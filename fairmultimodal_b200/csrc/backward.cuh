@@ -8,6 +8,7 @@
 
 #include "gemm_sm100.cuh"
 #include "rowwise.cuh"
+#include "dropout.cuh"
 
 namespace fame {
 
@@ -40,8 +41,13 @@ template <bool kXF32, bool kDyF32>
 __global__ void __launch_bounds__(kLnWarpsPerBlock * 32)
 layernorm_bwd_kernel(const void* __restrict__ x, const void* __restrict__ dy, const float2* __restrict__ stats,
                      const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dx_f32,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int cols) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int cols,
+                     __nv_bfloat16* __restrict__ dx_drop, const DropCfg drop) {
+    // dx_drop (optional): dx with the dropout mask of the layer that produced the residual branch re-applied
+    // (t = residual + dropout(linear(.)): the residual path takes dx, the linear layer's backward takes dx_drop)
     __shared__ float red[2][kLnWarpsPerBlock][1024 / 4];  // staged in 4 passes of 256 columns
+    const uint32_t drop_site = dx_drop != nullptr ? drop_site_seed(drop) : 0u;
+    const float drop_inv = drop_inv_keep(drop.thresh16);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = cols >> 3;
     float dg[kLnMaxChunks][8], db[kLnMaxChunks][8];
@@ -85,6 +91,16 @@ layernorm_bwd_kernel(const void* __restrict__ x, const void* __restrict__ dy, co
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] = st.y * (g[i][j] - s1 - xh[i][j] * s2);
                 store8(dx_bf16, dx_f32, (long long)row * cols + 8 * ch, o);
+                if (dx_drop != nullptr) {
+                    const uint32_t rs = drop_row_seed(drop_site, (uint32_t)row);
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const uint32_t bits = drop_pair_bits(rs, (uint32_t)(8 * ch + j) >> 1);
+                        o[j] = (bits & 0xffffu) >= drop.thresh16 ? o[j] * drop_inv : 0.f;
+                        o[j + 1] = (bits >> 16) >= drop.thresh16 ? o[j + 1] * drop_inv : 0.f;
+                    }
+                    store8(dx_drop, nullptr, (long long)row * cols + 8 * ch, o);
+                }
             }
         }
     }

@@ -136,14 +136,14 @@ static int launch_flash(const fame_attn_fwd_args* a, const CUtensorMap& tq, fame
     return launch_status();
 }
 
-template <int D>
-static int launch_pair(const fame_attn_fwd_args* a, const CUtensorMap& tq, int sm_count, fame_stream_t stream) {
+template <int D, bool kDrop>
+static int launch_pair_t(const fame_attn_fwd_args* a, const CUtensorMap& tq, int sm_count, fame_stream_t stream) {
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(fame::attn_fwd_pair_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             fame::ApCfg<D>::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(fame::attn_fwd_pair_kernel<D, kDrop>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, fame::ApCfg<D>::kSmemBytes);
         if (e != cudaSuccess) return cuda_fail(e);
         attr_set[dev] = true;
     }
@@ -160,25 +160,35 @@ static int launch_pair(const fame_attn_fwd_args* a, const CUtensorMap& tq, int s
     p.scale_log2e = a->scale * 1.4426950408889634f;
     p.lse = a->lse;
     p.kv_len = a->kv_len;
+    p.drop = drop_cfg(a->drop);
     const int qpairs = (a->seq + 255) / 256;
     const long long items = (long long)a->batch * a->heads * qpairs;
     if (items > 0x7fffffffll) return FAME_ERR_SHAPE;
     const int sms = persistent_sms(sm_count);
     const int grid = items < sms ? (int)items : sms;
-    fame::attn_fwd_pair_kernel<D><<<grid, fame::kApThreads, fame::ApCfg<D>::kSmemBytes, stream>>>(tq, p, (int)items,
-                                                                                                 qpairs);
+    fame::attn_fwd_pair_kernel<D, kDrop><<<grid, fame::kApThreads, fame::ApCfg<D>::kSmemBytes, stream>>>(
+        tq, p, (int)items, qpairs);
     return launch_status();
 }
 
-
 template <int D>
+static int launch_pair(const fame_attn_fwd_args* a, const CUtensorMap& tq, int sm_count, fame_stream_t stream) {
+    if (a->drop.thresh16 != 0) {
+        if (a->drop.thresh16 >= 65536u || a->drop.group_shift != 0) return FAME_ERR_SHAPE;
+        return launch_pair_t<D, true>(a, tq, sm_count, stream);
+    }
+    return launch_pair_t<D, false>(a, tq, sm_count, stream);
+}
+
+
+template <int D, bool kDrop>
 static int launch_attn_bwd_pds(const CUtensorMap& tq, const CUtensorMap& tdo, const fame::AbParams& p, int sm_count,
                                fame_stream_t stream) {
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(fame::attn_bwd_pds_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(fame::attn_bwd_pds_kernel<D, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              fame::AbCfg<D>::kSmemBytes);
         if (e != cudaSuccess) return cuda_fail(e);
         attr_set[dev] = true;
@@ -188,7 +198,7 @@ static int launch_attn_bwd_pds(const CUtensorMap& tq, const CUtensorMap& tdo, co
     if (items > 0x7fffffffll) return FAME_ERR_SHAPE;
     const int sms = persistent_sms(sm_count);
     const int grid = items < sms ? (int)items : sms;
-    fame::attn_bwd_pds_kernel<D><<<grid, fame::kAbThreads, fame::AbCfg<D>::kSmemBytes, stream>>>(tq, tdo, p, (int)items,
+    fame::attn_bwd_pds_kernel<D, kDrop><<<grid, fame::kAbThreads, fame::AbCfg<D>::kSmemBytes, stream>>>(tq, tdo, p, (int)items,
                                                                                                 qtiles);
     return launch_status();
 }
@@ -259,6 +269,7 @@ int fame_gemm_bias_act(const fame_gemm_args* a, void* /*workspace*/, size_t /*wo
     e.nb0 = e.nb1 = 1;
     e.act = a->act;
     e.alpha = 1.0f;
+    e.drop = a->drop;
     return gemm_ex(&e, stream);
 }
 
@@ -337,6 +348,7 @@ int fame_attn_fwd(const fame_attn_fwd_args* a, void*, size_t, fame_stream_t stre
     if (a->algo < 0 || a->algo > 3) return FAME_ERR_SHAPE;
     if (a->lse != nullptr && a->algo != 0 && a->algo != 3) return FAME_ERR_SHAPE;   // only the persistent kernel saves it
     if (a->kv_len != nullptr && a->algo != 0 && a->algo != 3) return FAME_ERR_SHAPE;
+    if (a->drop.thresh16 != 0 && a->algo != 0 && a->algo != 3) return FAME_ERR_SHAPE;
     const bool fullrow_ok = a->head_dim == fame::kAttnD && a->seq <= fame::kAttnMaxS;
     if (a->algo == 1 && !fullrow_ok) return FAME_ERR_SHAPE;
     const int64_t width = 3ll * a->heads * a->head_dim;

@@ -31,6 +31,7 @@
 //              with the next tile's MMAs (double-buffered TMEM).
 #pragma once
 #include "sm100_ptx.cuh"
+#include "dropout.cuh"
 
 namespace fame {
 
@@ -64,6 +65,7 @@ struct GemmParams {
     int split_k;                    // >= 1.  > 1: the K range is cut into split_k slices, one tile-task per slice;
     int kb_per_split;               //        f32 output only
     int atomic_out;                 // 1: tiles are ADDED to y with float4 atomics (split-K / accumulate mode)
+    DropCfg drop;                   // dropout after the activation, before the residual add (kDrop kernels only)
 };
 
 // erf-GELU (HF "gelu", modeling_bert.py:339-342):  0.5 x (1 + erf(x / sqrt 2)).
@@ -112,7 +114,8 @@ __device__ __forceinline__ void gelu_erf_x2(float& a, float& b) {
     f32x2_unpack(r, a, b);
 }
 
-template <bool kAMn, bool kBMn>
+// kDrop: a separate instantiation carries the dropout epilogue, so the inference / no-dropout kernels are unchanged.
+template <bool kAMn, bool kBMn, bool kDrop = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
@@ -254,6 +257,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int sw = r_local & 7;
         int acc = 0;
         uint32_t acc_phase = 0;
+        const uint32_t drop_site = kDrop ? drop_site_seed(p.drop) : 0u;
         for (int task = pair; task < num_tiles; task += npairs) {
             const int tile = task / p.split_k;
             const bool first_slice = (task % p.split_k) == 0;   // bias / residual are added by one slice only
@@ -303,6 +307,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 } else if (p.act == kActRelu) {
 #pragma unroll
                     for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.0f);
+                }
+                if (kDrop && p.drop.thresh16 != 0u) {
+                    // nn.Dropout on the layer output (after the activation, before the residual add)
+                    const uint32_t rs = drop_row_seed(drop_site, (uint32_t)row);
+                    const float inv = drop_inv_keep(p.drop.thresh16);
+                    if (p.drop.group_shift == 0) {
+#pragma unroll
+                        for (int j = 0; j < 64; j += 2) {
+                            const uint32_t bits = drop_pair_bits(rs, (uint32_t)(col0 + j) >> 1);
+                            v[j] = (bits & 0xffffu) >= p.drop.thresh16 ? v[j] * inv : 0.f;
+                            v[j + 1] = (bits >> 16) >= p.drop.thresh16 ? v[j + 1] * inv : 0.f;
+                        }
+                    } else {
+                        // group_shift >= 6 (host-checked): the 64 columns of this chunk (col0 % 64 == 0) share one draw
+                        const float m = drop_keep(rs, (uint32_t)col0 >> p.drop.group_shift, p.drop.thresh16) ? inv : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) v[j] *= m;
+                    }
                 }
                 if (p.res_mode != kResNone && row_ok && first_slice) {
                     const long long roff = (long long)b0 * p.rs_b0 + (long long)b1 * p.rs_b1 + (long long)row * p.ldr + col0;

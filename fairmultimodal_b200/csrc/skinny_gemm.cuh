@@ -39,6 +39,7 @@ struct SkinnyParams {
     int y_f32;
     int act;
     float alpha;
+    DropCfg drop;             // dropout after the activation, before the residual add
 };
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -118,6 +119,10 @@ skinny_gemm_kernel(const SkinnyParams p) {
     if (p.bias != nullptr) v += __ldg(p.bias + n);
     if (p.act == kActGelu) v = gelu_erf(v);
     else if (p.act == kActRelu) v = fmaxf(v, 0.f);
+    if (p.drop.thresh16 != 0u) {
+        const uint32_t rs = drop_row_seed(drop_site_seed(p.drop), (uint32_t)row);
+        v = drop_keep(rs, (uint32_t)n >> p.drop.group_shift, p.drop.thresh16) ? v * drop_inv_keep(p.drop.thresh16) : 0.f;
+    }
     if (p.res_mode == kResAddF32) {
         v += __ldg(reinterpret_cast<const float*>(p.residual) + (long long)row * p.ldr + n);
     } else if (p.res_mode == kResAddBf16) {

@@ -102,6 +102,22 @@ def _versions(params):
     return tuple((p.data_ptr(), p._version) for p in params)
 
 
+def set_dropout(model, p):
+    """Set every dropout probability of a FAME model (or one of its towers) to p -- what the parity scripts do to the
+    reference (`m.p = 0` on every nn.Dropout, `m.dropout = 0` on nn.MultiheadAttention, oracle/make_golden.py) --
+    including the BERT config entries that stand in for HF's dropout modules here."""
+    for m in model.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = p
+        if isinstance(m, nn.MultiheadAttention):
+            m.dropout = p
+        cfg = getattr(m, "config", None)
+        if cfg is not None and hasattr(cfg, "hidden_dropout_prob"):
+            cfg.hidden_dropout_prob = p
+            cfg.attention_probs_dropout_prob = p
+    return model
+
+
 class BEHRTModel_Demo(nn.Module):
     """Demographic encoder (10_FAME.py:175-206): a 12-layer BERT over a length-1 sequence (token id 0) whose CLS
     state is added to the mean of four demographic embedding rows.  Same constructor, forward signature and

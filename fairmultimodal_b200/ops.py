@@ -80,8 +80,14 @@ def _rowmajor(t: torch.Tensor, name: str) -> int:
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
 
 
-def gemm_bias_act(x, w, bias=None, residual=None, act=ACT_NONE, out=None, out_dtype=torch.bfloat16):
-    """y = act(x @ w.T + bias) (+ residual).  x [M,K] bf16, w [N,K] bf16, bias [N] f32, residual [M,N] bf16."""
+def _set_drop(dst, drop):
+    if drop is not None:
+        dst.step, dst.seed, dst.thresh16, dst.group_shift = drop.step, drop.seed, drop.thresh16, drop.group_shift
+
+
+def gemm_bias_act(x, w, bias=None, residual=None, act=ACT_NONE, out=None, out_dtype=torch.bfloat16, drop=None):
+    """y = dropout(act(x @ w.T + bias)) (+ residual).  x [M,K] bf16, w [N,K] bf16, bias [N] f32, residual [M,N] bf16
+    or f32; drop: a _lib.DropoutCfg (training) or None."""
     _cuda(x, "x", torch.bfloat16)
     _cuda(w, "w", torch.bfloat16)
     M, K = x.shape
@@ -105,6 +111,7 @@ def gemm_bias_act(x, w, bias=None, residual=None, act=ACT_NONE, out=None, out_dt
     a.y, a.ldy = out.data_ptr(), _rowmajor(out, "out")
     a.y_dtype = DT_F32 if out.dtype == torch.float32 else DT_BF16
     a.M, a.N, a.K, a.act = M, N, K, act
+    _set_drop(a.drop, drop)
     _call("fame_gemm_bias_act", a, 2.0 * M * N * K, f"{N}x{K}")
     return out
 
@@ -175,7 +182,8 @@ def mask_kv_len(key_mask):
     return out
 
 
-def attn_fwd(qkv, batch, seq, heads, head_dim, key_mask=None, scale=None, out=None, algo=0, lse=None, kv_len=None):
+def attn_fwd(qkv, batch, seq, heads, head_dim, key_mask=None, scale=None, out=None, algo=0, lse=None, kv_len=None,
+             drop=None):
     """qkv bf16 [batch*seq, 3*heads*head_dim] -> ctx bf16 [batch*seq, heads*head_dim].  lse (optional f32
     [batch, heads, seq]) receives the row log-sum-exp the backward pass needs.  kv_len (optional int32 [batch], from
     mask_kv_len(key_mask)) lets the kernel skip key blocks that hold only masked keys; the result does not change."""
@@ -202,6 +210,7 @@ def attn_fwd(qkv, batch, seq, heads, head_dim, key_mask=None, scale=None, out=No
         a.kv_len = _cuda(kv_len, "kv_len", torch.int32).data_ptr()
     else:
         a.kv_len = None
+    _set_drop(a.drop, drop)
     _call("fame_attn_fwd", a, 4.0 * batch * heads * seq * seq * head_dim)
     return out
 

@@ -1,6 +1,8 @@
 """Torch-tensor wrappers over the backward / optimizer entry points of the C ABI (see include/fame_b200.h)."""
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib, ops
@@ -29,7 +31,7 @@ def _p(t):
 
 def gemm_ex(a, b, y, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldy=None, bias=None, aux=None,
             aux_mode=AUX_NONE, ld_aux=0, act=0, alpha=1.0, nb0=1, nb1=1, sa=(0, 0), sb=(0, 0), sy=(0, 0), saux=(0, 0),
-            n_valid=0, a_off=0, b_off=0, y_off=0, aux_off=0, tag="", split_k=0):
+            n_valid=0, a_off=0, b_off=0, y_off=0, aux_off=0, tag="", split_k=0, drop=None):
     """General tcgen05 GEMM (fame_gemm_ex).  a / b / y / aux are tensors (any shape); geometry is explicit:
     leading dimensions, element offsets and batch strides (b0, b1) in elements."""
     g = _lib.GemmExArgs()
@@ -45,6 +47,7 @@ def gemm_ex(a, b, y, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldy=No
     g.ldy, g.y_stride_b0, g.y_stride_b1, g.y_dtype = ldy, sy[0], sy[1], _dt(y)
     g.M, g.N, g.K, g.nb0, g.nb1 = M, N, K, nb0, nb1
     g.act, g.alpha, g.n_valid, g.split_k = act, alpha, n_valid, split_k
+    ops._set_drop(g.drop, drop)
     ops._call("fame_gemm_ex", g, 2.0 * M * N * K * nb0 * nb1, tag)
     return y
 
@@ -52,7 +55,7 @@ def gemm_ex(a, b, y, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldy=No
 SKINNY_MAX_ROWS = 32
 
 
-def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, aux=None, aux_mode=AUX_NONE, wT=None):
+def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, aux=None, aux_mode=AUX_NONE, wT=None, alpha=1.0, drop=None):
     """dX[T, K] = dY[T, N] @ W[N, K]  (+ aux residual gradient, or ReLU-masked by aux).  With at most 32 rows and a
     transposed shadow wT [K, N] available the product runs as a K-major x K-major skinny GEMM (weight streaming)."""
     T, N = dy.shape
@@ -61,9 +64,11 @@ def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, aux=None, aux_mode=A
         out = torch.empty((T, K), device=dy.device, dtype=out_dtype)
     if wT is not None and T <= SKINNY_MAX_ROWS and N % 32 == 0:
         return gemm_ex(dy, wT, out, T, K, N, lda=dy.stride(0), ldb=wT.stride(0), ldy=out.stride(0), aux=aux,
-                       aux_mode=aux_mode, ld_aux=aux.stride(0) if aux is not None else 0, tag="dgrad")
+                       aux_mode=aux_mode, ld_aux=aux.stride(0) if aux is not None else 0, tag="dgrad", alpha=alpha,
+                       drop=drop)
     return gemm_ex(dy, w, out, T, K, N, a_mn=False, b_mn=True, lda=dy.stride(0), ldb=w.stride(0), ldy=out.stride(0),
-                   aux=aux, aux_mode=aux_mode, ld_aux=aux.stride(0) if aux is not None else 0, tag="dgrad")
+                   aux=aux, aux_mode=aux_mode, ld_aux=aux.stride(0) if aux is not None else 0, tag="dgrad", alpha=alpha,
+                   drop=drop)
 
 
 def linear_wgrad(dy, x, out, accumulate=True):
@@ -81,12 +86,29 @@ def linear_wgrad(dy, x, out, accumulate=True):
 
 
 def layernorm_bwd(x, dy, stats, gamma, dgamma, dbeta, want_bf16=True, want_f32=False):
+    return layernorm_bwd_drop(x, dy, stats, gamma, dgamma, dbeta, want_bf16, want_f32, None)[:2]
+
+
+def layernorm_bwd_drop(x, dy, stats, gamma, dgamma, dbeta, want_bf16=True, want_f32=False, drop=None):
+    """Returns (dx bf16 | None, dx f32 | None, dx_drop bf16 | None): with `drop` (a _lib.DropoutCfg) dx_drop is dx
+    with that dropout mask re-applied -- the gradient of the layer under the dropout."""
     rows, cols = x.shape
     dxb = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     dxf = torch.empty((rows, cols), device=x.device, dtype=torch.float32) if want_f32 else None
+    on = drop is not None and drop.thresh16 > 0
+    dxd = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16) if on else None
     _flat("fame_layernorm_bwd", x.data_ptr(), _dt(x), dy.data_ptr(), _dt(dy), stats.data_ptr(), gamma.data_ptr(),
-          _p(dxb), _p(dxf), _p(dgamma), _p(dbeta), rows, cols)
-    return dxb, dxf
+          _p(dxb), _p(dxf), _p(dgamma), _p(dbeta), rows, cols, _p(dxd), ctypes.addressof(drop) if on else None)
+    return dxb, dxf, dxd
+
+
+def dropout_apply(x, drop):
+    """In-place dropout of a 2-D bf16 / f32 tensor with the mask of site `drop` (no-op when thresh16 == 0)."""
+    if drop is None or drop.thresh16 == 0:
+        return x
+    rows, cols = x.shape
+    _flat("fame_dropout_apply", x.data_ptr(), _dt(x), x.stride(0), rows, cols, ctypes.addressof(drop))
+    return x
 
 
 def gelu_fwd(pre):
@@ -133,13 +155,14 @@ def attn_delta(dctx, ctx, batch, seq, heads, head_dim):
     return delta
 
 
-def attn_bwd_pds(qkv, dctx, lse, delta, batch, seq, heads, head_dim, ldp, scale):
+def attn_bwd_pds(qkv, dctx, lse, delta, batch, seq, heads, head_dim, ldp, scale, drop=None):
     """P and dS (bf16 [batch*heads*seq, ldp]) from the packed qkv, dO, the forward's lse and delta; scores stay in TMEM."""
     rows = batch * heads * seq
     p = torch.empty((rows, ldp), device=qkv.device, dtype=torch.bfloat16)
     ds = torch.empty((rows, ldp), device=qkv.device, dtype=torch.bfloat16)
     _flat("fame_attn_bwd_pds", qkv.data_ptr(), qkv.stride(0), dctx.data_ptr(), dctx.stride(0), lse.data_ptr(),
-          delta.data_ptr(), p.data_ptr(), ds.data_ptr(), ldp, batch, seq, heads, head_dim, float(scale))
+          delta.data_ptr(), p.data_ptr(), ds.data_ptr(), ldp, batch, seq, heads, head_dim, float(scale),
+          ctypes.addressof(drop) if drop is not None and drop.thresh16 > 0 else None)
     return p, ds
 
 

@@ -15,8 +15,12 @@ into it, their ``.grad`` are views into a flat gradient buffer, AdamW state is t
 feeds the tensor cores.  Parameters that receive no gradient in the reference (the three modality classifiers and
 the BERT pooler: they are not on the loss path, 10_FAME.py:444) are left out, exactly as torch skips ``grad is None``.
 
-Dropout: the reference trains with p = 0.1 everywhere; this implementation currently runs the training step with
-dropout disabled (the parity configuration of SURVEY.md 7.2).
+Dropout: as in the reference's train() mode -- BERT embedding / hidden / attention-probability dropout in the
+demographic tower (HF:111,205,297,355), dropout / dropout1 / dropout2 / attention dropout in the lab tower's
+TransformerEncoderLayers, fusion_mlp[2] -- with the probabilities read from the model (``modules.set_dropout(model, 0)``
+gives the parity configuration of SURVEY.md 7.2).  Masks come from a counter-based hash evaluated inside the kernels
+(csrc/dropout.cuh): nothing is stored, the backward regenerates them, and a device-side step counter feeds the seed
+so that CUDA-graph replays draw fresh masks.
 """
 from __future__ import annotations
 
@@ -59,6 +63,49 @@ def _layout_key(name):
     if name.startswith(("demo_projector.", "lab_projector.", "text_projector.", "fusion_mlp.")):
         return _R_HEAD
     return _R_REST
+
+
+class DropSites:
+    """Dropout sites of one training step: name -> _lib.DropoutCfg (seed per site, shared device step counter)."""
+
+    def __init__(self, model, step_dev, base_seed=0x5EED):
+        from . import _lib
+        self._lib, self.step_ptr, self.base, self.cache = _lib, step_dev.data_ptr(), base_seed, {}
+        cfg = model.behrt_demo.bert.config
+        active = model.training
+        self.p_demo_hidden = float(getattr(cfg, "hidden_dropout_prob", 0.0)) if active else 0.0
+        self.p_demo_attn = float(getattr(cfg, "attention_probs_dropout_prob", 0.0)) if active else 0.0
+        self.lab = []
+        for l in model.behrt_lab.transformer_encoder.layers:
+            self.lab.append(dict(attn=float(l.self_attn.dropout) if active else 0.0, d1=float(l.dropout1.p) if active else 0.0,
+                                 act=float(l.dropout.p) if active else 0.0, d2=float(l.dropout2.p) if active else 0.0))
+        self.p_fusion = float(model.fusion_mlp[2].p) if active else 0.0
+        self.any = active and (self.p_demo_hidden > 0 or self.p_demo_attn > 0 or self.p_fusion > 0 or
+                               any(v > 0 for d in self.lab for v in d.values()))
+
+    def key(self):
+        return (self.p_demo_hidden, self.p_demo_attn, self.p_fusion, tuple(tuple(sorted(d.items())) for d in self.lab))
+
+    def site(self, name, p, group_shift=0):
+        """DropoutCfg of site `name` (None when p == 0: the kernels then take their no-dropout instantiation)."""
+        if p <= 0.0:
+            return None
+        if not 0.0 < p < 1.0:
+            raise ValueError(f"dropout probability {p} of {name} outside (0, 1)")
+        c = self.cache.get((name, p, group_shift))
+        if c is None:
+            import zlib
+            c = self._lib.DropoutCfg()
+            c.step = self.step_ptr
+            c.seed = (zlib.crc32(name.encode()) ^ (self.base * 0x9E3779B1)) & 0xFFFFFFFF
+            c.thresh16 = max(1, min(65535, int(round(p * 65536.0))))
+            c.group_shift = group_shift
+            self.cache[(name, p, group_shift)] = c
+        return c
+
+    @staticmethod
+    def inv_keep(c):
+        return 1.0 if c is None else 65536.0 / (65536.0 - c.thresh16)
 
 
 def plan_layout(named_sizes):
@@ -246,7 +293,7 @@ def get_state(model) -> FlatTrainState:
 
 
 # ------------------------------------------------------------------------------------------------ demo tower
-def _demo_forward(st, model, ids, age, gender, eth, ins):
+def _demo_forward(st, model, ids, age, gender, eth, ins, ds=None):
     """BEHRTModel_Demo.forward for training (sequence length 1): returns (demo_emb f32 [B,768], saved)."""
     pre = "behrt_demo.bert."
     B, S = ids.shape
@@ -255,6 +302,9 @@ def _demo_forward(st, model, ids, age, gender, eth, ins):
     H = 768
     eps = model.behrt_demo.bert.config.layer_norm_eps
     dev = ids.device
+    ph = ds.p_demo_hidden if ds is not None else 0.0
+    pa = ds.p_demo_attn if ds is not None else 0.0
+    site = (lambda n, p, g=0: ds.site(n, p, g)) if ds is not None else (lambda n, p, g=0: None)
     e = pre + "embeddings."
     esum = torch.empty((B, H), device=dev, dtype=torch.float32)
     estats = torch.empty((B, 2), device=dev, dtype=torch.float32)
@@ -262,24 +312,31 @@ def _demo_forward(st, model, ids, age, gender, eth, ins):
     xb = ops.bert_embed(ids.to(torch.int64), st.f(e + "word_embeddings.weight"), st.f(e + "position_embeddings.weight"),
                         st.f(e + "token_type_embeddings.weight")[0], st.f(e + "LayerNorm.weight"),
                         st.f(e + "LayerNorm.bias"), eps, S, out_f32=x32, sum_out=esum, stats=estats)
+    d_emb = site("demo.emb", ph)
+    if d_emb is not None:                                   # BertEmbeddings.dropout (HF:111): same mask on both copies
+        T.dropout_apply(x32, d_emb)
+        T.dropout_apply(xb, d_emb)
     saved = {"esum": esum, "estats": estats, "layers": [], "ids": ids.to(torch.int64).contiguous().view(-1)}
     for i in range(12):
         p = f"{pre}encoder.layer.{i}."
         s = {"xb": xb}
-        v = ops.gemm_bias_act(xb, st.w(p + "attention.self.value.weight"), st.f(p + "attention.self.value.bias"))
+        # one key per sequence: softmax == 1, so attention-probability dropout (HF:205) keeps or drops a whole head of
+        # the value projection: one draw per (patient, head) = per 64 columns
+        v = ops.gemm_bias_act(xb, st.w(p + "attention.self.value.weight"), st.f(p + "attention.self.value.bias"),
+                              drop=site(f"demo.{i}.attn", pa, 6))
         t1 = ops.gemm_bias_act(v, st.w(p + "attention.output.dense.weight"), st.f(p + "attention.output.dense.bias"),
-                               residual=x32, out_dtype=torch.float32)
+                               residual=x32, out_dtype=torch.float32, drop=site(f"demo.{i}.h1", ph))
         st1 = torch.empty((B, 2), device=dev, dtype=torch.float32)
         x1b, x1f = ops.layernorm(t1, st.f(p + "attention.output.LayerNorm.weight"),
                                  st.f(p + "attention.output.LayerNorm.bias"), eps, want_f32=True, stats=st1)
-        pa = ops.gemm_bias_act(x1b, st.w(p + "intermediate.dense.weight"), st.f(p + "intermediate.dense.bias"))
-        h = T.gelu_fwd(pa)
+        pa_ = ops.gemm_bias_act(x1b, st.w(p + "intermediate.dense.weight"), st.f(p + "intermediate.dense.bias"))
+        h = T.gelu_fwd(pa_)
         t2 = ops.gemm_bias_act(h, st.w(p + "output.dense.weight"), st.f(p + "output.dense.bias"), residual=x1f,
-                               out_dtype=torch.float32)
+                               out_dtype=torch.float32, drop=site(f"demo.{i}.h2", ph))
         st2 = torch.empty((B, 2), device=dev, dtype=torch.float32)
         xb, x32 = ops.layernorm(t2, st.f(p + "output.LayerNorm.weight"), st.f(p + "output.LayerNorm.bias"), eps,
                                 want_f32=True, stats=st2)
-        s.update(v=v, t1=t1, st1=st1, x1b=x1b, pre=pa, h=h, t2=t2, st2=st2)
+        s.update(v=v, t1=t1, st1=st1, x1b=x1b, pre=pa_, h=h, t2=t2, st2=st2)
         saved["layers"].append(s)
     did = [age, gender, eth, ins]
     tabs = [st.f(f"behrt_demo.{n}_embedding.weight") for n in ("age", "gender", "ethnicity", "insurance")]
@@ -335,29 +392,45 @@ class _GradReducer:
         self.st.sumsq_valid = True
 
 
-def _demo_backward(st, model, saved, ddemo, reducer=None):
+def _demo_backward(st, model, saved, ddemo, reducer=None, ds=None):
     pre = "behrt_demo.bert."
+    ph = ds.p_demo_hidden if ds is not None else 0.0
+    pa = ds.p_demo_attn if ds is not None else 0.0
+    site = (lambda n, p, g=0: ds.site(n, p, g)) if ds is not None else (lambda n, p, g=0: None)
     tabs_g = [st.gr(f"behrt_demo.{n}_embedding.weight") for n in ("age", "gender", "ethnicity", "insurance")]
     T.demo_add_bwd(ddemo, saved["demo_ids"], tabs_g)
     dx = ddemo                                                      # f32 [B,768]: gradient of the last hidden state
     for i in reversed(range(12)):
         p = f"{pre}encoder.layer.{i}."
         s = saved["layers"][i]
-        dt2b, dt2f = T.layernorm_bwd(s["t2"], dx, s["st2"], st.f(p + "output.LayerNorm.weight"),
-                                     st.gr(p + "output.LayerNorm.weight"), st.gr(p + "output.LayerNorm.bias"),
-                                     want_bf16=True, want_f32=True)
-        _lin_bwd(st, p + "output.dense.weight", p + "output.dense.bias", dt2b, s["h"], colsum_src=dt2f)
-        dh = T.linear_dgrad(dt2b, st.w(p + "output.dense.weight"), wT=st.wt(p + "output.dense.weight"))
+        # t = residual + dropout(dense(.)): the residual branch takes dt (f32), the dense layer's backward the masked
+        # copy (without dropout the two coincide)
+        dt2b, dt2f, dt2m = T.layernorm_bwd_drop(s["t2"], dx, s["st2"], st.f(p + "output.LayerNorm.weight"),
+                                                st.gr(p + "output.LayerNorm.weight"), st.gr(p + "output.LayerNorm.bias"),
+                                                want_bf16=ph <= 0, want_f32=True, drop=site(f"demo.{i}.h2", ph))
+        if dt2m is None:
+            dt2m = dt2b
+            _lin_bwd(st, p + "output.dense.weight", p + "output.dense.bias", dt2m, s["h"], colsum_src=dt2f)
+        else:
+            _lin_bwd(st, p + "output.dense.weight", p + "output.dense.bias", dt2m, s["h"])
+        dh = T.linear_dgrad(dt2m, st.w(p + "output.dense.weight"), wT=st.wt(p + "output.dense.weight"))
         dpre = T.gelu_bwd(s["pre"], dh)
         _lin_bwd(st, p + "intermediate.dense.weight", p + "intermediate.dense.bias", dpre, s["x1b"])
         dx1 = T.linear_dgrad(dpre, st.w(p + "intermediate.dense.weight"), out_dtype=torch.float32, aux=dt2f,
                              aux_mode=T.AUX_ADD_F32, wT=st.wt(p + "intermediate.dense.weight"))
-        dt1b, dt1f = T.layernorm_bwd(s["t1"], dx1, s["st1"], st.f(p + "attention.output.LayerNorm.weight"),
-                                     st.gr(p + "attention.output.LayerNorm.weight"),
-                                     st.gr(p + "attention.output.LayerNorm.bias"), want_bf16=True, want_f32=True)
-        _lin_bwd(st, p + "attention.output.dense.weight", p + "attention.output.dense.bias", dt1b, s["v"], colsum_src=dt1f)
-        dv = T.linear_dgrad(dt1b, st.w(p + "attention.output.dense.weight"),
-                            wT=st.wt(p + "attention.output.dense.weight"))
+        dt1b, dt1f, dt1m = T.layernorm_bwd_drop(s["t1"], dx1, s["st1"], st.f(p + "attention.output.LayerNorm.weight"),
+                                                st.gr(p + "attention.output.LayerNorm.weight"),
+                                                st.gr(p + "attention.output.LayerNorm.bias"), want_bf16=ph <= 0,
+                                                want_f32=True, drop=site(f"demo.{i}.h1", ph))
+        if dt1m is None:
+            dt1m = dt1b
+            _lin_bwd(st, p + "attention.output.dense.weight", p + "attention.output.dense.bias", dt1m, s["v"],
+                     colsum_src=dt1f)
+        else:
+            _lin_bwd(st, p + "attention.output.dense.weight", p + "attention.output.dense.bias", dt1m, s["v"])
+        # s["v"] is the context = head-dropped value projection; its gradient passes the same per-head mask
+        dv = T.linear_dgrad(dt1m, st.w(p + "attention.output.dense.weight"),
+                            wT=st.wt(p + "attention.output.dense.weight"), drop=site(f"demo.{i}.attn", pa, 6))
         _lin_bwd(st, p + "attention.self.value.weight", p + "attention.self.value.bias", dv, s["xb"])
         # one key per sequence: softmax == 1, so query / key receive exactly zero gradient (their .grad stays 0 and
         # AdamW still applies weight decay to them, as in the reference)
@@ -366,6 +439,7 @@ def _demo_backward(st, model, saved, ddemo, reducer=None):
         if reducer is not None and i in DEMO_BUCKET_LAYERS:
             reducer.ready(("demo", i))
     e = pre + "embeddings."
+    T.dropout_apply(dx, site("demo.emb", ph))                       # BertEmbeddings.dropout backward (no-op when off)
     _, dsum = T.layernorm_bwd(saved["esum"], dx, saved["estats"], st.f(e + "LayerNorm.weight"),
                               st.gr(e + "LayerNorm.weight"), st.gr(e + "LayerNorm.bias"), want_bf16=False, want_f32=True)
     T.bert_embed_bwd(dsum, saved["ids"], st.gr(e + "word_embeddings.weight"), st.gr(e + "position_embeddings.weight"),
@@ -373,7 +447,7 @@ def _demo_backward(st, model, saved, ddemo, reducer=None):
 
 
 # ------------------------------------------------------------------------------------------------ lab tower
-def _lab_forward(st, model, lab):
+def _lab_forward(st, model, lab, ds=None):
     pre = "behrt_lab."
     B, L = lab.shape
     H, nh = 768, model.behrt_lab.nhead
@@ -384,15 +458,21 @@ def _lab_forward(st, model, lab):
     dev = lab.device
     for i, layer in enumerate(model.behrt_lab.transformer_encoder.layers):
         p = f"{pre}transformer_encoder.layers.{i}."
+        pr = ds.lab[i] if ds is not None else dict(attn=0.0, d1=0.0, act=0.0, d2=0.0)
+        site = (lambda n, q: ds.site(f"lab.{i}.{n}", q)) if ds is not None else (lambda n, q: None)
         s = {"x": x}
         qkv = ops.gemm_bias_act(x, st.w(p + "self_attn.in_proj_weight"), st.f(p + "self_attn.in_proj_bias"))
         lse = torch.empty((B, nh, L), device=dev, dtype=torch.float32)       # saved for the attention backward
-        ctx = ops.attn_fwd(qkv, B, L, nh, H // nh, lse=lse)
-        t1 = ops.gemm_bias_act(ctx, st.w(p + "self_attn.out_proj.weight"), st.f(p + "self_attn.out_proj.bias"), residual=x)
+        ctx = ops.attn_fwd(qkv, B, L, nh, H // nh, lse=lse, drop=site("attn", pr["attn"]))
+        # x = norm1(x + dropout1(out_proj(ctx)));  x = norm2(x + dropout2(linear2(dropout(relu(linear1(x))))))
+        t1 = ops.gemm_bias_act(ctx, st.w(p + "self_attn.out_proj.weight"), st.f(p + "self_attn.out_proj.bias"), residual=x,
+                               drop=site("d1", pr["d1"]))
         st1 = torch.empty((B * L, 2), device=dev, dtype=torch.float32)
         x1 = ops.layernorm(t1, st.f(p + "norm1.weight"), st.f(p + "norm1.bias"), layer.norm1.eps, stats=st1)
-        h = ops.gemm_bias_act(x1, st.w(p + "linear1.weight"), st.f(p + "linear1.bias"), act=ops.ACT_RELU)
-        t2 = ops.gemm_bias_act(h, st.w(p + "linear2.weight"), st.f(p + "linear2.bias"), residual=x1)
+        h = ops.gemm_bias_act(x1, st.w(p + "linear1.weight"), st.f(p + "linear1.bias"), act=ops.ACT_RELU,
+                              drop=site("act", pr["act"]))
+        t2 = ops.gemm_bias_act(h, st.w(p + "linear2.weight"), st.f(p + "linear2.bias"), residual=x1,
+                               drop=site("d2", pr["d2"]))
         st2 = torch.empty((B * L, 2), device=dev, dtype=torch.float32)
         x = ops.layernorm(t2, st.f(p + "norm2.weight"), st.f(p + "norm2.bias"), layer.norm2.eps, stats=st2)
         s.update(qkv=qkv, ctx=ctx, lse=lse, t1=t1, st1=st1, x1=x1, h=h, t2=t2, st2=st2)
@@ -400,10 +480,11 @@ def _lab_forward(st, model, lab):
     return ops.seq_mean(x, B, L), saved
 
 
-def _attn_backward(qkv, dctx, ctx, lse, B, L, nh, D):
+def _attn_backward(qkv, dctx, ctx, lse, B, L, nh, D, drop=None):
     """dqkv [T, 3*nh*D] bf16 from dctx [T, nh*D]: P and dS come out of one kernel that keeps both score products
-    (Q K^T and dO V^T) in TMEM and recomputes the softmax from the forward's row log-sum-exp; three batched tensor-core
-    products turn them into dV, dK, dQ."""
+    (Q K^T and dO V^T) in TMEM and recomputes the softmax from the forward's row log-sum-exp (and, in training with
+    attention dropout, the forward's mask from its seed); three batched tensor-core products turn them into dV, dK,
+    dQ."""
     dev = qkv.device
     W = 3 * nh * D
     HD = nh * D
@@ -412,7 +493,7 @@ def _attn_backward(qkv, dctx, ctx, lse, B, L, nh, D):
     sc = (L * HD, D)                # same inside ctx / dctx
     ss = (nh * L * ldp, L * ldp)    # inside the [B, nh, L, ldp] probability / score-gradient tensors
     delta = T.attn_delta(dctx, ctx, B, L, nh, D)
-    p, ds = T.attn_bwd_pds(qkv, dctx, lse, delta, B, L, nh, D, ldp, D ** -0.5)
+    p, ds = T.attn_bwd_pds(qkv, dctx, lse, delta, B, L, nh, D, ldp, D ** -0.5, drop=drop)
     dqkv = torch.empty((B * L, W), device=dev, dtype=torch.bfloat16)
     # dV = P^T dO, dK = dS^T Q  (A MN-major: stored [query rows, key cols]; B MN-major: stored [query rows, d cols])
     T.gemm_ex(p, dctx, dqkv, L, D, L, a_mn=True, b_mn=True, lda=ldp, ldb=HD, ldy=W, nb0=B, nb1=nh, sa=ss, sb=sc, sy=sq,
@@ -425,7 +506,7 @@ def _attn_backward(qkv, dctx, ctx, lse, B, L, nh, D):
     return dqkv
 
 
-def _lab_backward(st, model, saved, dlab):
+def _lab_backward(st, model, saved, dlab, ds=None):
     pre = "behrt_lab."
     lab = saved["lab"]
     B, L = lab.shape
@@ -433,18 +514,26 @@ def _lab_backward(st, model, saved, dlab):
     dx = T.seq_mean_bwd(dlab, B, L)                                  # bf16 [B*L, 768]
     for i in reversed(range(len(saved["layers"]))):
         p = f"{pre}transformer_encoder.layers.{i}."
+        pr = ds.lab[i] if ds is not None else dict(attn=0.0, d1=0.0, act=0.0, d2=0.0)
+        site = (lambda n, q: ds.site(f"lab.{i}.{n}", q)) if ds is not None else (lambda n, q: None)
         s = saved["layers"][i]
-        dt2, _ = T.layernorm_bwd(s["t2"], dx, s["st2"], st.f(p + "norm2.weight"), st.gr(p + "norm2.weight"),
-                                 st.gr(p + "norm2.bias"))
-        _lin_bwd(st, p + "linear2.weight", p + "linear2.bias", dt2, s["h"])
-        dh = T.linear_dgrad(dt2, st.w(p + "linear2.weight"), aux=s["h"], aux_mode=T.AUX_RELU_MASK_BF16)
+        # dt2: gradient of t2 = x1 + dropout2(linear2(h)) -> residual branch; dt2m (masked) -> linear2
+        dt2, _, dt2m = T.layernorm_bwd_drop(s["t2"], dx, s["st2"], st.f(p + "norm2.weight"), st.gr(p + "norm2.weight"),
+                                            st.gr(p + "norm2.bias"), drop=site("d2", pr["d2"]))
+        dt2m = dt2 if dt2m is None else dt2m
+        _lin_bwd(st, p + "linear2.weight", p + "linear2.bias", dt2m, s["h"])
+        # s["h"] = dropout(relu(.)) is zero exactly where ReLU or the dropout zeroed it; the kept entries carry 1/(1-p)
+        d_act = site("act", pr["act"])
+        dh = T.linear_dgrad(dt2m, st.w(p + "linear2.weight"), aux=s["h"], aux_mode=T.AUX_RELU_MASK_BF16,
+                            alpha=DropSites.inv_keep(d_act))
         _lin_bwd(st, p + "linear1.weight", p + "linear1.bias", dh, s["x1"])
         dx1 = T.linear_dgrad(dh, st.w(p + "linear1.weight"), aux=dt2, aux_mode=T.AUX_ADD_BF16)
-        dt1, _ = T.layernorm_bwd(s["t1"], dx1, s["st1"], st.f(p + "norm1.weight"), st.gr(p + "norm1.weight"),
-                                 st.gr(p + "norm1.bias"))
-        _lin_bwd(st, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", dt1, s["ctx"])
-        dctx = T.linear_dgrad(dt1, st.w(p + "self_attn.out_proj.weight"))
-        dqkv = _attn_backward(s["qkv"], dctx, s["ctx"], s["lse"], B, L, nh, H // nh)
+        dt1, _, dt1m = T.layernorm_bwd_drop(s["t1"], dx1, s["st1"], st.f(p + "norm1.weight"), st.gr(p + "norm1.weight"),
+                                            st.gr(p + "norm1.bias"), drop=site("d1", pr["d1"]))
+        dt1m = dt1 if dt1m is None else dt1m
+        _lin_bwd(st, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", dt1m, s["ctx"])
+        dctx = T.linear_dgrad(dt1m, st.w(p + "self_attn.out_proj.weight"))
+        dqkv = _attn_backward(s["qkv"], dctx, s["ctx"], s["lse"], B, L, nh, H // nh, drop=site("attn", pr["attn"]))
         _lin_bwd(st, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", dqkv, s["x"])
         dx = T.linear_dgrad(dqkv, st.w(p + "self_attn.in_proj_weight"), aux=dt1, aux_mode=T.AUX_ADD_BF16)
     # token embedding: Linear(1, 768).weight has shape [768, 1] -> its gradient is the [768] vector
@@ -465,16 +554,17 @@ def _fusion_pack(st):
         b4=f("fusion_mlp.3.bias"))
 
 
-def _fusion_backward(st, fo, embs, dlogits, w_mod, lambda_l1):
+def _fusion_backward(st, fo, embs, dlogits, w_mod, lambda_l1, d_fus=None):
     """Returns (d demo_emb, d lab_emb) f32 [B,768]; writes every head gradient into the flat buffer."""
     B = dlogits.shape[0]
     dev = dlogits.device
     f, g = st.f, st.gr
-    hid = torch.relu(fo["pre_relu"])                                           # [B,512]
+    hid = fo["hid_drop"] if d_fus is not None else torch.relu(fo["pre_relu"])  # [B,512] input of fusion_mlp[3]
     # fusion_mlp.3: dW4[3,512] = dlogits^T hid ; db4 = colsum(dlogits)
     T.sgemm(dlogits, 1, 3, hid, 512, 1, g("fusion_mlp.3.weight"), 3, 512, B)
     T.colsum(dlogits, g("fusion_mlp.3.bias"))
     dhid = T.fusion_bwd_hidden(dlogits, f("fusion_mlp.3.weight"), fo["pre_relu"])
+    T.dropout_apply(dhid, d_fus)                                               # fusion_mlp[2] backward (no-op when off)
     # fusion_mlp.0: dW3[512,768] = dhid^T gated ; db3 ; dgated[B,768] = dhid W3
     T.sgemm(dhid, 1, 512, fo["gated"], 768, 1, g("fusion_mlp.0.weight"), 512, 768, B)
     T.colsum(dhid, g("fusion_mlp.0.bias"))
@@ -509,6 +599,9 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
     st.zero_grad()
     st.sumsq.zero_()
     st.post_stream().wait_stream(torch.cuda.current_stream())
+    ds = DropSites(model, st.step_dev)
+    if not ds.any:
+        ds = None                                                             # parity configuration / eval: no site active
     # The two towers are independent until the fusion head.  At 32 patients the demographic tower is ~270 launches of
     # 3-9 us (weight streaming, latency bound) and the lab tower a chain of tensor-core kernels, so they run on two
     # streams (two branches of the captured graph) and the short kernels fill the gaps between the long ones.
@@ -517,14 +610,14 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
     if side is not None:
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            demo, sv_d = _demo_forward(st, model, ids, age, gender, eth, ins)
+            demo, sv_d = _demo_forward(st, model, ids, age, gender, eth, ins, ds)
         ops.set_sm_budget(_lab_budget(group))
-        labe, sv_l = _lab_forward(st, model, lab)
+        labe, sv_l = _lab_forward(st, model, lab, ds)
         ops.set_sm_budget(0)
         main.wait_stream(side)
     else:
-        demo, sv_d = _demo_forward(st, model, ids, age, gender, eth, ins)
-        labe, sv_l = _lab_forward(st, model, lab)
+        demo, sv_d = _demo_forward(st, model, ids, age, gender, eth, ins, ds)
+        labe, sv_l = _lab_forward(st, model, lab, ds)
     text = text.float().contiguous()
     pk = _fusion_pack(st)
     if want_outputs:
@@ -534,6 +627,14 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
     else:
         pk["wc"] = pk["bc"] = pk["b4"]                                        # unused (mod_logits not requested)
     fo = ops.fusion_fwd((demo, labe, text), pk, w_mod, want_mod_logits=want_outputs, want_intermediates=True)
+    d_fus = ds.site("fusion.hidden", ds.p_fusion) if ds is not None else None
+    if d_fus is not None:
+        # fusion_mlp = Linear, ReLU, Dropout, Linear (10_FAME.py:255): the fused kernel's logits skip the dropout, so
+        # the last layer is redone on the dropped hidden activations (three small launches, training only)
+        hid = T.dropout_apply(torch.relu(fo["pre_relu"]), d_fus)
+        logits = pk["b4"].repeat(hid.shape[0], 1)
+        T.sgemm(hid, 512, 1, pk["w4"], 1, 512, logits, hid.shape[0], 3, 512, accumulate=True)
+        fo["hid_drop"], fo["logits"] = hid, logits
     labels = labels.float().contiguous()
     attrs = [batch[i].to(torch.int64).contiguous() for i in ATTR_IDX]
     stats = ops.loss_stats(fo["logits"], labels, attrs, pos_weight)
@@ -549,20 +650,20 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
     # gradient SUM over ranks, bucket by bucket as the backward completes them (sig_weights, produced here by the
     # fusion head, lives in the 'rest' region and travels with the last demographic bucket)
     red = _GradReducer(st, group)
-    ddemo, dlab = _fusion_backward(st, fo, (demo, labe, text), dlogits, w_mod, lambda_l1)
+    ddemo, dlab = _fusion_backward(st, fo, (demo, labe, text), dlogits, w_mod, lambda_l1, d_fus)
     # the demographic tower owns 88 % of the gradient bytes: its buckets cross NVLink while the tensor-core-bound lab
     # backward runs (side stream, or simply first when single-stream)
     if side is not None:
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            _demo_backward(st, model, sv_d, ddemo, red)
+            _demo_backward(st, model, sv_d, ddemo, red, ds)
         ops.set_sm_budget(_lab_budget(group))
-        _lab_backward(st, model, sv_l, dlab)
+        _lab_backward(st, model, sv_l, dlab, ds)
         ops.set_sm_budget(0)
         main.wait_stream(side)
     else:
-        _demo_backward(st, model, sv_d, ddemo, red)
-        _lab_backward(st, model, sv_l, dlab)
+        _demo_backward(st, model, sv_d, ddemo, red, ds)
+        _lab_backward(st, model, sv_l, dlab, ds)
     red.ready("tail")
     red.finish()
     # tensors that crossed streams (allocated on one, read on the other) stay referenced until both branches have been
@@ -625,7 +726,7 @@ def optimisation_step(model, batch, pw, lambda_edd, lambda_l1, w_mod, hp, group=
     if not use_graph:
         return eager(batch)
     key = (tuple((tuple(x.shape), x.dtype) for x in batch), tuple(w_mod), lambda_edd, lambda_l1, hp["betas"], hp["eps"],
-           pw.data_ptr(), group is not None)
+           pw.data_ptr(), group is not None, DropSites(model, st.step_dev).key())
     entry = st.graphs.get(key)
     if entry is None:
         st.graphs[key] = {"graph": None}

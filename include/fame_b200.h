@@ -49,6 +49,22 @@ int fame_sm_count(void);
 int fame_set_sm_budget(int sms);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Dropout of the training step (train() mode of the reference: HF hidden_dropout_prob / attention_probs_dropout_prob,
+ * HF:111,205,297,355; nn.TransformerEncoderLayer dropout / dropout1 / dropout2 / self_attn.dropout, 10_FAME.py:214;
+ * fusion_mlp[2], 10_FAME.py:255).  Masks are never stored: every kernel that applies a site's mask in the forward
+ * pass or needs it again in the backward pass evaluates the same counter-based hash of (seed, *step, row, column),
+ * fairmultimodal_b200/csrc/dropout.cuh.  Kept values are scaled by 65536 / (65536 - thresh16).  torch's Philox
+ * stream is not reproducible by another implementation; the distribution (independent Bernoulli keeps) is. */
+typedef struct {
+    const int32_t* step;  /* device memory: step counter mixed into the seed at run time, so that replays of a captured
+                             CUDA graph draw fresh masks; may be NULL (= 0) */
+    uint32_t seed;        /* seed of this dropout site */
+    uint32_t thresh16;    /* round(p * 65536); 0 = no dropout (all other fields ignored) */
+    int32_t group_shift;  /* 2^group_shift consecutive columns share one draw (0 = per element; 6 = one draw per
+                             64-wide attention head: dropout of a length-1 softmax, HF:205) */
+} fame_dropout_cfg;
+
+/* ------------------------------------------------------------------------------------------------------------
  * K1  fame_gemm_bias_act:  Y[M,N] = act(X[M,K] . W[N,K]^T + bias[N]) (+ residual[M,N])
  * X, W, residual: bf16 row-major; bias: f32; Y: bf16 or f32.  tcgen05 + TMEM + TMA.
  * Replaces nn.Linear: HF:179-181 (Q/K/V), HF:295 (attention output dense), HF:340 (intermediate dense + GELU),
@@ -68,6 +84,7 @@ typedef struct {
     int32_t y_dtype; /* FAME_DT_* */
     int32_t M, N, K;
     int32_t act; /* FAME_ACT_* */
+    fame_dropout_cfg drop; /* dropout of act(X W^T + bias) BEFORE the residual add; thresh16 = 0: none */
 } fame_gemm_args;
 int fame_gemm_bias_act(const fame_gemm_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
 
@@ -104,6 +121,8 @@ typedef struct {
                         gradient buffer) += result through float4 atomics, with the contraction cut into n slices
                         (n > 0) or into as many as fill the SMs (-1).  Used by the weight-gradient products, whose
                         contraction runs over all tokens while the output has only a few tiles. */
+    fame_dropout_cfg drop; /* dropout of the result (after alpha / bias / act, before an additive aux); K-major A,
+                              unbatched, split_k = 0 only.  thresh16 = 0: none */
 } fame_gemm_ex_args;
 int fame_gemm_ex(const fame_gemm_ex_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
 
@@ -172,6 +191,8 @@ typedef struct {
                      sequence.  Key blocks (128 keys) that lie entirely beyond it hold only masked keys (probability
                      exactly 0) and are not loaded, multiplied or exponentiated; results are identical with and
                      without it.  algo 0 / 3 only; may be NULL */
+    fame_dropout_cfg drop; /* dropout of the attention probabilities (training): mask row = (sequence, head, query),
+                     column = key; thresh16 = 0: none.  algo 0 / 3 only */
 } fame_attn_fwd_args;
 int fame_attn_fwd(const fame_attn_fwd_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
 
@@ -355,10 +376,17 @@ int fame_sigmoid_probs(const fame_sigmoid_probs_args* a, void* workspace, size_t
  * flat argument lists (device pointers, sizes, scalars) and are asynchronous on `stream` like everything else.
  * ============================================================================================================ */
 
-/* LayerNorm backward from the saved {mean, rstd}: dx (bf16 and/or f32), dgamma/dbeta ACCUMULATED with f32 atomics. */
+/* LayerNorm backward from the saved {mean, rstd}: dx (bf16 and/or f32), dgamma/dbeta ACCUMULATED with f32 atomics.
+ * dx_drop (bf16, optional): dx with the per-element dropout mask `drop` re-applied -- the gradient of the linear layer
+ * inside  t = residual + dropout(linear(.))  (the residual branch takes the unmasked dx); NULL when the site has no
+ * dropout. */
 int fame_layernorm_bwd(const void* x, int32_t x_dtype, const void* dy, int32_t dy_dtype, const float* stats,
                        const float* gamma, void* dx_bf16, float* dx_f32, float* dgamma, float* dbeta, int32_t rows,
-                       int32_t cols, fame_stream_t stream);
+                       int32_t cols, void* dx_drop, const fame_dropout_cfg* drop, fame_stream_t stream);
+/* In-place dropout of x [rows, cols] (bf16 or f32, row stride ld): the sites with no producing GEMM epilogue
+ * (BertEmbeddings dropout HF:111, fusion_mlp[2] 10_FAME.py:255) and their gradients. */
+int fame_dropout_apply(void* x, int32_t x_dtype, int64_t ld, int32_t rows, int32_t cols, const fame_dropout_cfg* drop,
+                       fame_stream_t stream);
 /* erf-GELU forward on a saved bf16 pre-activation and its backward dpre = dh * gelu'(pre); n % 8 == 0. */
 int fame_gelu_fwd(const void* pre, void* h, int64_t n, fame_stream_t stream);
 int fame_gelu_bwd(const void* pre, const void* dh, void* dpre, int64_t n, fame_stream_t stream);
@@ -414,7 +442,8 @@ int fame_attn_delta(const void* dctx, const void* ctx, int64_t ld, float* delta,
                     int32_t heads, int32_t head_dim, fame_stream_t stream);
 int fame_attn_bwd_pds(const void* qkv, int64_t ld_qkv, const void* dctx, int64_t ld_dctx, const float* lse,
                       const float* delta, void* p, void* ds, int64_t ldp, int32_t batch, int32_t seq, int32_t heads,
-                      int32_t head_dim, float scale, fame_stream_t stream);
+                      int32_t head_dim, float scale, const fame_dropout_cfg* drop /* the forward's, or NULL */,
+                      fame_stream_t stream);
 int fame_transpose_bf16_table(const void* table, int32_t n_entries, int32_t total_tiles, fame_stream_t stream);
 
 #ifdef __cplusplus

@@ -23,6 +23,9 @@ keys = ("demo_dummy_ids", "demo_attn_mask", "age_ids", "gender_ids", "ethnicity_
         "text", "labels")
 batch = [torch.from_numpy(co[k]).cuda() for k in keys]
 pw = torch.from_numpy(synth.pos_weight(co["labels"])).cuda()
+if os.environ.get("FAME_DROPOUT", "1") == "0":
+    modules.set_dropout(model, 0.0)
+print("dropout:", "off (parity configuration)" if os.environ.get("FAME_DROPOUT", "1") == "0" else "0.1 (reference train() mode)")
 model.train()
 st = train.get_state(model)
 w = (0.33, 0.33, 0.33)

@@ -13,7 +13,7 @@ w0 = {k: torch.from_numpy(v) for k, v in synth.synth_state_dict(synth.fame_shape
 hp = dict(lr=0.0, weight_decay=0.01, betas=(0.9, 0.999), eps=1e-8)
 def run():
     m = modules.MultimodalTransformer_EDDI_Sigmoid(768, modules.BEHRTModel_Demo(5, 2, 5, 5), modules.BEHRTModel_Lab(L), "cuda")
-    m.load_state_dict(w0); m = m.cuda().train()
+    m.load_state_dict(w0); modules.set_dropout(m, 0.0); m = m.cuda().train()
     st = train.get_state(m)
     out = []
     for b in batches:

@@ -19,7 +19,7 @@ for (L, B) in ((24, 8), (542, 32), (40, 5)):
     pw = torch.tensor([3.0, 1.2, 0.6]).cuda()
     w0 = {k: torch.from_numpy(v) for k, v in synth.synth_state_dict(synth.fame_shapes(lab_tokens=L), 12).items()}
     m = modules.MultimodalTransformer_EDDI_Sigmoid(768, modules.BEHRTModel_Demo(5, 2, 5, 5), modules.BEHRTModel_Lab(L), "cuda")
-    m.load_state_dict(w0); m = m.cuda().train()
+    m.load_state_dict(w0); modules.set_dropout(m, 0.0); m = m.cuda().train()
     st = train.get_state(m)
     gs = []
     for rep in range(4):

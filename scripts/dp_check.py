@@ -31,6 +31,7 @@ def build():
     m = modules.MultimodalTransformer_EDDI_Sigmoid(768, modules.BEHRTModel_Demo(5, 2, 5, 5), modules.BEHRTModel_Lab(L), dev)
     sd = {k: torch.from_numpy(v) for k, v in synth.synth_state_dict(synth.fame_shapes(lab_tokens=L), 4).items()}
     m.load_state_dict(sd)
+    modules.set_dropout(m, 0.0)      # parity check: N ranks == one process is only defined without random masks
     return m.to(dev).train()
 
 

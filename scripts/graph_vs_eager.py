@@ -25,6 +25,7 @@ def run(graph):
     lab = modules.BEHRTModel_Lab(L)
     model = modules.MultimodalTransformer_EDDI_Sigmoid(768, demo, lab, "cuda")
     model.load_state_dict(w0)
+    modules.set_dropout(model, 0.0)
     model = model.cuda()
     crit = torch.nn.BCEWithLogitsLoss(pos_weight=pw.cuda())
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)

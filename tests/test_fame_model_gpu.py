@@ -32,6 +32,7 @@ def _build_model(L, seed):
     assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in sd)
     w = {k: torch.from_numpy(v) for k, v in synth.synth_state_dict(shapes, seed).items()}
     model.load_state_dict(w, strict=True)
+    modules.set_dropout(model, 0.0)          # parity configuration (the golden vectors were made with dropout off)
     return model.cuda(), w
 
 

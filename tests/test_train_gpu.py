@@ -25,6 +25,7 @@ def _model(L, seed):
     model = modules.MultimodalTransformer_EDDI_Sigmoid(768, demo, lab, "cuda", fusion_hidden=512, beta=1.0)
     w = {k: torch.from_numpy(v) for k, v in synth.synth_state_dict(synth.fame_shapes(lab_tokens=L), seed).items()}
     model.load_state_dict(w, strict=True)
+    modules.set_dropout(model, 0.0)          # parity configuration (the golden vectors were made with dropout off)
     return model.cuda(), w
 
 
@@ -349,3 +350,144 @@ def test_fusion_head_backward_isolated():
               "fusion_mlp.3.weight", "fusion_mlp.3.bias"):
         ref, got = sd[k].grad, st.gr(k).cpu()
         assert (got - ref).abs().max() <= 1e-4 * ref.abs().max() + 1e-9, k
+
+
+# ------------------------------------------------------------------------------------------------ dropout (training)
+def _drop_cfg(name, p, step=None, shift=0):
+    from fairmultimodal_b200 import _lib
+    c = _lib.DropoutCfg()
+    c.step = step.data_ptr() if step is not None else None
+    c.seed, c.thresh16, c.group_shift = hash(name) & 0xFFFFFFFF, int(round(p * 65536)), shift
+    return c
+
+
+def test_dropout_mask_statistics_and_consistency():
+    """The mask is a pure function of (seed, step, row, column): the GEMM epilogue (tensor-core and skinny kernels), the
+    LayerNorm backward and the stand-alone kernel produce the SAME mask; keep rate = 1 - p; kept values scaled by
+    1 / (1 - p); a different step or seed gives a different mask; per-head groups share one draw."""
+    from fairmultimodal_b200 import ops, ops_train as T
+    torch.manual_seed(0)
+    p = 0.1
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    c = _drop_cfg("site", p, step)
+    for M in (1000, 32):                                     # tcgen05 kernel / weight-streaming kernel
+        N, K = 768, 256
+        x = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+        w = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+        b = torch.randn(N, device="cuda")
+        res = torch.randn(M, N, device="cuda").bfloat16()
+        plain = ops.gemm_bias_act(x, w, b, out_dtype=torch.float32)
+        dropped = ops.gemm_bias_act(x, w, b, out_dtype=torch.float32, drop=c)
+        ones = torch.ones(M, N, device="cuda")
+        mask = T.dropout_apply(ones.clone(), c)              # stand-alone kernel: 0 or 1 / (1 - p)
+        keep = mask > 0
+        assert abs(keep.float().mean().item() - (1 - p)) < (0.01 if M >= 1000 else 0.03)
+        assert torch.allclose(mask[keep], torch.full_like(mask[keep], 65536.0 / (65536 - c.thresh16)))
+        assert torch.allclose(dropped, plain * mask, rtol=1e-6, atol=1e-6)          # same mask in the epilogue
+        with_res = ops.gemm_bias_act(x, w, b, residual=res, out_dtype=torch.float32, drop=c)
+        assert torch.allclose(with_res, plain * mask + res.float(), rtol=1e-5, atol=1e-5)   # residual is not dropped
+        # rows and columns are not correlated with each other
+        if M >= 1000:
+            assert abs(keep.float().mean(0).std().item()) < 0.03 and abs(keep.float().mean(1).std().item()) < 0.03
+            assert abs(keep[:, ::2].float().mean().item() - keep[:, 1::2].float().mean().item()) < 0.01
+    step += 1
+    mask2 = T.dropout_apply(torch.ones(1000, 768, device="cuda"), c)
+    step -= 1
+    mask1 = T.dropout_apply(torch.ones(1000, 768, device="cuda"), c)
+    assert (mask1 > 0).ne(mask2 > 0).float().mean().item() > 0.1             # fresh mask every step
+    assert torch.equal(mask1, T.dropout_apply(torch.ones(1000, 768, device="cuda"), c))   # and reproducible
+    # per-head groups (length-1 softmax dropout): all 64 columns of a head share the draw
+    g = _drop_cfg("heads", p, step, shift=6)
+    mh = T.dropout_apply(torch.ones(512, 768, device="cuda"), g).view(512, 12, 64)
+    assert torch.equal(mh, mh[:, :, :1].expand_as(mh)) and abs((mh[:, :, 0] > 0).float().mean().item() - 0.9) < 0.02
+    xg = (torch.randn(512, 256, device="cuda") * 0.5).bfloat16()
+    wg = (torch.randn(768, 256, device="cuda") * 0.1).bfloat16()
+    assert torch.allclose(ops.gemm_bias_act(xg, wg, out_dtype=torch.float32, drop=g),
+                          ops.gemm_bias_act(xg, wg, out_dtype=torch.float32) * mh.view(512, 768), rtol=1e-6, atol=1e-6)
+    # LayerNorm backward: the masked copy is the unmasked gradient times the same mask
+    rows, cols = 300, 768
+    xln = torch.randn(rows, cols, device="cuda").bfloat16()
+    dy = torch.randn(rows, cols, device="cuda").bfloat16()
+    gam = torch.randn(cols, device="cuda")
+    stats = torch.empty(rows, 2, device="cuda")
+    ops.layernorm(xln, gam, torch.zeros(cols, device="cuda"), 1e-5, stats=stats)
+    dg, db = torch.zeros(cols, device="cuda"), torch.zeros(cols, device="cuda")
+    dxb, dxf, dxm = T.layernorm_bwd_drop(xln, dy, stats, gam, dg, db, want_bf16=True, want_f32=True, drop=c)
+    m = T.dropout_apply(torch.ones(rows, cols, device="cuda"), c)
+    assert torch.allclose(dxm.float(), (dxf * m).bfloat16().float(), rtol=1e-2, atol=1e-3)
+
+
+@pytest.mark.parametrize("B,L,nh,D", [(3, 542, 8, 96), (2, 300, 12, 64)])
+def test_attention_dropout_forward_backward_share_the_mask(B, L, nh, D):
+    """Attention-probability dropout: the forward output equals (mask * softmax / (1 - p)) V with the mask recovered
+    from the backward kernel's P output, the keep rate is 1 - p, and dQ / dK / dV match autograd through that mask."""
+    from fairmultimodal_b200 import ops, ops_train as T
+    from fairmultimodal_b200 import train
+    torch.manual_seed(L)
+    p = 0.1
+    c = _drop_cfg("attn", p)
+    W = 3 * nh * D
+    qkv = (torch.randn(B * L, W, device="cuda") * 0.7).bfloat16()
+    lse = torch.empty(B, nh, L, device="cuda")
+    ctx = ops.attn_fwd(qkv, B, L, nh, D, lse=lse, drop=c)
+    dctx = (torch.randn(B * L, nh * D, device="cuda") * 0.1).bfloat16()
+    ldp = (L + 7) // 8 * 8
+    delta = T.attn_delta(dctx, ctx, B, L, nh, D)
+    pd, _ = T.attn_bwd_pds(qkv, dctx, lse, delta, B, L, nh, D, ldp, D ** -0.5, drop=c)
+    p0, _ = T.attn_bwd_pds(qkv, dctx, lse, delta, B, L, nh, D, ldp, D ** -0.5)
+    pd = pd.view(B, nh, L, ldp)[..., :L].float()
+    p0 = p0.view(B, nh, L, ldp)[..., :L].float()
+    sig = p0 > 1e-4                                           # where the undropped probability is visible in bf16
+    keep = pd > 0
+    assert abs(keep[sig].float().mean().item() - (1 - p)) < 0.01
+    assert torch.allclose(pd[sig & keep], p0[sig & keep] / (1 - 6554 / 65536), rtol=2e-2)
+    mask = torch.where(sig, keep, torch.ones_like(keep)).float() / (1 - 6554 / 65536)
+    # reference through autograd with that mask
+    q, k, v = (t.clone().requires_grad_(True) for t in qkv.float().view(B, L, 3, nh, D).permute(2, 0, 3, 1, 4))
+    pr = torch.softmax((q @ k.transpose(-1, -2)) * D ** -0.5, -1) * mask
+    out = (pr @ v).permute(0, 2, 1, 3).reshape(B * L, nh * D)
+    assert (ctx.float() - out).abs().max() <= 3e-2 * out.abs().max()
+    out.backward(dctx.float())
+    dqkv = train._attn_backward(qkv, dctx, ctx, lse, B, L, nh, D, drop=c).float().view(B, L, 3, nh, D).permute(2, 0, 3, 1, 4)
+    for got, ref in zip(dqkv, (q.grad, k.grad, v.grad)):
+        assert (got - ref).abs().max() <= 4e-2 * ref.abs().max()
+
+
+def test_train_step_with_dropout():
+    """Reference train() mode (p = 0.1 everywhere): the step runs, stays finite, draws a fresh mask every step (also
+    under CUDA-graph replay: the seed follows the device step counter), is reproducible for a fixed step counter, and
+    its loss / gradients agree with the dropout-free step in expectation (loose bound); with p set back to 0 the
+    parity path is bit-identical to a model that never had dropout."""
+    from fairmultimodal_b200 import modules, synth, train
+    L, B = 40, 16
+    co = synth.make_cohort(B, lab_tokens=L, chunks=0, with_tokens=False, seed=3)
+    co["text"] = (np.random.default_rng(1).standard_normal((B, 768)) * 0.5).astype(np.float32)
+    batch = [torch.from_numpy(co[k]).cuda() for k in KEYS9]
+    pw = torch.tensor([3.0, 1.2, 0.6], device="cuda")
+    w = (0.33, 0.33, 0.33)
+    model, _ = _model(L, 4)
+    model.train()
+    loss0, _ = train.forward_backward(model, batch, pw, 0.8, 0.01, w)
+    g0 = train.get_state(model).g.clone()
+    modules.set_dropout(model, 0.1)
+    st = train.get_state(model)
+    loss1, _ = train.forward_backward(model, batch, pw, 0.8, 0.01, w)
+    g1 = st.g.clone()
+    loss1b, _ = train.forward_backward(model, batch, pw, 0.8, 0.01, w)
+    assert torch.equal(loss1, loss1b) or (loss1 - loss1b).abs().max() < 1e-6   # same step counter -> same masks
+    assert torch.isfinite(g1).all() and torch.isfinite(loss1).all()
+    assert not torch.equal(loss0, loss1)
+    assert (loss1[1] - loss0[1]).abs().item() < 0.5                             # BCE of the same order
+    cos = torch.nn.functional.cosine_similarity(g0, g1, dim=0).item()
+    assert cos > 0.3, cos                                                       # same direction on average
+    st.step_dev += 1
+    loss2, _ = train.forward_backward(model, batch, pw, 0.8, 0.01, w)
+    assert not torch.equal(loss1, loss2)                                        # new step -> new masks
+    # graph replay draws fresh masks too
+    hp = dict(lr=0.0, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8)
+    losses = [train.optimisation_step(model, batch, pw, 0.8, 0.01, w, hp).clone() for _ in range(5)]
+    assert any(e.get("graph") is not None for e in st.graphs.values())
+    assert len({round(l[0].item(), 6) for l in losses}) >= 4
+    modules.set_dropout(model, 0.0)
+    loss3, _ = train.forward_backward(model, batch, pw, 0.8, 0.01, w)
+    assert torch.equal(loss3, loss0)
