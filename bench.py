@@ -104,6 +104,42 @@ def cpu_reference_chunks_per_s(n_chunks, threads=None):
     return n_chunks / dt, torch.get_num_threads(), dt
 
 
+def cpu_reference_train_patients_per_s(steps=1, threads=None):
+    """The reference's CPU path for the training step (10_FAME.py:401-449 on the CPU device): forward of the three
+    modules + BCE / LEDDI loss + autograd backward + clip_grad_norm_(1.0) + AdamW, fp32 eager, 32 patients, L = 542 --
+    the oracle's forward / loss under torch.autograd, torch's own clip and AdamW.  Dropout off (the oracle restates
+    the eval-mode arithmetic), which only makes the CPU side cheaper.  Returns (patients/s, threads, seconds)."""
+    import numpy as np
+    import torch
+
+    from fairmultimodal_b200 import synth
+    from oracle import fame_oracle as O
+
+    if threads:
+        torch.set_num_threads(threads)
+    shapes = synth.fame_shapes(lab_tokens=TRAIN_L)
+    sd = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in synth.synth_state_dict(shapes, 4).items()}
+    co = synth.make_cohort(TRAIN_B, lab_tokens=TRAIN_L, chunks=0, with_tokens=False, seed=77)
+    co["text"] = np.random.default_rng(0).standard_normal((TRAIN_B, 768)).astype(np.float32)
+    keys = ("demo_dummy_ids", "demo_attn_mask", "age_ids", "gender_ids", "ethnicity_ids", "insurance_ids",
+            "lab_features", "text", "labels")
+    batch = [torch.from_numpy(co[k]) for k in keys]
+    pw = torch.from_numpy(synth.pos_weight(co["labels"]))
+    params = list(sd.values())
+    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=0.01)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        opt.zero_grad()
+        o = O.fame_forward(sd, batch, (0.33, 0.33, 0.33))
+        total, _, _ = O.fame_loss(o["fused_logits"], batch[8], (batch[2], batch[4], batch[5]), sd["sig_weights"], pw,
+                                  0.8, 0.01)
+        total.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 1.0)
+        opt.step()
+    dt = time.perf_counter() - t0
+    return steps * TRAIN_B / dt, torch.get_num_threads(), dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -333,6 +369,12 @@ def run_ours(args):
             "clocks": clocks,
         }
         if train_info is not None:
+            if world == 1 and args.cpu_train_steps > 0:
+                tv, tthreads, tdt = cpu_reference_train_patients_per_s(args.cpu_train_steps)
+                train_info["cpu_baseline"] = {
+                    "value": tv, "unit": "patients/s", "cores": tthreads, "kind": "port",
+                    "sample": f"{args.cpu_train_steps} step(s) of 32 patients, L = 542 ({tdt:.1f} s): oracle forward + "
+                              "loss under torch.autograd, clip_grad_norm_, torch AdamW, fp32, dropout off"}
             line["train"] = train_info
         if cpu_v is not None:
             line["cpu_baseline"] = {"value": cpu_v, "unit": "chunks/s", "cores": cpu_threads, "kind": "port",
@@ -356,6 +398,7 @@ if __name__ == "__main__":
     ap.add_argument("--ref-chunks-per-step", type=int, default=16,
                     help="--impl reference: chunks per step (bounded sample of the 256-chunk step)")
     ap.add_argument("--skip-train", action="store_true", help="only the note-encoder workload")
+    ap.add_argument("--cpu-train-steps", type=int, default=1, help="CPU training steps timed beside the GPU step (0 = skip)")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--no-dropout", action="store_true", help="training step with every dropout probability 0")
     ap.add_argument("--only-train", action="store_true", help="diagnostic: print only the training-step object")

@@ -43,7 +43,7 @@ class LayerNormArgs(C.Structure):
         ("gamma", C.c_void_p), ("beta", C.c_void_p),
         ("y", C.c_void_p), ("y_f32", C.c_void_p), ("ldy", C.c_int64), ("stats", C.c_void_p),
         ("rows", C.c_int32), ("cols", C.c_int32),
-        ("eps", C.c_float),
+        ("eps", C.c_float), ("residual", C.c_void_p), ("ldr", C.c_int64),
     ]
 
 

@@ -192,8 +192,10 @@ class BertModelB200(nn.Module):
             else:
                 qkv = ops.gemm_bias_act(x, l["wqkv"], l["bqkv"])
                 ctx = ops.attn_fwd(qkv, B, S, nh, H // nh, key_mask=mask, kv_len=kv_len)
-            t = ops.gemm_bias_act(ctx, l["wo"], l["bo"], residual=x)
-            x = ops.layernorm(t, l["ln1"][0], l["ln1"][1], eps, out=t)
+            # the residual of the short-K attention-output projection is added by the LayerNorm kernel, not by the
+            # GEMM epilogue (whose scattered residual loads were that GEMM's critical path); same rounding either way
+            t = ops.gemm_bias_act(ctx, l["wo"], l["bo"])
+            x = ops.layernorm(t, l["ln1"][0], l["ln1"][1], eps, out=t, residual=x)
             h = ops.gemm_bias_act(x, l["w1"], l["b1"], act=ops.ACT_GELU_ERF)
             t = ops.gemm_bias_act(h, l["w2"], l["b2"], residual=x)
             x = ops.layernorm(t, l["ln2"][0], l["ln2"][1], eps, out=t)

@@ -290,20 +290,28 @@ int fame_layernorm(const fame_layernorm_args* a, void*, size_t, fame_stream_t st
     int rc = device_info(&d);
     if (rc != FAME_OK) return rc;
     if (a->rows == 0) return FAME_OK;
+    if (a->residual != nullptr) {
+        if (a->x_dtype != FAME_DT_BF16 || a->y == nullptr || a->y_f32 != nullptr) return FAME_ERR_SHAPE;
+        if (!aligned16(a->residual) || (a->ldr & 7) || a->ldr < a->cols) return FAME_ERR_ALIGN;
+    }
     if (a->x_dtype == FAME_DT_BF16 && a->y != nullptr && a->y_f32 == nullptr) {
         // bf16 -> bf16: two rows per warp, packed registers (rowwise.cuh)
         const int per_block = 2 * fame::kLn2WarpsPerBlock;
         const int grid2 = (a->rows + per_block - 1) / per_block;
-        if (a->cols <= 768)
-            fame::layernorm_bf16_rows2_kernel<3><<<grid2, fame::kLn2WarpsPerBlock * 32, 0, stream>>>(
-                reinterpret_cast<const __nv_bfloat16*>(a->x), a->ldx, a->gamma, a->beta,
-                reinterpret_cast<__nv_bfloat16*>(a->y), a->ldy, reinterpret_cast<float2*>(a->stats), a->rows, a->cols,
-                a->eps);
-        else
-            fame::layernorm_bf16_rows2_kernel<4><<<grid2, fame::kLn2WarpsPerBlock * 32, 0, stream>>>(
-                reinterpret_cast<const __nv_bfloat16*>(a->x), a->ldx, a->gamma, a->beta,
-                reinterpret_cast<__nv_bfloat16*>(a->y), a->ldy, reinterpret_cast<float2*>(a->stats), a->rows, a->cols,
-                a->eps);
+        const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(a->x);
+        const __nv_bfloat16* rr = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+        __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(a->y);
+        float2* st = reinterpret_cast<float2*>(a->stats);
+        const int th = fame::kLn2WarpsPerBlock * 32;
+#define FAME_LN2(CH, RES) \
+    fame::layernorm_bf16_rows2_kernel<CH, RES><<<grid2, th, 0, stream>>>(xr, a->ldx, a->gamma, a->beta, yr, a->ldy, st, \
+                                                                         a->rows, a->cols, a->eps, rr, a->ldr)
+        if (a->cols <= 768) {
+            if (rr != nullptr) FAME_LN2(3, true); else FAME_LN2(3, false);
+        } else {
+            if (rr != nullptr) FAME_LN2(4, true); else FAME_LN2(4, false);
+        }
+#undef FAME_LN2
         return launch_status();
     }
     const int grid = (a->rows + fame::kLnWarpsPerBlock - 1) / fame::kLnWarpsPerBlock;

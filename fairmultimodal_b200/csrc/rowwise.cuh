@@ -206,11 +206,24 @@ __device__ __forceinline__ uint32_t ln_out2(uint32_t w, float m, float rs, float
     return pack_bf16x2((bf16_lo(w) - m) * rs * g0 + b0, (bf16_hi(w) - m) * rs * g1 + b1);
 }
 
-template <int CH>   // chunks of 8 columns per lane: cols <= CH * 256
-__global__ void __launch_bounds__(kLn2WarpsPerBlock * 32, 5)
+// bf16(a + b) of two packed rows chunks, summed in f32 (same rounding as the GEMM epilogue's residual add)
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+    return pack_bf16x2(bf16_lo(a) + bf16_lo(b), bf16_hi(a) + bf16_hi(b));
+}
+__device__ __forceinline__ uint4 add_bf16x8(const uint4& a, const uint4& b) {
+    return make_uint4(add_bf16x2(a.x, b.x), add_bf16x2(a.y, b.y), add_bf16x2(a.z, b.z), add_bf16x2(a.w, b.w));
+}
+
+// kRes: y = LN(x + residual).  The residual add of  LN(dense(.) + x)  (HF:297, 355) normally rides in the producing
+// GEMM's epilogue; for the attention-output projection (K = N = 768: 6144 clk of MMAs per tile) the epilogue's
+// scattered 16-byte residual loads were its critical path (tensor pipe 33 % active, stall reason long_scoreboard),
+// while this streaming kernel absorbs the same 201 MB at HBM speed.
+template <int CH, bool kRes = false>   // chunks of 8 columns per lane: cols <= CH * 256
+__global__ void __launch_bounds__(kLn2WarpsPerBlock * 32, kRes ? 4 : 5)
 layernorm_bf16_rows2_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                             const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, long long ldy,
-                            float2* __restrict__ stats, int rows, int cols, float eps) {
+                            float2* __restrict__ stats, int rows, int cols, float eps,
+                            const __nv_bfloat16* __restrict__ res = nullptr, long long ldr = 0) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = (blockIdx.x * kLn2WarpsPerBlock + warp) * 2;
     if (row0 >= rows) return;
@@ -228,6 +241,26 @@ layernorm_bf16_rows2_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, 
         } else {
             ra[i] = make_uint4(0, 0, 0, 0);
             rb[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    if (kRes) {
+        const uint4* qa = reinterpret_cast<const uint4*>(res + (long long)row0 * ldr);
+        const uint4* qb = reinterpret_cast<const uint4*>(res + (long long)(row0 + (two ? 1 : 0)) * ldr);
+        uint4 sa4[CH], sb4[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int ch = lane + 32 * i;
+            if (ch < nchunks) {
+                sa4[i] = ld_nc_na(qa + ch);
+                sb4[i] = ld_nc_na(qb + ch);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            if (lane + 32 * i < nchunks) {
+                ra[i] = add_bf16x8(ra[i], sa4[i]);
+                rb[i] = add_bf16x8(rb[i], sb4[i]);
+            }
         }
     }
     float sa = 0.f, sb = 0.f;

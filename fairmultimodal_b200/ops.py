@@ -116,9 +116,9 @@ def gemm_bias_act(x, w, bias=None, residual=None, act=ACT_NONE, out=None, out_dt
     return out
 
 
-def layernorm(x, gamma, beta, eps, out=None, out_f32=None, want_f32=False, stats=None):
+def layernorm(x, gamma, beta, eps, out=None, out_f32=None, want_f32=False, stats=None, residual=None):
     """x bf16 or f32 [rows, cols] -> bf16 `out` (default) and / or f32 `out_f32`; optional {mean, rstd} per row.
-    Returns out (bf16) unless want_f32, in which case (out_bf16, out_f32)."""
+    residual (bf16, optional): LN(x + residual).  Returns out (bf16) unless want_f32, in which case (out_bf16, out_f32)."""
     _cuda(x, "x")
     if x.dtype not in (torch.bfloat16, torch.float32):
         raise _lib.FameError("layernorm: x must be bf16 or f32")
@@ -140,7 +140,10 @@ def layernorm(x, gamma, beta, eps, out=None, out_f32=None, want_f32=False, stats
     if stats is not None:
         a.stats = _cuda(stats, "stats", torch.float32).data_ptr()
     a.rows, a.cols, a.eps = rows, cols, eps
-    _call("fame_layernorm", a, 4.0 * rows * cols)
+    if residual is not None:
+        _cuda(residual, "residual", torch.bfloat16)
+        a.residual, a.ldr = residual.data_ptr(), _rowmajor(residual, "residual")
+    _call("fame_layernorm", a, (6.0 if residual is not None else 4.0) * rows * cols)
     return (out, out_f32) if want_f32 else out
 
 

@@ -143,6 +143,10 @@ typedef struct {
     float* stats; /* [rows][2] = {mean, rstd} saved for the backward pass, may be NULL */
     int32_t rows, cols;
     float eps;
+    const void* residual; /* optional bf16 [rows, cols] (row stride ldr): Y = LN(bf16(X + residual)) -- the residual add
+                             of BertSelfOutput / BertOutput when it does not ride in the producing GEMM's epilogue;
+                             bf16 X and bf16 Y only; may be NULL */
+    int64_t ldr;
 } fame_layernorm_args;
 int fame_layernorm(const fame_layernorm_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
 

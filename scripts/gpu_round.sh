@@ -1,6 +1,7 @@
 #!/bin/bash
-# One GPU trip: parity tests, the bench line, the ncu launch list of the same command and full captures of the
-# two dominant kernels.  Outputs under gpurun_out/ (copied to profiles/ by hand after reading them).
+# One GPU trip: parity tests, the bench line, the ncu launch list of the same command, full captures of the
+# dominant kernels, and the launch list of one training step.  Outputs under gpurun_out/ (summaries copied to
+# profiles/ by scripts/summarize_profiles.py after reading them).
 set -u
 TAG=${1:-r01}
 mkdir -p gpurun_out
@@ -24,4 +25,13 @@ echo "ncu attn exit=$?"
 $CMD > gpurun_out/plain_${TAG}.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 48 -c 4 -o gpurun_out/prof_gemm_${TAG} -f $CMD > gpurun_out/ncu_gemm_${TAG}.log 2>&1
 echo "ncu gemm exit=$?"
-ls -la gpurun_out/*.ncu-rep
+$CMD > gpurun_out/plain_${TAG}.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:layernorm_bf16_rows2 -s 24 -c 1 -o gpurun_out/prof_ln_${TAG} -f $CMD > gpurun_out/ncu_ln_${TAG}.log 2>&1
+echo "ncu ln exit=$?"
+export FAME_NO_GRAPH=1
+TCMD="python scripts/bench_train.py 32 542 2"
+$TCMD > gpurun_out/plain_train_${TAG}.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_train_${TAG}.csv $TCMD > gpurun_out/ncu_train_${TAG}.log 2>&1
+echo "ncu train exit=$?"
+unset FAME_NO_GRAPH
+ls -la gpurun_out/*${TAG}*

@@ -194,6 +194,12 @@ def test_layernorm_bf16_fast_path(rows, cols):
     y = x.clone()
     ops.layernorm(y, g, b, 1e-12, out=y)                 # in place, as the note encoder calls it
     _close(y, ref, 1e-2)
+    # fused residual add: LN(bf16(x + r)), in place over x
+    r = torch.randn(rows, cols, device="cuda").bfloat16()
+    ref_r = torch.nn.functional.layer_norm((x.float() + r.float()).bfloat16().float(), (cols,), g, b, 1e-12)
+    y = x.clone()
+    ops.layernorm(y, g, b, 1e-12, out=y, residual=r)
+    _close(y, ref_r, 1e-2)
 
 
 def test_layernorm_and_embed():
