@@ -274,15 +274,29 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const int col0 = n_blk * kGemmBN + half * 128 + cc * 64;
                 const bool active = col0 < p.N;  // warpgroup-uniform
                 float v[64];
+                const bool with_bias = p.bias != nullptr && first_slice;
                 if (active) {
                     uint32_t r0[32], r1[32];
                     tmem_ld_x32(t_addr + cc * 64, r0);
                     tmem_ld_x32(t_addr + cc * 64 + 32, r1);
                     tmem_ld_wait();
+                    if (with_bias && col0 + 64 <= p.N) {
+                        // alpha * acc + bias as one FMA per element (the common case: a full 64-column chunk)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = __uint_as_float(r0[j]) * p.alpha;
-                        v[32 + j] = __uint_as_float(r1[j]) * p.alpha;
+                        for (int j = 0; j < 64; j += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                            const uint32_t* r = j < 32 ? r0 + j : r1 + (j - 32);
+                            v[j] = fmaf(__uint_as_float(r[0]), p.alpha, b.x);
+                            v[j + 1] = fmaf(__uint_as_float(r[1]), p.alpha, b.y);
+                            v[j + 2] = fmaf(__uint_as_float(r[2]), p.alpha, b.z);
+                            v[j + 3] = fmaf(__uint_as_float(r[3]), p.alpha, b.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            v[j] = __uint_as_float(r0[j]) * p.alpha;
+                            v[32 + j] = __uint_as_float(r1[j]) * p.alpha;
+                        }
                     }
                 }
                 if (cc == 1) {
@@ -292,7 +306,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
                 }
                 if (!active) continue;
-                if (p.bias != nullptr && first_slice) {
+                if (with_bias && col0 + 64 > p.N) {      // ragged last chunk: bias added under the column guard
 #pragma unroll
                     for (int j = 0; j < 64; j += 4) {
                         if (col0 + j < p.N) {

@@ -147,3 +147,22 @@ def test_note_encoder_and_pool_match_reference(golden_dir):
     pooled = O.pool_patient_notes(g["cls"], g["offsets"])
     np.testing.assert_array_equal(pooled, g["pooled"])      # chunk->patient indexing + mean: bit-exact
     assert not pooled[1].any()                              # note-less patient -> zero row (10_FAME.py:153-154)
+
+
+def test_dropout_hash_restatement_statistics():
+    """The numpy restatement of the in-kernel dropout mask (oracle/dropout_hash.py): keep rate 1 - p, no visible
+    row / column / neighbour correlation, a new mask per step and per seed, head-grouped draws shared by 64 columns.
+    (The GPU suite checks the kernels against this restatement bit for bit.)"""
+    from oracle import dropout_hash as D
+    th = 6554                                                     # p = 0.1
+    m = D.keep_mask(0xABCDEF, 5, 4000, 768, th)
+    assert abs(m.mean() - 0.9) < 2e-3
+    assert m.mean(0).std() < 0.01 and m.mean(1).std() < 0.02       # binomial: 0.0047 and 0.0108
+    for a, b in ((m[:, 0], m[:, 1]), (m[:, 2], m[:, 3]), (m[0], m[1]), (m[:-1, 10], m[1:, 10])):
+        assert abs(np.corrcoef(a, b)[0, 1]) < 0.08
+    assert (m != D.keep_mask(0xABCDEF, 6, 4000, 768, th)).mean() > 0.15      # step changes the mask
+    assert (m != D.keep_mask(0xABCDEE, 5, 4000, 768, th)).mean() > 0.15      # so does the seed
+    assert np.array_equal(m, D.keep_mask(0xABCDEF, 5, 4000, 768, th))        # pure function
+    g = D.keep_mask(3, 0, 2048, 768, th, group_shift=6).reshape(2048, 12, 64)
+    assert (g == g[:, :, :1]).all() and abs(g[:, :, 0].mean() - 0.9) < 0.01
+    assert D.keep_mask(1, 0, 64, 64, 0).all()                                 # thresh 0: nothing dropped

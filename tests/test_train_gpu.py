@@ -361,6 +361,19 @@ def _drop_cfg(name, p, step=None, shift=0):
     return c
 
 
+@pytest.mark.parametrize("rows,cols,shift,step", [(300, 768, 0, 0), (33, 3072, 0, 7), (512, 768, 6, 2), (5, 40, 0, 123456)])
+def test_dropout_mask_bit_exact_vs_restatement(rows, cols, shift, step):
+    """Integer work: the mask the kernels generate equals the numpy restatement of the hash bit for bit."""
+    from fairmultimodal_b200 import ops_train as T
+    from oracle import dropout_hash as D
+    sd = torch.full((1,), step, dtype=torch.int32, device="cuda")
+    c = _drop_cfg(f"exact{rows}", 0.1, sd, shift)
+    got = T.dropout_apply(torch.ones(rows, cols, device="cuda"), c).cpu().numpy()
+    keep = D.keep_mask(c.seed, step, rows, cols, c.thresh16, shift)
+    np.testing.assert_array_equal(got > 0, keep)
+    np.testing.assert_array_equal(got[keep], np.full(int(keep.sum()), D.inv_keep(c.thresh16), dtype=np.float32))
+
+
 def test_dropout_mask_statistics_and_consistency():
     """The mask is a pure function of (seed, step, row, column): the GEMM epilogue (tensor-core and skinny kernels), the
     LayerNorm backward and the stand-alone kernel produce the SAME mask; keep rate = 1 - p; kept values scaled by
