@@ -138,6 +138,19 @@ def fame_shapes(num_ages=5, num_genders=2, num_eth=5, num_ins=5, lab_tokens=542,
     return s
 
 
+def behrt_combined_shapes(lab_tokens=542, hidden=768):
+    """state_dict layout of BEHRTModel_Combined (01_BEHRT.py:112-131): the lab tower under `lab_model.` + the head."""
+    full = fame_shapes(lab_tokens=lab_tokens, hidden=hidden)
+    out = OrderedDict()
+    for k, shp in full.items():
+        if k.startswith("behrt_lab."):
+            out["lab_model." + k[len("behrt_lab."):]] = shp
+    out["fusion_fc.weight"], out["fusion_fc.bias"] = (hidden, hidden), (hidden,)
+    for h in ("classifier_mort", "classifier_los", "classifier_mech"):
+        out[h + ".weight"], out[h + ".bias"] = (1, hidden), (1,)
+    return out
+
+
 def synth_tensor(name, shape, seed):
     rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
     x = rng.standard_normal(shape, dtype=np.float32)

@@ -68,18 +68,24 @@ def _layout_key(name):
 class DropSites:
     """Dropout sites of one training step: name -> _lib.DropoutCfg (seed per site, shared device step counter)."""
 
-    def __init__(self, model, step_dev, base_seed=0x5EED):
+    def __init__(self, model, step_dev, base_seed=0x5EED, lab_module=None, head_dropout=None):
+        """FAME model by default; with lab_module / head_dropout given: a model that has only the lab tower and one
+        nn.Dropout in its head (behrt_combined.BEHRTModel_Combined)."""
         from . import _lib
         self._lib, self.step_ptr, self.base, self.cache = _lib, step_dev.data_ptr(), base_seed, {}
-        cfg = model.behrt_demo.bert.config
         active = model.training
-        self.p_demo_hidden = float(getattr(cfg, "hidden_dropout_prob", 0.0)) if active else 0.0
-        self.p_demo_attn = float(getattr(cfg, "attention_probs_dropout_prob", 0.0)) if active else 0.0
+        if lab_module is None:
+            cfg = model.behrt_demo.bert.config
+            self.p_demo_hidden = float(getattr(cfg, "hidden_dropout_prob", 0.0)) if active else 0.0
+            self.p_demo_attn = float(getattr(cfg, "attention_probs_dropout_prob", 0.0)) if active else 0.0
+            lab_module, head_dropout = model.behrt_lab, model.fusion_mlp[2]
+        else:
+            self.p_demo_hidden = self.p_demo_attn = 0.0
         self.lab = []
-        for l in model.behrt_lab.transformer_encoder.layers:
+        for l in lab_module.transformer_encoder.layers:
             self.lab.append(dict(attn=float(l.self_attn.dropout) if active else 0.0, d1=float(l.dropout1.p) if active else 0.0,
                                  act=float(l.dropout.p) if active else 0.0, d2=float(l.dropout2.p) if active else 0.0))
-        self.p_fusion = float(model.fusion_mlp[2].p) if active else 0.0
+        self.p_fusion = float(head_dropout.p) if (active and head_dropout is not None) else 0.0
         self.any = active and (self.p_demo_hidden > 0 or self.p_demo_attn > 0 or self.p_fusion > 0 or
                                any(v > 0 for d in self.lab for v in d.values()))
 
@@ -137,15 +143,19 @@ def plan_buckets(region, total):
 class FlatTrainState:
     """Flat parameter / gradient / AdamW-state buffers for one MultimodalTransformer_EDDI_Sigmoid."""
 
-    def __init__(self, model):
+    def __init__(self, model, no_grad_prefixes=NO_GRAD_PREFIXES, fame_layout=True):
+        """fame_layout: the region / bucket layout of MultimodalTransformer_EDDI_Sigmoid (below).  Other models
+        (behrt_combined.BEHRTModel_Combined) use module order and a single all-reduce bucket."""
         self.model = model
+        self.fame_layout = fame_layout
         dev = next(model.parameters()).device
-        named = [(n, p) for n, p in model.named_parameters() if not n.startswith(NO_GRAD_PREFIXES)]
+        named = [(n, p) for n, p in model.named_parameters() if not (no_grad_prefixes and n.startswith(no_grad_prefixes))]
         # Layout = the order in which the backward completes gradients, so that every all-reduce bucket is ONE
         # contiguous range:  [never reduced | rest | demo layers 0..11 | lab | head].  "Never reduced": query / key
         # projections of the demographic BERT -- with its length-1 sequences the softmax is identically 1, their
         # gradient is exactly zero on every rank (never written, SURVEY A.3-3); 57 MB that need not cross NVLink.
-        named.sort(key=lambda np_: _layout_key(np_[0]))          # stable: module order inside each region
+        if fame_layout:
+            named.sort(key=lambda np_: _layout_key(np_[0]))      # stable: module order inside each region
         self.offsets, self.region, self.n = plan_layout([(n, p.numel()) for n, p in named])
         off = self.n
         self.p = torch.zeros(off, device=dev, dtype=torch.float32)
@@ -207,7 +217,7 @@ class FlatTrainState:
         piece and 1.67 ms in eight, and every call costs 40-70 us of latency."""
         if getattr(self, "_buckets", None) is not None:
             return self._buckets
-        cuts = plan_buckets(self.region, self.n)
+        cuts = plan_buckets(self.region, self.n) if self.fame_layout else {"tail": (0, self.n)}
         self._buckets = cuts
         return cuts
 
@@ -268,10 +278,9 @@ class FlatTrainState:
     def invalidate_caches(self):
         """The kernels update the flat buffer behind torch's back (no version bump): drop the inference-path
         packed-weight caches so the next eval forward re-reads the parameters."""
-        m = self.model
-        m._packed = None
-        m.behrt_lab._packed = None
-        m.behrt_demo.bert._packed = None
+        for m in self.model.modules():
+            if getattr(m, "_packed", None) is not None:
+                m._packed = None
 
 
 def release_graphs(model):
@@ -447,16 +456,16 @@ def _demo_backward(st, model, saved, ddemo, reducer=None, ds=None):
 
 
 # ------------------------------------------------------------------------------------------------ lab tower
-def _lab_forward(st, model, lab, ds=None):
-    pre = "behrt_lab."
+def _lab_forward(st, model, lab, ds=None, lab_module=None, pre="behrt_lab."):
+    lab_module = model.behrt_lab if lab_module is None else lab_module
     B, L = lab.shape
-    H, nh = 768, model.behrt_lab.nhead
+    H, nh = 768, lab_module.nhead
     lab = lab.float().contiguous()
     x = ops.lab_embed(lab, st.f(pre + "token_embedding.weight")[:, 0].contiguous(), st.f(pre + "token_embedding.bias"),
                       st.f(pre + "pos_embedding"))
     saved = {"lab": lab, "layers": []}
     dev = lab.device
-    for i, layer in enumerate(model.behrt_lab.transformer_encoder.layers):
+    for i, layer in enumerate(lab_module.transformer_encoder.layers):
         p = f"{pre}transformer_encoder.layers.{i}."
         pr = ds.lab[i] if ds is not None else dict(attn=0.0, d1=0.0, act=0.0, d2=0.0)
         site = (lambda n, q: ds.site(f"lab.{i}.{n}", q)) if ds is not None else (lambda n, q: None)
@@ -506,11 +515,11 @@ def _attn_backward(qkv, dctx, ctx, lse, B, L, nh, D, drop=None):
     return dqkv
 
 
-def _lab_backward(st, model, saved, dlab, ds=None):
-    pre = "behrt_lab."
+def _lab_backward(st, model, saved, dlab, ds=None, lab_module=None, pre="behrt_lab."):
+    lab_module = model.behrt_lab if lab_module is None else lab_module
     lab = saved["lab"]
     B, L = lab.shape
-    H, nh = 768, model.behrt_lab.nhead
+    H, nh = 768, lab_module.nhead
     dx = T.seq_mean_bwd(dlab, B, L)                                  # bf16 [B*L, 768]
     for i in reversed(range(len(saved["layers"]))):
         p = f"{pre}transformer_encoder.layers.{i}."

@@ -122,6 +122,46 @@ def behrt_lab(sd, lab, prefix="behrt_lab.", nhead=8, num_layers=2, eps=1e-5):
     return x.mean(dim=1)
 
 
+def behrt_combined(sd, lab):
+    """BEHRTModel_Combined.forward (01_BEHRT.py:122-131), eval mode: logits f32 [B, 3] (mort, los, mech)."""
+    e = behrt_lab(sd, lab, prefix="lab_model.")
+    fused = F.linear(e, sd["fusion_fc.weight"].float(), sd["fusion_fc.bias"].float())
+    w = torch.cat([sd[h + ".weight"].float() for h in ("classifier_mort", "classifier_los", "classifier_mech")])
+    b = torch.cat([sd[h + ".bias"].float() for h in ("classifier_mort", "classifier_los", "classifier_mech")])
+    return F.linear(fused, w, b)
+
+
+def behrt_combined_loss(logits, labels, pos_weight):
+    """Training objective of 01_BEHRT.py:218-222: the SUM of three BCEWithLogitsLoss(pos_weight_i) batch means."""
+    total = 0.0
+    for i in range(3):
+        total = total + F.binary_cross_entropy_with_logits(logits[:, i], labels[:, i], pos_weight=pos_weight[i])
+    return total
+
+
+def eo_difference_n2(tpr, fpr):
+    """calculate_equalized_odds_difference (01_BEHRT.py:27-42): sum over i < j of |d| divided by n^2."""
+    g = list(tpr.keys())
+    n = len(g)
+    if n == 0:
+        return 0.0, 0.0, 0.0
+    t = sum(abs(tpr[g[i]] - tpr[g[j]]) for i in range(n) for j in range(i + 1, n)) / n ** 2
+    f = sum(abs(fpr[g[i]] - fpr[g[j]]) for i in range(n) for j in range(i + 1, n)) / n ** 2
+    return t, f, (t + f) / 2.0
+
+
+def eddi_unique_groups(sensitive, y_true, score, threshold=0.5):
+    """compute_eddi of 01_BEHRT.py:85-100 (groups = np.unique, denominator 1.0 when the error rate is 0 or 1)."""
+    pred = (score > threshold).astype(int)
+    err = np.mean(pred != y_true)
+    denom = max(err, 1 - err) if err not in [0, 1] else 1.0
+    sub = {}
+    for gval in np.unique(sensitive):
+        m = sensitive == gval
+        sub[gval] = (np.mean(pred[m] != y_true[m]) - err) / denom
+    return float(np.sqrt(np.nansum(np.array(list(sub.values())) ** 2)) / len(sub)), sub
+
+
 def fusion(sd, demo_emb, lab_emb, text_emb, weights=(0.33, 0.33, 0.33)):
     """MultimodalTransformer_EDDI_Sigmoid.forward after the encoders (FAME:276-308), eval mode.
     weights = (w_demo, w_lab, w_text): the 'mortality' entry of old_eddi_weights (FAME:283-285) or 0.33."""

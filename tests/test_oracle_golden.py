@@ -166,3 +166,41 @@ def test_dropout_hash_restatement_statistics():
     g = D.keep_mask(3, 0, 2048, 768, th, group_shift=6).reshape(2048, 12, 64)
     assert (g == g[:, :, :1]).all() and abs(g[:, :, 0].mean() - 0.9) < 0.01
     assert D.keep_mask(1, 0, 64, 64, 0).all()                                 # thresh 0: nothing dropped
+
+
+def test_behrt_combined_oracle_vs_reference_golden(golden_dir):
+    """Structured-only baseline (01_BEHRT.py): the oracle restatement of BEHRTModel_Combined, its summed
+    BCE objective (autograd gradients) and the EO / EDDI variants against the unmodified reference."""
+    import os
+    import torch
+    from fairmultimodal_b200 import synth
+    from oracle import fame_oracle as O
+    g = np.load(os.path.join(golden_dir, "behrt_combined.npz"))
+    L = g["lab"].shape[1]
+    sd = {k: torch.from_numpy(v).clone().requires_grad_(True)
+          for k, v in synth.synth_state_dict(synth.behrt_combined_shapes(lab_tokens=L), 9).items()}
+    lab, labels = torch.from_numpy(g["lab"]), torch.from_numpy(g["labels"])
+    logits = O.behrt_combined(sd, lab)
+    np.testing.assert_allclose(logits.detach().numpy(), g["logits_eval"], atol=2e-5, rtol=1e-4)
+    loss = O.behrt_combined_loss(logits, labels, torch.from_numpy(g["pos_weight"]))
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    loss.backward()
+    names = [str(n) for n in g["gnorm_by_param_names"]]
+    got = np.array([sd[n].grad.norm().item() for n in names])
+    np.testing.assert_allclose(got, g["gnorm_by_param"], rtol=2e-3, atol=1e-7)
+    for k in g.files:
+        if k.startswith("grad."):
+            ref = g[k]
+            mine = sd[k[5:]].grad.numpy()
+            np.testing.assert_allclose(mine[:ref.shape[0]] if ref.ndim == 2 else mine, ref, rtol=2e-3, atol=1e-6)
+    # metric variants
+    code, y, score = g["m_code"], g["m_y"].astype(int), g["m_score"]
+    ed, sub = O.eddi_unique_groups(code, y, score, 0.5)
+    assert abs(ed - float(g["m_eddi"])) < 1e-12
+    np.testing.assert_allclose([sub[k] for k in sorted(sub)], g["m_eddi_sub"], atol=1e-12)
+    pred = (score > 0.5).astype(int)
+    tpr, fpr = {}, {}
+    for gv in np.unique(code):
+        m = code == gv
+        tpr[gv], fpr[gv] = O.group_rates(y[m], pred[m], np.ones(m.sum(), bool))[:2]
+    np.testing.assert_allclose(O.eo_difference_n2(tpr, fpr), g["m_eo"], atol=1e-12)
