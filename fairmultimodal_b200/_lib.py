@@ -171,6 +171,9 @@ FLAT_OPS = {
     "fame_mask_kv_len": [_P, _I32, _I32, _P],
     "fame_layernorm_bwd": [_P, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P],
     "fame_dropout_apply": [_P, _I32, _I64, _I32, _I32, _P],
+    "fame_focal_loss_fwd_bwd": [_P, _P, _P, _F, _F, _I32, _P, _P],
+    "fame_relu_fwd": [_P, _I64],
+    "fame_relu_bwd": [_P, _P, _I64],
     "fame_gelu_fwd": [_P, _P, _I64],
     "fame_gelu_bwd": [_P, _P, _P, _I64],
     "fame_colsum": [_P, _I32, _I64, _I32, _I32, _P],

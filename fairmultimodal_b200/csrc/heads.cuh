@@ -600,4 +600,52 @@ loss_fwd_bwd_kernel(const LossGradParams p) {
     }
 }
 
+// ================================================================================================ focal loss (f-1)
+// Text-only baseline of the reference (02_BioClinicalBERT.py:18-38, 138-152): per outcome i
+//   bce = BCEWithLogits(pos_weight_i)(z, y) elementwise;  pt = exp(-bce);  fl = alpha * (1 - pt)^gamma * bce;
+//   loss = sum_i mean_b fl[b, i].          d fl / d z = alpha * (gamma (1-pt)^(gamma-1) pt bce + (1-pt)^gamma) * d bce / d z,
+//   d bce / d z = -pw y (1 - sigmoid z) + (1 - y) sigmoid z.
+// One thread per (patient, outcome); the loss is accumulated in float64 (one atomic per block).
+__global__ void __launch_bounds__(256)
+focal_loss_fwd_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
+                          const float* __restrict__ pos_weight, float gamma, float alpha, float inv_batch, int n,
+                          double* __restrict__ loss_out, float* __restrict__ dlogits) {
+    __shared__ double part[8];
+    double acc = 0.0;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int i = idx % 3;
+        const float z = __ldg(logits + idx), y = __ldg(labels + idx), pw = __ldg(pos_weight + i);
+        const float sp = fmaxf(-z, 0.f) + log1pf(expf(-fabsf(z)));          // softplus(-z) = -log sigmoid(z)
+        const float bce = pw * y * sp + (1.0f - y) * (sp + z);
+        const float pt = expf(-bce), om = 1.0f - pt;
+        const float omg = gamma == 2.0f ? om * om : powf(om, gamma);
+        const float omg1 = gamma == 2.0f ? om : (om > 0.f ? powf(om, gamma - 1.0f) : (gamma == 1.0f ? 1.0f : 0.f));
+        acc += (double)(alpha * omg * bce);
+        if (dlogits != nullptr) {
+            const float sg = 1.0f / (1.0f + expf(-z));
+            const float dbce = -pw * y * (1.0f - sg) + (1.0f - y) * sg;
+            dlogits[idx] = alpha * (gamma * omg1 * pt * bce + omg) * dbce * inv_batch;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+        atomicAdd(loss_out, t * (double)inv_batch);
+    }
+}
+
+// h = relu(x) in place;  dh = pre > 0 ? dh : 0 in place  (the 256-wide hidden layer of the text-only classifier)
+__global__ void relu_fwd_kernel(float* __restrict__ x, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        x[i] = fmaxf(x[i], 0.f);
+}
+__global__ void relu_bwd_kernel(float* __restrict__ dh, const float* __restrict__ pre, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dh[i] = pre[i] > 0.f ? dh[i] : 0.f;
+}
+
 }  // namespace fame

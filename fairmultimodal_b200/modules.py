@@ -28,6 +28,11 @@ class BioClinicalBERT_FT(nn.Module):
         self.BioBert = base_model
         self.device = device
 
+    @property
+    def bert(self):
+        """Name of the encoder attribute in 02_BioClinicalBERT.py:62 (10_FAME.py calls it BioBert)."""
+        return self.BioBert
+
     @classmethod
     def from_state_dict(cls, sd, prefix="BioBert.", **cfg):
         sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}

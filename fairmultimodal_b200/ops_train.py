@@ -218,3 +218,24 @@ def transpose_bf16_table(table, n_entries, total_tiles):
 
 def cast_bf16(x, y):
     _flat("fame_cast_bf16", x.data_ptr(), y.data_ptr(), x.numel())
+
+
+def focal_loss_fwd_bwd(logits, labels, pos_weight, gamma=2.0, alpha=1.0, want_grad=True):
+    """sum_i mean_b FocalLoss(gamma, alpha, pos_weight_i)(logits[:, i], labels[:, i]) -> (loss f64 [1], dlogits | None)."""
+    B = logits.shape[0]
+    loss = torch.zeros(1, device=logits.device, dtype=torch.float64)
+    dl = torch.empty((B, 3), device=logits.device, dtype=torch.float32) if want_grad else None
+    keep = (logits.float().contiguous(), labels.float().contiguous(), pos_weight.float().contiguous())
+    _flat("fame_focal_loss_fwd_bwd", keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(), float(gamma), float(alpha),
+          B, loss.data_ptr(), _p(dl))
+    return loss, dl
+
+
+def relu_(x):
+    _flat("fame_relu_fwd", x.data_ptr(), x.numel())
+    return x
+
+
+def relu_bwd_(dh, pre):
+    _flat("fame_relu_bwd", dh.data_ptr(), pre.data_ptr(), dh.numel())
+    return dh

@@ -448,6 +448,14 @@ int fame_attn_bwd_pds(const void* qkv, int64_t ld_qkv, const void* dctx, int64_t
                       const float* delta, void* p, void* ds, int64_t ldp, int32_t batch, int32_t seq, int32_t heads,
                       int32_t head_dim, float scale, const fame_dropout_cfg* drop /* the forward's, or NULL */,
                       fame_stream_t stream);
+/* Text-only baseline (02_BioClinicalBERT.py): FocalLoss(gamma, alpha, pos_weight_i) summed over the three
+ * outcomes, each a batch mean (18-38, 143-147): *loss_out += loss (float64, caller zeroes it); dlogits [batch, 3] =
+ * d loss / d logits (may be NULL).  fame_relu_fwd / fame_relu_bwd: ReLU of the classifier's 256-wide hidden layer, in
+ * place, and its backward mask (dh = pre > 0 ? dh : 0). */
+int fame_focal_loss_fwd_bwd(const float* logits, const float* labels, const float* pos_weight, float gamma, float alpha,
+                            int32_t batch, double* loss_out, float* dlogits, fame_stream_t stream);
+int fame_relu_fwd(float* x, int64_t n, fame_stream_t stream);
+int fame_relu_bwd(float* dh, const float* pre, int64_t n, fame_stream_t stream);
 int fame_transpose_bf16_table(const void* table, int32_t n_entries, int32_t total_tiles, fame_stream_t stream);
 
 #ifdef __cplusplus

@@ -139,6 +139,24 @@ def behrt_combined_loss(logits, labels, pos_weight):
     return total
 
 
+def text_classifier(sd, x):
+    """UnstructuredClassifier.forward (02_BioClinicalBERT.py:122-134), eval mode: logits f32 [B, 3]."""
+    h = torch.relu(F.linear(x, sd["classifier.0.weight"].float(), sd["classifier.0.bias"].float()))
+    return F.linear(h, sd["classifier.3.weight"].float(), sd["classifier.3.bias"].float())
+
+
+def focal_loss(logits, targets, pos_weight, gamma=2.0, alpha=None):
+    """FocalLoss.forward, reduction='mean' (02_BioClinicalBERT.py:26-38)."""
+    bce = F.binary_cross_entropy_with_logits(logits, targets, reduction="none", pos_weight=pos_weight)
+    fl = (1 - torch.exp(-bce)) ** gamma * bce
+    return (fl if alpha is None else alpha * fl).mean()
+
+
+def text_classifier_loss(logits, labels, pos_weight, gamma=2.0):
+    """train_model's objective (02_BioClinicalBERT.py:143-146): the sum of the three focal losses."""
+    return sum(focal_loss(logits[:, i:i + 1], labels[:, i:i + 1], pos_weight[i], gamma) for i in range(3))
+
+
 def eo_difference_n2(tpr, fpr):
     """calculate_equalized_odds_difference (01_BEHRT.py:27-42): sum over i < j of |d| divided by n^2."""
     g = list(tpr.keys())

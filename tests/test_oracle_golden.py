@@ -204,3 +204,52 @@ def test_behrt_combined_oracle_vs_reference_golden(golden_dir):
         m = code == gv
         tpr[gv], fpr[gv] = O.group_rates(y[m], pred[m], np.ones(m.sum(), bool))[:2]
     np.testing.assert_allclose(O.eo_difference_n2(tpr, fpr), g["m_eo"], atol=1e-12)
+
+
+TEXT_SHAPES = {"classifier.0.weight": (256, 768), "classifier.0.bias": (256,), "classifier.3.weight": (3, 256),
+               "classifier.3.bias": (3,)}
+
+
+def text_state(seed=13):
+    import torch
+    from fairmultimodal_b200 import synth
+    return {k: torch.from_numpy(synth.synth_tensor(k, shp, seed) * (3.0 if "weight" in k else 1.0))
+            for k, shp in TEXT_SHAPES.items()}
+
+
+def test_text_classifier_oracle_vs_reference_golden(golden_dir):
+    """Text-only baseline (02_BioClinicalBERT.py): classifier, focal loss, one epoch of train_model
+    (AdamW without clipping) restated in the oracle against the unmodified reference."""
+    import os
+    import torch
+    from oracle import fame_oracle as O
+    g = np.load(os.path.join(golden_dir, "text_classifier.npz"))
+    sd = {k: v.clone().requires_grad_(True) for k, v in text_state().items()}
+    emb, labels, pw = torch.from_numpy(g["emb"]), torch.from_numpy(g["labels"]), torch.from_numpy(g["pos_weight"])
+    np.testing.assert_allclose(O.text_classifier(sd, emb).detach().numpy(), g["logits_eval"], atol=1e-5, rtol=1e-5)
+    fl = O.focal_loss(torch.from_numpy(g["fl_z"]), torch.from_numpy(g["fl_y"]), pw[0])
+    assert abs(fl.item() - float(g["fl_value"])) < 1e-6
+    loss0 = O.text_classifier_loss(O.text_classifier(sd, emb[:8]), labels[:8], pw)
+    assert abs(loss0.item() - float(g["loss_batch0"])) < 1e-6
+    loss0.backward()
+    for k in TEXT_SHAPES:
+        ref = g["grad." + k]
+        np.testing.assert_allclose(sd[k].grad.numpy()[:ref.shape[0]], ref, rtol=1e-4, atol=1e-7)
+    # the epoch: three batches of 8, AdamW(lr 1e-3, wd 0.01), no clipping
+    params = {k: v.detach().clone() for k, v in text_state().items()}
+    m = {k: torch.zeros_like(v) for k, v in params.items()}
+    v2 = {k: torch.zeros_like(v) for k, v in params.items()}
+    losses = []
+    for step in range(3):
+        leaf = {k: p.clone().requires_grad_(True) for k, p in params.items()}
+        sl = slice(8 * step, 8 * step + 8)
+        loss = O.text_classifier_loss(O.text_classifier(leaf, emb[sl]), labels[sl], pw)
+        loss.backward()
+        losses.append(loss.item())
+        names = list(params)
+        O.clip_and_adamw([params[k] for k in names], [leaf[k].grad for k in names], [m[k] for k in names],
+                         [v2[k] for k in names], step + 1, 1e-3, 0.01, max_norm=1e30)        # updates in place
+    assert abs(np.mean(losses) - float(g["epoch_loss"])) < 1e-5
+    for k in TEXT_SHAPES:
+        ref = g["after." + k]
+        np.testing.assert_allclose(params[k].numpy()[:ref.shape[0]], ref, rtol=1e-4, atol=2e-6)
