@@ -509,15 +509,18 @@ seq_mean_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, in
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     if (c0 < cols) {
         int l = sp;
-        for (; l + 3 * splits < L; l += 4 * splits) {
-            float f[4][8];
+        for (; l + 7 * splits < L; l += 8 * splits) {      // 8 independent 16-byte loads in flight per thread
+            uint4 raw[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(xb + (long long)(l + u * splits) * cols + c0)), f[u]);
+            for (int u = 0; u < 8; ++u)
+                raw[u] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(l + u * splits) * cols + c0));
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 8; ++u) {
+                float f[8];
+                bf16x8_to_float(raw[u], f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += f[u][j];
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
         }
         for (; l < L; l += splits) {
             float f[8];
