@@ -157,11 +157,11 @@ class GemmExArgs(C.Structure):
         ("y_dtype", C.c_int32),
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("nb0", C.c_int32), ("nb1", C.c_int32),
         ("act", C.c_int32), ("alpha", C.c_float), ("n_valid", C.c_int32), ("split_k", C.c_int32),
-        ("drop", DropoutCfg),
+        ("drop", DropoutCfg), ("pre_act", C.c_void_p), ("ld_pre", C.c_int64),
     ]
 
 
-AUX_NONE, AUX_ADD_BF16, AUX_ADD_F32, AUX_RELU_MASK_BF16 = 0, 1, 2, 3
+AUX_NONE, AUX_ADD_BF16, AUX_ADD_F32, AUX_RELU_MASK_BF16, AUX_GELU_BWD_BF16 = 0, 1, 2, 3, 4
 LOSS_STATS_LEN = 104
 EVAL_COUNTS_LEN = 914
 
@@ -189,7 +189,7 @@ FLAT_OPS = {
     "fame_clip_adamw": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _I32, _P, _P, _P, _P],
     "fame_cast_bf16": [_P, _P, _I64],
     "fame_transpose_bf16_table": [_P, _I32, _I32],
-    "fame_wgrad_small": [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32],
+    "fame_wgrad_small": [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "fame_attn_delta": [_P, _P, _I64, _P, _I32, _I32, _I32, _I32],
     "fame_attn_bwd_pds": [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _F, _P],
 }

@@ -102,9 +102,11 @@ def forward_backward(model, lab, labels, pos_weight, group=None):
     loss = sum_i BCEWithLogits(pos_weight_i)(logits_i, labels_i), each a mean over the (global) batch.
     Returns (loss f32 [1] on the device, logits [B,3])."""
     st = get_state(model)
-    st.zero_grad()
-    st.sumsq.zero_()
-    st.post_stream().wait_stream(torch.cuda.current_stream())
+    post = st.post_stream()
+    post.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(post):                       # beside the forward pass (see train.forward_backward)
+        st.zero_grad()
+        st.sumsq.zero_()
     ds = _drop_sites(model, st)
     emb, saved = train._lab_forward(st, model, lab, ds, lab_module=model.lab_model, pre="lab_model.")
     wf, wc = st.f("fusion_fc.weight"), _wc(st)
@@ -124,6 +126,7 @@ def forward_backward(model, lab, labels, pos_weight, group=None):
     loss = loss4[1:2] * 3.0
     dlogits = dlogits * 3.0
     red = train._GradReducer(st, group)
+    torch.cuda.current_stream().wait_stream(post)
     # head backward (fp32): dWc = dlogits^T fused, dbc = colsum(dlogits); dfused = dlogits Wc (through the dropout);
     # dWf = dfused^T emb, dbf = colsum(dfused); demb = dfused Wf
     dwc = torch.empty((3, 768), device=dev, dtype=torch.float32)

@@ -48,7 +48,7 @@ constexpr int kGemmThreads = 384;
 constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + 2 * kGemmCBoxBytes + 1024 /*align slack*/ + 256;
 
 enum { kActNone = 0, kActGelu = 1, kActRelu = 2 };
-enum { kResNone = 0, kResAddBf16 = 1, kResAddF32 = 2, kResReluMaskBf16 = 3 };
+enum { kResNone = 0, kResAddBf16 = 1, kResAddF32 = 2, kResReluMaskBf16 = 3, kResGeluBwdBf16 = 4 /* skinny only */ };
 
 struct GemmParams {
     int M, N, K;                    // per-batch output rows / cols and contraction length

@@ -40,6 +40,8 @@ struct SkinnyParams {
     int act;
     float alpha;
     DropCfg drop;             // dropout after the activation, before the residual add
+    __nv_bfloat16* pre_act;   // optional [M, ld_pre]: x W^T + bias BEFORE the activation (saved for the GELU backward)
+    long long ld_pre;
 };
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -117,6 +119,11 @@ skinny_gemm_kernel(const SkinnyParams p) {
     const int n = n0 + col;
     v *= p.alpha;
     if (p.bias != nullptr) v += __ldg(p.bias + n);
+    if (p.pre_act != nullptr) {
+        const __nv_bfloat16 pb = __float2bfloat16_rn(v);
+        p.pre_act[(long long)row * p.ld_pre + n] = pb;
+        v = __bfloat162float(pb);      // the activation sees the rounded value, as when it is applied by a second kernel
+    }
     if (p.act == kActGelu) v = gelu_erf(v);
     else if (p.act == kActRelu) v = fmaxf(v, 0.f);
     if (p.drop.thresh16 != 0u) {
@@ -130,6 +137,13 @@ skinny_gemm_kernel(const SkinnyParams p) {
     } else if (p.res_mode == kResReluMaskBf16) {
         const float a = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[(long long)row * p.ldr + n]);
         v = a > 0.f ? v : 0.f;
+    } else if (p.res_mode == kResGeluBwdBf16) {
+        // erf-GELU backward: d pre = d h * (Phi(x) + x phi(x)), x = the saved pre-activation; d h rounded to bf16 first,
+        // as when the product and the GELU backward are two kernels
+        const float x = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[(long long)row * p.ldr + n]);
+        const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+        const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+        v = __bfloat162float(__float2bfloat16_rn(v)) * (cdf + x * pdf);
     }
     if (p.y_f32) reinterpret_cast<float*>(p.y)[(long long)row * p.ldy + n] = v;
     else reinterpret_cast<__nv_bfloat16*>(p.y)[(long long)row * p.ldy + n] = __float2bfloat16_rn(v);
@@ -143,7 +157,8 @@ constexpr int kWsBN = 64, kWsBK = 128;
 
 __global__ void __launch_bounds__(256)
 wgrad_small_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const __nv_bfloat16* __restrict__ x,
-                   long long ld_x, float* __restrict__ out, long long ld_out, int M, int N, int K, int accumulate) {
+                   long long ld_x, float* __restrict__ out, long long ld_out, int M, int N, int K, int accumulate,
+                   float* __restrict__ dbias) {
     __shared__ __align__(16) float s_dy[kSkMaxM][kWsBN];
     __shared__ __align__(16) float s_x[kSkMaxM][kWsBK];
     const int n0 = blockIdx.y * kWsBN, k0 = blockIdx.x * kWsBK;
@@ -185,6 +200,15 @@ wgrad_small_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const 
         }
     }
     __syncthreads();
+    // bias gradient = column sums of dY, from the tile the first k-block of each n-block has staged anyway (saves the
+    // separate column-sum launch: 48 of the ~270 launches of the demographic tower's step)
+    if (dbias != nullptr && blockIdx.x == 0 && threadIdx.x < kWsBN && n0 + (int)threadIdx.x < N) {
+        float sacc = 0.f;
+#pragma unroll 8
+        for (int m = 0; m < kSkMaxM; ++m) sacc += s_dy[m][threadIdx.x];
+        if (accumulate) dbias[n0 + threadIdx.x] += sacc;
+        else dbias[n0 + threadIdx.x] = sacc;
+    }
     const int tk = threadIdx.x & 15, tn = threadIdx.x >> 4;   // 16 threads along k (8 each), 16 along n (4 each)
     float acc[4][8];
 #pragma unroll

@@ -6,7 +6,7 @@ import ctypes
 import torch
 
 from . import _lib, ops
-from ._lib import AUX_ADD_BF16, AUX_ADD_F32, AUX_NONE, AUX_RELU_MASK_BF16, DT_BF16, DT_F32  # noqa: F401
+from ._lib import AUX_ADD_BF16, AUX_ADD_F32, AUX_GELU_BWD_BF16, AUX_NONE, AUX_RELU_MASK_BF16, DT_BF16, DT_F32  # noqa: F401
 
 
 def _dt(t):
@@ -31,7 +31,7 @@ def _p(t):
 
 def gemm_ex(a, b, y, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldy=None, bias=None, aux=None,
             aux_mode=AUX_NONE, ld_aux=0, act=0, alpha=1.0, nb0=1, nb1=1, sa=(0, 0), sb=(0, 0), sy=(0, 0), saux=(0, 0),
-            n_valid=0, a_off=0, b_off=0, y_off=0, aux_off=0, tag="", split_k=0, drop=None):
+            n_valid=0, a_off=0, b_off=0, y_off=0, aux_off=0, tag="", split_k=0, drop=None, pre_act=None):
     """General tcgen05 GEMM (fame_gemm_ex).  a / b / y / aux are tensors (any shape); geometry is explicit:
     leading dimensions, element offsets and batch strides (b0, b1) in elements."""
     g = _lib.GemmExArgs()
@@ -48,6 +48,8 @@ def gemm_ex(a, b, y, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldy=No
     g.M, g.N, g.K, g.nb0, g.nb1 = M, N, K, nb0, nb1
     g.act, g.alpha, g.n_valid, g.split_k = act, alpha, n_valid, split_k
     ops._set_drop(g.drop, drop)
+    if pre_act is not None:
+        g.pre_act, g.ld_pre = pre_act.data_ptr(), pre_act.stride(0)
     ops._call("fame_gemm_ex", g, 2.0 * M * N * K * nb0 * nb1, tag)
     return y
 
@@ -71,7 +73,7 @@ def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, aux=None, aux_mode=A
                    drop=drop)
 
 
-def linear_wgrad(dy, x, out, accumulate=True):
+def linear_wgrad(dy, x, out, accumulate=True, dbias=None):
     """dW[N, K] (+)= dY[T, N]^T @ X[T, K] -> f32 `out` (a view into the flat gradient buffer).  With accumulate (the
     training step: the buffer was zeroed by zero_grad) the token contraction is split over the SMs (split-K) and the
     slices are added with float4 atomics; otherwise `out` is overwritten by a single-pass product."""
@@ -79,8 +81,10 @@ def linear_wgrad(dy, x, out, accumulate=True):
     K = x.shape[1]
     if T <= SKINNY_MAX_ROWS:
         _flat("fame_wgrad_small", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0),
-              T, N, K, int(accumulate))
+              T, N, K, int(accumulate), _p(dbias))
         return out
+    if dbias is not None:
+        raise ValueError("the fused bias gradient exists on the <= 32-row path only")
     return gemm_ex(dy, x, out, N, K, T, a_mn=True, b_mn=True, lda=dy.stride(0), ldb=x.stride(0), ldy=out.stride(0),
                    tag="wgrad", split_k=-1 if accumulate else 0)
 
@@ -239,3 +243,14 @@ def relu_(x):
 def relu_bwd_(dh, pre):
     _flat("fame_relu_bwd", dh.data_ptr(), pre.data_ptr(), dh.numel())
     return dh
+
+
+def linear_gelu_small(x, w, bias):
+    """<= 32 rows: h = gelu(x W^T + b) and the bf16 pre-activation from ONE weight-streaming launch.  Returns (pre, h)."""
+    M, K = x.shape
+    N = w.shape[0]
+    pre = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
+    h = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
+    gemm_ex(x, w, h, M, N, K, lda=x.stride(0), ldb=w.stride(0), ldy=N, bias=bias, act=_lib.ACT_GELU_ERF, pre_act=pre,
+            tag="fwd")
+    return pre, h

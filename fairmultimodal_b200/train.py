@@ -272,7 +272,7 @@ class FlatTrainState:
         self.sumsq_valid = False
         T.clip_adamw(self.p, self.g, self.m, self.v, self.sumsq, max_norm, lr, betas[0], betas[1], eps, weight_decay,
                      0, self.grad_norm, step_dev=self.step_dev, hyper_dev=self.hyper_dev, p_bf16=self.pb)
-        self.refresh_transposed()
+        # the transposed shadows are refreshed by the next forward_backward (beside its forward pass, not here)
         self.invalidate_caches()
 
     def invalidate_caches(self):
@@ -338,8 +338,11 @@ def _demo_forward(st, model, ids, age, gender, eth, ins, ds=None):
         st1 = torch.empty((B, 2), device=dev, dtype=torch.float32)
         x1b, x1f = ops.layernorm(t1, st.f(p + "attention.output.LayerNorm.weight"),
                                  st.f(p + "attention.output.LayerNorm.bias"), eps, want_f32=True, stats=st1)
-        pa_ = ops.gemm_bias_act(x1b, st.w(p + "intermediate.dense.weight"), st.f(p + "intermediate.dense.bias"))
-        h = T.gelu_fwd(pa_)
+        if B <= T.SKINNY_MAX_ROWS and FUSE_GELU:
+            pa_, h = T.linear_gelu_small(x1b, st.w(p + "intermediate.dense.weight"), st.f(p + "intermediate.dense.bias"))
+        else:
+            pa_ = ops.gemm_bias_act(x1b, st.w(p + "intermediate.dense.weight"), st.f(p + "intermediate.dense.bias"))
+            h = T.gelu_fwd(pa_)
         t2 = ops.gemm_bias_act(h, st.w(p + "output.dense.weight"), st.f(p + "output.dense.bias"), residual=x1f,
                                out_dtype=torch.float32, drop=site(f"demo.{i}.h2", ph))
         st2 = torch.empty((B, 2), device=dev, dtype=torch.float32)
@@ -353,12 +356,22 @@ def _demo_forward(st, model, ids, age, gender, eth, ins, ds=None):
     return ops.demo_add(x32, H, saved["demo_ids"], tabs), saved
 
 
+FUSE_BIAS_GRAD = os.environ.get("FAME_FUSE_BIAS_GRAD", "1") != "0"
+FUSE_GELU = os.environ.get("FAME_FUSE_GELU", "1") != "0"    # <= 32 rows: GELU forward / backward inside the skinny GEMM
+
+
 def _lin_bwd(st, wname, bname, dy_bf16, x_bf16, colsum_src=None):
     """Bias and weight gradients of y = x W^T + b into the flat gradient buffer."""
+    small = dy_bf16.shape[0] <= T.SKINNY_MAX_ROWS
+    if small and FUSE_BIAS_GRAD:
+        # <= 32 rows (demographic tower): the weight-gradient kernel also writes the bias gradient from the dY tile it
+        # has staged -- one launch instead of two on a chain that is bound by launch latency
+        T.linear_wgrad(dy_bf16, x_bf16, st.gr(wname), accumulate=False, dbias=st.gr(bname))
+        return
     T.colsum(colsum_src if colsum_src is not None else dy_bf16, st.gr(bname))
     # every weight gradient is produced exactly once per step: the <= 32-row kernel overwrites its (already zeroed)
     # slice with plain stores, the split-K tensor-core product accumulates into it with atomics
-    T.linear_wgrad(dy_bf16, x_bf16, st.gr(wname), accumulate=dy_bf16.shape[0] > T.SKINNY_MAX_ROWS)
+    T.linear_wgrad(dy_bf16, x_bf16, st.gr(wname), accumulate=not small)
 
 
 # a gradient bucket closes after each of these demographic-BERT layers (backward runs 11 -> 0, on the side stream next
@@ -422,8 +435,12 @@ def _demo_backward(st, model, saved, ddemo, reducer=None, ds=None):
             _lin_bwd(st, p + "output.dense.weight", p + "output.dense.bias", dt2m, s["h"], colsum_src=dt2f)
         else:
             _lin_bwd(st, p + "output.dense.weight", p + "output.dense.bias", dt2m, s["h"])
-        dh = T.linear_dgrad(dt2m, st.w(p + "output.dense.weight"), wT=st.wt(p + "output.dense.weight"))
-        dpre = T.gelu_bwd(s["pre"], dh)
+        if dt2m.shape[0] <= T.SKINNY_MAX_ROWS and FUSE_GELU and st.wt(p + "output.dense.weight") is not None:
+            dpre = T.linear_dgrad(dt2m, st.w(p + "output.dense.weight"), wT=st.wt(p + "output.dense.weight"), aux=s["pre"],
+                                  aux_mode=T.AUX_GELU_BWD_BF16)
+        else:
+            dh = T.linear_dgrad(dt2m, st.w(p + "output.dense.weight"), wT=st.wt(p + "output.dense.weight"))
+            dpre = T.gelu_bwd(s["pre"], dh)
         _lin_bwd(st, p + "intermediate.dense.weight", p + "intermediate.dense.bias", dpre, s["x1b"])
         dx1 = T.linear_dgrad(dpre, st.w(p + "intermediate.dense.weight"), out_dtype=torch.float32, aux=dt2f,
                              aux_mode=T.AUX_ADD_F32, wT=st.wt(p + "intermediate.dense.weight"))
@@ -605,9 +622,14 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
     = (total, bce, leddi, l1) of the GLOBAL batch."""
     st = get_state(model)
     (ids, mask, age, gender, eth, ins, lab, text, labels) = batch
-    st.zero_grad()
-    st.sumsq.zero_()
-    st.post_stream().wait_stream(torch.cuda.current_stream())
+    # off the critical path, on the third stream while the forward runs: zero the gradient buffer (53 us), refresh the
+    # transposed bf16 shadows the demographic backward reads (77 us); the backward waits for this stream below
+    post = st.post_stream()
+    post.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(post):
+        st.zero_grad()
+        st.sumsq.zero_()
+        st.refresh_transposed()
     ds = DropSites(model, st.step_dev)
     if not ds.any:
         ds = None                                                             # parity configuration / eval: no site active
@@ -659,6 +681,7 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
     # gradient SUM over ranks, bucket by bucket as the backward completes them (sig_weights, produced here by the
     # fusion head, lives in the 'rest' region and travels with the last demographic bucket)
     red = _GradReducer(st, group)
+    main.wait_stream(post)                              # gradient buffer zeroed, transposed shadows current
     ddemo, dlab = _fusion_backward(st, fo, (demo, labe, text), dlogits, w_mod, lambda_l1, d_fus)
     # the demographic tower owns 88 % of the gradient bytes: its buckets cross NVLink while the tensor-core-bound lab
     # backward runs (side stream, or simply first when single-stream)

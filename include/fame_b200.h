@@ -97,7 +97,8 @@ int fame_gemm_bias_act(const fame_gemm_args* a, void* workspace, size_t workspac
  * and, with the two batch levels (b0 = sequence, b1 = head), the five products of the attention backward.
  * aux: FAME_AUX_ADD_* adds a residual, FAME_AUX_RELU_MASK_BF16 zeroes the result where aux <= 0 (ReLU backward).
  * Strides and leading dimensions are in elements and must be multiples of 8; N % 8 == 0. */
-enum { FAME_AUX_NONE = 0, FAME_AUX_ADD_BF16 = 1, FAME_AUX_ADD_F32 = 2, FAME_AUX_RELU_MASK_BF16 = 3 };
+enum { FAME_AUX_NONE = 0, FAME_AUX_ADD_BF16 = 1, FAME_AUX_ADD_F32 = 2, FAME_AUX_RELU_MASK_BF16 = 3,
+       FAME_AUX_GELU_BWD_BF16 = 4 /* result *= gelu'(aux), aux = saved bf16 pre-activation; M <= 32 path only */ };
 typedef struct {
     const void* ptr; /* bf16 */
     int64_t ld;
@@ -123,6 +124,9 @@ typedef struct {
                         contraction runs over all tokens while the output has only a few tiles. */
     fame_dropout_cfg drop; /* dropout of the result (after alpha / bias / act, before an additive aux); K-major A,
                               unbatched, split_k = 0 only.  thresh16 = 0: none */
+    void* pre_act;         /* optional bf16 [M, ld_pre]: alpha * A B^T + bias before the activation (what the GELU backward
+                              needs); M <= 32 (weight-streaming path) only, NULL otherwise */
+    int64_t ld_pre;
 } fame_gemm_ex_args;
 int fame_gemm_ex(const fame_gemm_ex_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
 
@@ -434,9 +438,11 @@ int fame_cast_bf16(const float* x, void* y, int64_t n, fame_stream_t stream);
  *   { const bf16* src [rows, cols]; bf16* dst [cols, rows]; int32 rows, cols, tile0, tiles_x; }   (32 bytes each)
  * tile0 = index of the record's first 64x64 tile within the launch, tiles_x = ceil(cols / 64). */
 /* Weight gradient of a layer with at most 32 rows (demographic tower): dW[N,K] (+)= dY[M,N]^T . X[M,K]; bf16 operands,
- * f32 result; accumulate = 0 overwrites dW.  Bound by the gradient write, CUDA-core FMAs (skinny_gemm.cuh). */
+ * f32 result; accumulate = 0 overwrites dW.  dbias (optional, [N]): the bias gradient sum_m dY[m, n] from the same
+ * staged tile, written (or added when accumulate) by the first k-block.  Bound by the gradient write, CUDA-core FMAs
+ * (skinny_gemm.cuh). */
 int fame_wgrad_small(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, float* out, int64_t ld_out, int32_t M,
-                     int32_t N, int32_t K, int32_t accumulate, fame_stream_t stream);
+                     int32_t N, int32_t K, int32_t accumulate, float* dbias, fame_stream_t stream);
 /* Attention backward, first half (autograd of the sdpa call inside nn.MultiheadAttention, 10_FAME.py:214,445):
  * P = softmax(Q K^T scale) and dS = scale P (dO V^T - delta) per (sequence, head), both bf16 [batch, heads, seq, ldp]
  * (columns >= seq zero), from the packed qkv tensor, dO = dctx, the forward's lse and delta = rowsum(dO * O)

@@ -97,6 +97,13 @@ def test_wgrad_small(M, N, K):
     _close(out, ref, 1e-5)
     T.linear_wgrad(dy, x, out, accumulate=True)
     _close(out, 2 * ref, 1e-5)
+    # fused bias gradient (column sums of dY) from the same launch: overwrite, then accumulate
+    db = torch.full((N,), 3.0, device="cuda")
+    T.linear_wgrad(dy, x, out, accumulate=False, dbias=db)
+    _close(out, ref, 1e-5)
+    _close(db, dy.float().sum(0), 1e-5)
+    T.linear_wgrad(dy, x, out, accumulate=True, dbias=db)
+    _close(db, 2 * dy.float().sum(0), 1e-5)
 
 
 def test_transpose_table():
