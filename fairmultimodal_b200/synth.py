@@ -151,13 +151,33 @@ def behrt_combined_shapes(lab_tokens=542, hidden=768):
     return out
 
 
+def sigmoid_fusion_shapes(lab_tokens=542, hidden=768):
+    """state_dict layout of 09_multimodal_sigmoid_fusion.py's MultimodalTransformer (09:162-195): the FAME towers under
+    `BEHRT.` / `behrt_lab.` + projectors, three 256-wide sigmoid gates, aggregate_projector and classifier."""
+    full = fame_shapes(lab_tokens=lab_tokens, hidden=hidden)
+    out = OrderedDict()
+    out["sig_weights_demo"] = out["sig_weights_lab"] = out["sig_weights_text"] = (256,)   # own parameters come first
+    for k, shp in full.items():
+        if k.startswith("behrt_demo."):
+            out["BEHRT." + k[len("behrt_demo."):]] = shp
+    for k, shp in full.items():
+        if k.startswith("behrt_lab."):
+            out[k] = shp
+    for m in ("demo", "lab", "text"):
+        out[f"{m}_projector.0.weight"], out[f"{m}_projector.0.bias"] = (256, hidden), (256,)
+    out["aggregate_projector.0.weight"], out["aggregate_projector.0.bias"] = (512, 768), (512,)
+    out["classifier.0.weight"], out["classifier.0.bias"] = (512, 512), (512,)
+    out["classifier.3.weight"], out["classifier.3.bias"] = (3, 512), (3,)
+    return out
+
+
 def synth_tensor(name, shape, seed):
     rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
     x = rng.standard_normal(shape, dtype=np.float32)
     leaf = name.rsplit(".", 2)
     if name.endswith(("LayerNorm.weight", "norm1.weight", "norm2.weight")):
         return 1.0 + 0.05 * x
-    if name.endswith(("sig_weights", "pos_embedding")):
+    if name.endswith(("sig_weights", "pos_embedding")) or "sig_weights_" in name:
         return x                                         # nn.Parameter(torch.randn(...)), 10_FAME.py:213,252
     if name.endswith("token_embedding.weight"):
         return 0.5 * x                                   # Linear(1, 768): default init is U(-1, 1)

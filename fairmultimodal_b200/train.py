@@ -51,16 +51,22 @@ def _r_demo(i):
 
 
 
-def _layout_key(name):
-    """Region of the flat buffers a parameter lives in (see FlatTrainState.__init__)."""
-    if name.startswith("behrt_demo.bert.encoder.layer."):
-        i = int(name.split(".")[4])
+FAME_NAMES = dict(demo="behrt_demo.", lab="behrt_lab.",
+                  head=("demo_projector.", "lab_projector.", "text_projector.", "fusion_mlp."))
+
+
+def _layout_key(name, names=FAME_NAMES):
+    """Region of the flat buffers a parameter lives in (see FlatTrainState.__init__).  `names`: module prefixes of the
+    demographic tower, the lab tower and the head (FAME_NAMES; sigmoid_fusion.py uses the reference's other names)."""
+    enc = names["demo"] + "bert.encoder.layer."
+    if name.startswith(enc):
+        i = int(name[len(enc):].split(".")[0])
         if ".attention.self.query." in name or ".attention.self.key." in name:
             return _R_NORED
         return _r_demo(i)
-    if name.startswith("behrt_lab."):
+    if name.startswith(names["lab"]):
         return _R_LAB
-    if name.startswith(("demo_projector.", "lab_projector.", "text_projector.", "fusion_mlp.")):
+    if name.startswith(names["head"]):
         return _R_HEAD
     return _R_REST
 
@@ -68,7 +74,7 @@ def _layout_key(name):
 class DropSites:
     """Dropout sites of one training step: name -> _lib.DropoutCfg (seed per site, shared device step counter)."""
 
-    def __init__(self, model, step_dev, base_seed=0x5EED, lab_module=None, head_dropout=None):
+    def __init__(self, model, step_dev, base_seed=0x5EED, lab_module=None, head_dropout=None, demo_module=None):
         """FAME model by default; with lab_module / head_dropout given: a model that has only the lab tower and one
         nn.Dropout in its head (behrt_combined.BEHRTModel_Combined)."""
         from . import _lib
@@ -81,6 +87,10 @@ class DropSites:
             lab_module, head_dropout = model.behrt_lab, model.fusion_mlp[2]
         else:
             self.p_demo_hidden = self.p_demo_attn = 0.0
+            if demo_module is not None:
+                cfg = demo_module.bert.config
+                self.p_demo_hidden = float(getattr(cfg, "hidden_dropout_prob", 0.0)) if active else 0.0
+                self.p_demo_attn = float(getattr(cfg, "attention_probs_dropout_prob", 0.0)) if active else 0.0
         self.lab = []
         for l in lab_module.transformer_encoder.layers:
             self.lab.append(dict(attn=float(l.self_attn.dropout) if active else 0.0, d1=float(l.dropout1.p) if active else 0.0,
@@ -114,12 +124,12 @@ class DropSites:
         return 1.0 if c is None else 65536.0 / (65536.0 - c.thresh16)
 
 
-def plan_layout(named_sizes):
+def plan_layout(named_sizes, names=FAME_NAMES):
     """[(name, numel)] sorted by region -> (offsets {name: first element}, regions {region: (lo, hi)}, total)."""
     offsets, region, off = {}, {}, 0
     for n, k in named_sizes:
         offsets[n] = off
-        r = _layout_key(n)
+        r = _layout_key(n, names)
         lo, _ = region.get(r, (off, off))
         off += (k + 7) // 8 * 8                                  # 32-byte aligned segments
         region[r] = (lo, off)
@@ -143,11 +153,12 @@ def plan_buckets(region, total):
 class FlatTrainState:
     """Flat parameter / gradient / AdamW-state buffers for one MultimodalTransformer_EDDI_Sigmoid."""
 
-    def __init__(self, model, no_grad_prefixes=NO_GRAD_PREFIXES, fame_layout=True):
+    def __init__(self, model, no_grad_prefixes=NO_GRAD_PREFIXES, fame_layout=True, names=FAME_NAMES):
         """fame_layout: the region / bucket layout of MultimodalTransformer_EDDI_Sigmoid (below).  Other models
         (behrt_combined.BEHRTModel_Combined) use module order and a single all-reduce bucket."""
         self.model = model
         self.fame_layout = fame_layout
+        self.names = names
         dev = next(model.parameters()).device
         named = [(n, p) for n, p in model.named_parameters() if not (no_grad_prefixes and n.startswith(no_grad_prefixes))]
         # Layout = the order in which the backward completes gradients, so that every all-reduce bucket is ONE
@@ -155,8 +166,8 @@ class FlatTrainState:
         # projections of the demographic BERT -- with its length-1 sequences the softmax is identically 1, their
         # gradient is exactly zero on every rank (never written); 57 MB that need not cross NVLink.
         if fame_layout:
-            named.sort(key=lambda np_: _layout_key(np_[0]))      # stable: module order inside each region
-        self.offsets, self.region, self.n = plan_layout([(n, p.numel()) for n, p in named])
+            named.sort(key=lambda np_: _layout_key(np_[0], names))   # stable: module order inside each region
+        self.offsets, self.region, self.n = plan_layout([(n, p.numel()) for n, p in named], names)
         off = self.n
         self.p = torch.zeros(off, device=dev, dtype=torch.float32)
         self.g = torch.zeros(off, device=dev, dtype=torch.float32)
@@ -191,7 +202,8 @@ class FlatTrainState:
 
     def _build_transposed_shadows(self, dev):
         import numpy as np
-        names = [n for n in self.offsets if n.startswith("behrt_demo.bert.encoder.layer.") and n.endswith(self._T_SUFFIXES)]
+        enc = self.names["demo"] + "bert.encoder.layer."
+        names = [n for n in self.offsets if n.startswith(enc) and n.endswith(self._T_SUFFIXES)]
         total = sum(self.views[n].numel() for n in names)
         self.pbT = torch.zeros(max(total, 8), device=dev, dtype=torch.bfloat16)
         self.tviews = {}
@@ -302,14 +314,15 @@ def get_state(model) -> FlatTrainState:
 
 
 # ------------------------------------------------------------------------------------------------ demo tower
-def _demo_forward(st, model, ids, age, gender, eth, ins, ds=None):
+def _demo_forward(st, model, ids, age, gender, eth, ins, ds=None, demo_module=None, dpre="behrt_demo."):
     """BEHRTModel_Demo.forward for training (sequence length 1): returns (demo_emb f32 [B,768], saved)."""
-    pre = "behrt_demo.bert."
+    demo_module = model.behrt_demo if demo_module is None else demo_module
+    pre = dpre + "bert."
     B, S = ids.shape
     if S != 1:
         raise NotImplementedError("training path of the demographic encoder handles the reference's length-1 input")
     H = 768
-    eps = model.behrt_demo.bert.config.layer_norm_eps
+    eps = demo_module.bert.config.layer_norm_eps
     dev = ids.device
     ph = ds.p_demo_hidden if ds is not None else 0.0
     pa = ds.p_demo_attn if ds is not None else 0.0
@@ -351,7 +364,7 @@ def _demo_forward(st, model, ids, age, gender, eth, ins, ds=None):
         s.update(v=v, t1=t1, st1=st1, x1b=x1b, pre=pa_, h=h, t2=t2, st2=st2)
         saved["layers"].append(s)
     did = [age, gender, eth, ins]
-    tabs = [st.f(f"behrt_demo.{n}_embedding.weight") for n in ("age", "gender", "ethnicity", "insurance")]
+    tabs = [st.f(f"{dpre}{n}_embedding.weight") for n in ("age", "gender", "ethnicity", "insurance")]
     saved["demo_ids"] = [t.to(torch.int64).contiguous() for t in did]
     return ops.demo_add(x32, H, saved["demo_ids"], tabs), saved
 
@@ -414,12 +427,12 @@ class _GradReducer:
         self.st.sumsq_valid = True
 
 
-def _demo_backward(st, model, saved, ddemo, reducer=None, ds=None):
-    pre = "behrt_demo.bert."
+def _demo_backward(st, model, saved, ddemo, reducer=None, ds=None, dpre="behrt_demo."):
+    pre = dpre + "bert."
     ph = ds.p_demo_hidden if ds is not None else 0.0
     pa = ds.p_demo_attn if ds is not None else 0.0
     site = (lambda n, p, g=0: ds.site(n, p, g)) if ds is not None else (lambda n, p, g=0: None)
-    tabs_g = [st.gr(f"behrt_demo.{n}_embedding.weight") for n in ("age", "gender", "ethnicity", "insurance")]
+    tabs_g = [st.gr(f"{dpre}{n}_embedding.weight") for n in ("age", "gender", "ethnicity", "insurance")]
     T.demo_add_bwd(ddemo, saved["demo_ids"], tabs_g)
     dx = ddemo                                                      # f32 [B,768]: gradient of the last hidden state
     for i in reversed(range(12)):

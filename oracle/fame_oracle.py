@@ -139,6 +139,21 @@ def behrt_combined_loss(logits, labels, pos_weight):
     return total
 
 
+def sigmoid_fusion_forward(sd, batch8):
+    """MultimodalTransformer.forward of 09_multimodal_sigmoid_fusion.py:186-222, eval mode: (logits [B,3], aggregated)."""
+    ids, mask, age, gender, eth, ins, lab, text = batch8
+    d = behrt_demo(sd, ids, mask, age, gender, eth, ins, prefix="BEHRT.")
+    l = behrt_lab(sd, lab)
+    parts = []
+    for m, e in (("demo", d), ("lab", l), ("text", text)):
+        pr = torch.relu(F.linear(e, sd[f"{m}_projector.0.weight"].float(), sd[f"{m}_projector.0.bias"].float()))
+        parts.append(pr * torch.sigmoid(sd[f"sig_weights_{m}"].float()))
+    agg = torch.relu(F.linear(torch.cat(parts, dim=1), sd["aggregate_projector.0.weight"].float(),
+                              sd["aggregate_projector.0.bias"].float()))
+    hid = torch.relu(F.linear(agg, sd["classifier.0.weight"].float(), sd["classifier.0.bias"].float()))
+    return F.linear(hid, sd["classifier.3.weight"].float(), sd["classifier.3.bias"].float()), agg
+
+
 def text_classifier(sd, x):
     """UnstructuredClassifier.forward (02_BioClinicalBERT.py:122-134), eval mode: logits f32 [B, 3]."""
     h = torch.relu(F.linear(x, sd["classifier.0.weight"].float(), sd["classifier.0.bias"].float()))

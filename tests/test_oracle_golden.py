@@ -253,3 +253,40 @@ def test_text_classifier_oracle_vs_reference_golden(golden_dir):
     for k in TEXT_SHAPES:
         ref = g["after." + k]
         np.testing.assert_allclose(params[k].numpy()[:ref.shape[0]], ref, rtol=1e-4, atol=2e-6)
+
+
+def _sigfusion_inputs(g, L):
+    import torch
+    from fairmultimodal_b200 import synth
+    co = synth.make_cohort(g["labels"].shape[0], lab_tokens=L, chunks=0, with_tokens=False, seed=int(g["cohort_seed"]))
+    t = lambda k: torch.from_numpy(co[k])
+    assert np.array_equal(co["labels"], g["labels"])
+    return (t("demo_dummy_ids"), t("demo_attn_mask"), t("age_ids"), t("gender_ids"), t("ethnicity_ids"), t("insurance_ids"),
+            t("lab_features"), torch.from_numpy(g["text"])), t("labels")
+
+
+def test_sigmoid_fusion_oracle_vs_reference_golden(golden_dir):
+    """Per-modality sigmoid-gate ablation (09_multimodal_sigmoid_fusion.py): oracle forward, summed
+    focal loss (gamma 1) and autograd gradients against the unmodified reference."""
+    import os
+    import torch
+    from fairmultimodal_b200 import synth
+    from oracle import fame_oracle as O
+    g = np.load(os.path.join(golden_dir, "sigmoid_fusion.npz"))
+    L = 24
+    sd = {k: torch.from_numpy(v).clone().requires_grad_(True)
+          for k, v in synth.synth_state_dict(synth.sigmoid_fusion_shapes(lab_tokens=L), 17).items()}
+    batch8, labels = _sigfusion_inputs(g, L)
+    logits, agg = O.sigmoid_fusion_forward(sd, batch8)
+    np.testing.assert_allclose(logits.detach().numpy(), g["logits_eval"], atol=3e-5, rtol=1e-4)
+    np.testing.assert_allclose(agg.detach().numpy(), g["agg_eval"], atol=3e-5, rtol=1e-4)
+    loss = O.text_classifier_loss(logits, labels, torch.from_numpy(g["pos_weight"]), gamma=1.0)
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    loss.backward()
+    names = [str(n) for n in g["gnorm_names"]]
+    got = np.array([sd[n].grad.norm().item() if sd[n].grad is not None else 0.0 for n in names])
+    np.testing.assert_allclose(got, g["gnorm"], rtol=5e-3, atol=1e-7)
+    assert sorted(str(n) for n in g["none_grad"]) == ["BEHRT.bert.pooler.dense.bias", "BEHRT.bert.pooler.dense.weight"]
+    for k in g.files:
+        if k.startswith("grad."):
+            np.testing.assert_allclose(sd[k[5:]].grad.numpy(), g[k], rtol=5e-3, atol=1e-6)
