@@ -131,3 +131,35 @@ def test_flat_layout_and_gradient_buckets():
     spans = list(cuts.values())
     assert spans[0][0] == region[train._R_NORED][1] and spans[-1][1] == total
     assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_dropout_sites_follow_the_model_configuration():
+    """Host logic of the training-step dropout: probabilities are read from the model exactly where the reference keeps
+    them (BertConfig, nn.Dropout, nn.MultiheadAttention.dropout), eval mode and set_dropout(0) switch every site off,
+    thresholds are round(p * 65536), seeds differ per site and are stable."""
+    from fairmultimodal_b200 import modules, train
+    model = modules.MultimodalTransformer_EDDI_Sigmoid(768, modules.BEHRTModel_Demo(5, 2, 5, 5), modules.BEHRTModel_Lab(12), "cpu")
+    step = torch.zeros(1, dtype=torch.int32)
+    model.train()
+    ds = train.DropSites(model, step)
+    assert ds.any and ds.p_demo_hidden == 0.1 and ds.p_demo_attn == 0.1 and ds.p_fusion == 0.1
+    assert ds.lab == [dict(attn=0.1, d1=0.1, act=0.1, d2=0.1)] * 2
+    a, b = ds.site("lab.0.d1", 0.1), ds.site("lab.1.d1", 0.1)
+    assert a.thresh16 == 6554 and a.seed != b.seed and a.group_shift == 0 and a.step == step.data_ptr()
+    assert ds.site("lab.0.d1", 0.1) is a                          # cached: same struct, same seed
+    assert ds.site("demo.3.attn", 0.1, 6).group_shift == 6
+    assert ds.site("x", 0.0) is None
+    assert abs(train.DropSites.inv_keep(a) - 65536 / (65536 - 6554)) < 1e-12 and train.DropSites.inv_keep(None) == 1.0
+    with pytest.raises(ValueError):
+        ds.site("bad", 1.0)
+    model.behrt_lab.transformer_encoder.layers[1].dropout2.p = 0.25
+    model.behrt_demo.bert.config.attention_probs_dropout_prob = 0.0
+    ds2 = train.DropSites(model, step)
+    assert ds2.lab[1]["d2"] == 0.25 and ds2.p_demo_attn == 0.0 and ds2.key() != ds.key()
+    model.eval()
+    assert not train.DropSites(model, step).any
+    model.train()
+    modules.set_dropout(model, 0.0)
+    assert not train.DropSites(model, step).any
+    modules.set_dropout(model, 0.1)
+    assert train.DropSites(model, step).key() == ds.key()
