@@ -290,3 +290,41 @@ def test_sigmoid_fusion_oracle_vs_reference_golden(golden_dir):
     for k in g.files:
         if k.startswith("grad."):
             np.testing.assert_allclose(sd[k[5:]].grad.numpy(), g[k], rtol=5e-3, atol=1e-6)
+
+
+def test_host_metric_formulas_from_counts_match_reference(golden_dir):
+    """Host half of the evaluation path (metrics.py: calibrated thresholds from the sweep histogram, EDDI, Equalized
+    Odds, F1 / TPR / FPR / precision, the dynamic weight update) driven by the numpy restatement of the count kernel's
+    vector, against the unmodified reference's numbers."""
+    import os
+    from fairmultimodal_b200 import metrics as M
+    from oracle import count_vector as CV
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    attrs = [g["age"], g["eth"], g["ins"]]
+    names = M.OUTCOMES
+    c0 = M.Counts(CV.eval_count_vector(g["logits"], g["labels"], attrs, (0.5, 0.5, 0.5), sweep=np.linspace(0, 1, 101)))
+    th = M.thresholds_from_hist(c0.hist)
+    np.testing.assert_array_equal([th[n] for n in names], g["thresholds"])
+    c = M.Counts(CV.eval_count_vector(g["logits"], g["labels"], attrs, [th[n] for n in names]))
+    assert c.n == len(g["labels"])
+    for o in range(3):
+        tp, fn, fp, tn = (int(x) for x in c.tot[o])
+        assert M._f1(tp, fp, fn) == pytest.approx(float(g["f1"][o]), abs=1e-12)
+        assert tp / (tp + fn) == pytest.approx(float(g["tpr"][o]), abs=1e-15)
+        assert fp / (fp + tn) == pytest.approx(float(g["fpr"][o]), abs=1e-15)
+        assert tp / (tp + fp) == pytest.approx(float(g["precision"][o]), abs=1e-12)
+        eos = []
+        for a, groups in enumerate((M.AGE_GROUPS, M.ETH_GROUPS, M.INS_GROUPS)):
+            dt, df, eo, _, _ = M.eo_from_counts(c.conf[o, a])
+            assert (dt, df, eo) == pytest.approx((g["tpr_diff"][o, a], g["fpr_diff"][o, a], g["eo"][o, a]), abs=1e-14)
+            eos.append(eo)
+            assert M.eddi_from_counts(c.conf[o, a], c.tot[o], groups)[0] == pytest.approx(float(g["eddi"][o, a]), abs=1e-14)
+        assert float(np.mean(eos)) == pytest.approx(float(g["overall_eo"][o]), abs=1e-14)
+    # dynamic weight update from the modality logits (two epochs)
+    counts = {m: M.Counts(CV.eval_count_vector(g["mod_logits"][:, 3 * i:3 * i + 3], g["labels"], attrs, (0.5,) * 3))
+              for i, m in enumerate(M.MODALITIES)}
+    w0 = {n: {m: 0.33 for m in M.MODALITIES} for n in names}
+    w1 = M.weights_from_modality_counts(counts, w0, 1.0, verbose=False)
+    w2 = M.weights_from_modality_counts(counts, w1, 1.0, verbose=False)
+    np.testing.assert_allclose([[w1[n][m] for m in M.MODALITIES] for n in names], g["weights_epoch1"], atol=1e-14)
+    np.testing.assert_allclose([[w2[n][m] for m in M.MODALITIES] for n in names], g["weights_epoch2"], atol=1e-14)
