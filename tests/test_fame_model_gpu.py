@@ -183,6 +183,21 @@ def test_metrics_match_reference_golden(golden_dir):
     np.testing.assert_allclose([[w2[n][m] for m in M.MODALITIES] for n in NAMES], g["weights_epoch2"], atol=1e-14)
 
 
+def test_count_vector_bit_exact_vs_restatement(golden_dir):
+    """All 914 integers of fame_eval_counts (confusion cells, totals, the 101-threshold F1 histogram, sample count)
+    equal the numpy restatement that the CPU suite feeds to the host formulas."""
+    from fairmultimodal_b200 import ops
+    from oracle import count_vector as CV
+    g = _golden(golden_dir, "metrics.npz")
+    attrs_np = [g["age"], g["eth"], g["ins"]]
+    attrs = [torch.from_numpy(a).cuda() for a in attrs_np]
+    sweep = np.linspace(0, 1, 101)
+    for logits, thr in ((g["logits"], (0.5, 0.5, 0.5)), (g["logits"], (0.23, 0.61, 0.5)), (g["mod_logits"][:, 3:6], (0.4, 0.5, 0.7))):
+        got = ops.eval_counts(torch.from_numpy(np.ascontiguousarray(logits)).cuda(), torch.from_numpy(g["labels"]).cuda(),
+                              attrs, thr, sweep=torch.from_numpy(sweep).cuda()).cpu().numpy()
+        np.testing.assert_array_equal(got, CV.eval_count_vector(logits, g["labels"], attrs_np, thr, sweep=sweep))
+
+
 def test_compute_eddi_dropin_and_counts_vs_oracle():
     from fairmultimodal_b200 import metrics as M, ops, synth
     from oracle import fame_oracle as O
