@@ -80,3 +80,20 @@ def test_synth_cohort_shapes():
     assert (co["input_ids"][range(C), v - 1] == synth.SEP_ID).all()
     assert ((co["attention_mask"].sum(1)) == v).all()
     assert co["insurance_ids"].max() <= 4 and co["age_ids"].max() <= 4
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path for the note-chunk step, oracle port) runs without a GPU and
+    prints ONE JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-chunks-per-step", "1"], capture_output=True, text=True, timeout=600, check=True).stdout
+    lines = [l for l in out.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "chunks/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["steps"] == 1 and d["n_gpus"] == 1 and d["config"]["workload"].startswith("note_encoder_fwd")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
