@@ -80,6 +80,15 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """Host threads available to this process.  torchrun exports OMP_NUM_THREADS=1 to every rank, which would time the
+    reference arm on one core: the CPU legs set the thread count explicitly instead."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_chunks_per_s(n_chunks, threads=None):
     """The reference's CPU path for this workload: BioClinicalBERT_FT.forward on ONE chunk per call (10_FAME.py:
     157-169), fp32, eager -- as restated by oracle/fame_oracle.py (the reference script itself cannot travel to
@@ -89,8 +98,7 @@ def cpu_reference_chunks_per_s(n_chunks, threads=None):
     from fairmultimodal_b200 import synth
     from oracle import fame_oracle as O
 
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or host_threads())
     sd = {k: torch.from_numpy(v) for k, v in
           synth.synth_state_dict(synth.bert_shapes("BioBert.", synth.VOCAB), WSEED).items()}
     co = synth.make_cohort(max(1, (n_chunks + 3) // 4), lab_tokens=4, chunks="fixed4", seq_len=SEQ, seed=1234)
@@ -115,8 +123,7 @@ def cpu_reference_train_patients_per_s(steps=1, threads=None):
     from fairmultimodal_b200 import synth
     from oracle import fame_oracle as O
 
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or host_threads())
     shapes = synth.fame_shapes(lab_tokens=TRAIN_L)
     sd = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in synth.synth_state_dict(shapes, 4).items()}
     co = synth.make_cohort(TRAIN_B, lab_tokens=TRAIN_L, chunks=0, with_tokens=False, seed=77)
