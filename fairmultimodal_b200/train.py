@@ -194,6 +194,9 @@ class FlatTrainState:
         self.graphs = {}
         self._build_transposed_shadows(dev)
         self.refresh_bf16()
+        self._params = [p for _, p in named]
+        self._view_ptrs = [self.views[n].data_ptr() for n, _ in named]
+        self._versions = self._param_versions()
 
     # weights of the demographic tower whose data-gradient product runs on the <= 32-row skinny path: dX = dY . W reads
     # W^T rows, so a transposed bf16 shadow is kept next to the plain one (one table-driven transpose launch per step)
@@ -232,6 +235,24 @@ class FlatTrainState:
         cuts = plan_buckets(self.region, self.n) if self.fame_layout else {"tail": (0, self.n)}
         self._buckets = cuts
         return cuts
+
+    def _param_versions(self):
+        return tuple(p._version for p in self._params)
+
+    def aliased(self):
+        """False once the module's parameters stopped being views of the flat buffer (e.g. model.to(other_device) or a
+        parameter was re-assigned): the state must then be rebuilt."""
+        return all(p.data_ptr() == ptr for p, ptr in zip(self._params, self._view_ptrs))
+
+    def sync_external_updates(self):
+        """The kernels update the flat fp32 buffer behind torch's back (no version bump), so a changed `_version` means
+        that somebody ELSE wrote the parameters in place -- load_state_dict(), an initialiser, p.copy_() under no_grad.
+        The bf16 shadows the tensor cores read are then stale: refresh them (one cast pass) before the next step."""
+        v = self._param_versions()
+        if v != self._versions:
+            self.refresh_bf16()
+            self.invalidate_caches()
+            self._versions = v
 
     def side_stream(self):
         if getattr(self, "_side", None) is None:
@@ -307,7 +328,7 @@ def release_graphs(model):
 
 def get_state(model) -> FlatTrainState:
     st = getattr(model, "_fame_train_state", None)
-    if st is None or st.model is not model:
+    if st is None or st.model is not model or not st.aliased():
         st = FlatTrainState(model)
         object.__setattr__(model, "_fame_train_state", st)
     return st
@@ -758,6 +779,7 @@ def optimisation_step(model, batch, pw, lambda_edd, lambda_l1, w_mod, hp, group=
     a CUDA graph per batch shape (first call of a shape runs eagerly, the second captures, later ones replay): at
     32 patients per GPU the step is otherwise bound by host launch overhead, not by the GPU."""
     st = get_state(model)
+    st.sync_external_updates()                 # e.g. load_state_dict() between two steps
     use_graph = USE_CUDA_GRAPH if use_graph is None else use_graph
     if group is not None and not _GRAPH_WITH_COLLECTIVES:
         use_graph = False

@@ -163,3 +163,38 @@ def test_dropout_sites_follow_the_model_configuration():
     assert not train.DropSites(model, step).any
     modules.set_dropout(model, 0.1)
     assert train.DropSites(model, step).key() == ds.key()
+
+
+def test_flat_train_state_host_logic(monkeypatch):
+    """Host side of the flat training state (device kernels stubbed out): module parameters and gradients alias the
+    flat buffers at the planned offsets, parameters without gradient in the reference are left out, an in-place update
+    from outside (load_state_dict) is detected through the version counters and refreshes the bf16 shadows exactly
+    once, and a parameter that stops aliasing the buffer invalidates the state."""
+    from fairmultimodal_b200 import modules, ops_train, train
+    calls = {"cast": 0, "transpose": 0}
+    monkeypatch.setattr(ops_train, "cast_bf16", lambda *a, **k: calls.__setitem__("cast", calls["cast"] + 1))
+    monkeypatch.setattr(ops_train, "transpose_bf16_table", lambda *a, **k: calls.__setitem__("transpose", calls["transpose"] + 1))
+    model = modules.MultimodalTransformer_EDDI_Sigmoid(768, modules.BEHRTModel_Demo(5, 2, 5, 5), modules.BEHRTModel_Lab(12), "cpu")
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    st = train.get_state(model)
+    assert calls == {"cast": 1, "transpose": 1}
+    assert train.get_state(model) is st and st.aliased()
+    named = dict(model.named_parameters())
+    assert not any(n.startswith(train.NO_GRAD_PREFIXES) for n in st.offsets)
+    assert set(st.offsets) == {n for n in named if not n.startswith(train.NO_GRAD_PREFIXES)}
+    for n in ("sig_weights", "behrt_lab.pos_embedding", "fusion_mlp.3.bias", "behrt_demo.bert.encoder.layer.5.output.dense.weight"):
+        o, k = st.offsets[n], named[n].numel()
+        assert named[n].data_ptr() == st.p[o:o + k].data_ptr() and named[n].grad.data_ptr() == st.g[o:o + k].data_ptr()
+        assert torch.equal(named[n].detach().reshape(-1), st.p[o:o + k]) and torch.equal(st.f(n), sd0[n])
+    assert model.classifier_demo.weight.grad is None               # outside the loss path: untouched, as torch leaves it
+    st.sync_external_updates()
+    assert calls["cast"] == 1                                       # nothing changed
+    sd1 = {k: v + 1.0 for k, v in sd0.items()}
+    model.load_state_dict(sd1)                                      # in place: the views still alias the flat buffer
+    assert st.aliased() and torch.equal(st.f("sig_weights"), sd1["sig_weights"])
+    st.sync_external_updates()
+    st.sync_external_updates()
+    assert calls["cast"] == 2 and calls["transpose"] == 2           # shadows refreshed exactly once
+    model.sig_weights.data = model.sig_weights.data.clone()         # stops aliasing -> a new state is built
+    assert not st.aliased()
+    assert train.get_state(model) is not st
