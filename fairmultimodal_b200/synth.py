@@ -171,6 +171,25 @@ def sigmoid_fusion_shapes(lab_tokens=542, hidden=768):
     return out
 
 
+def eddi_fusion_shapes(lab_tokens=542, hidden=768, demo_layers=6):
+    """state_dict layout of 08_multimodal_eddi_fusion.py's MultimodalTransformer (08:314-346): a SIX-layer demographic
+    BERT (08:264-267: 6 layers, 6 heads, 128 positions) + the lab tower + three projectors + nine scalar heads
+    classifier_{demo,lab,text}_{mort,los,mv}."""
+    full = fame_shapes(lab_tokens=lab_tokens, hidden=hidden)
+    out = OrderedDict()
+    for k, shp in full.items():
+        if k.startswith("behrt_demo.bert.encoder.layer.") and int(k.split(".")[4]) >= demo_layers:
+            continue
+        if k.startswith(("behrt_demo.", "behrt_lab.")):
+            out[k] = (128, hidden) if k.endswith("position_embeddings.weight") else shp   # max_position_embeddings=128
+    for m in ("demo", "lab", "text"):
+        out[f"{m}_projector.0.weight"], out[f"{m}_projector.0.bias"] = (256, hidden), (256,)
+    for o in ("mort", "los", "mv"):
+        for m in ("demo", "lab", "text"):
+            out[f"classifier_{m}_{o}.weight"], out[f"classifier_{m}_{o}.bias"] = (1, 256), (1,)
+    return out
+
+
 def synth_tensor(name, shape, seed):
     rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
     x = rng.standard_normal(shape, dtype=np.float32)

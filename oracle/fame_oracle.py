@@ -89,11 +89,11 @@ def pool_patient_notes(cls_rows, offsets, hidden=768):
     return out
 
 
-def behrt_demo(sd, input_ids, attention_mask, age, gender, eth, ins, prefix="behrt_demo."):
+def behrt_demo(sd, input_ids, attention_mask, age, gender, eth, ins, prefix="behrt_demo.", num_layers=12, num_heads=12):
     """BEHRTModel_Demo.forward (FAME:194-206)."""
     tab = {n: sd[prefix + n + "_embedding.weight"].float() for n in ("age", "gender", "ethnicity", "insurance")}
     cl = lambda ids, t: ids.clamp(0, t.shape[0] - 1)
-    cls = bert_encode(sd, prefix + "bert.", input_ids, attention_mask)[:, 0, :]
+    cls = bert_encode(sd, prefix + "bert.", input_ids, attention_mask, num_layers=num_layers, num_heads=num_heads)[:, 0, :]
     extra = (tab["age"][cl(age, tab["age"])] + tab["gender"][cl(gender, tab["gender"])]
              + tab["ethnicity"][cl(eth, tab["ethnicity"])] + tab["insurance"][cl(ins, tab["insurance"])]) / 4.0
     return cls + extra
@@ -152,6 +152,50 @@ def sigmoid_fusion_forward(sd, batch8):
                               sd["aggregate_projector.0.bias"].float()))
     hid = torch.relu(F.linear(agg, sd["classifier.0.weight"].float(), sd["classifier.0.bias"].float()))
     return F.linear(hid, sd["classifier.3.weight"].float(), sd["classifier.3.bias"].float()), agg
+
+
+def eddi_08(y_true, y_prob, sensitive, threshold=0.5):
+    """compute_eddi of 08_multimodal_eddi_fusion.py:45-59 (np.unique groups; NaN-free here; sum, not nansum)."""
+    pred = (y_prob > threshold).astype(int)
+    err = np.mean(pred != y_true)
+    denom = max(err, 1 - err) if err not in [0, 1] else 1.0
+    groups = np.unique(sensitive)
+    sub = [(np.mean(pred[sensitive == g] != y_true[sensitive == g]) - err) / denom for g in groups]
+    return float(np.sqrt(np.sum(np.array(sub) ** 2)) / len(groups))
+
+
+def eddi_fusion_forward(sd, batch8, labels=None, sensitive=None, beta=0.3, old_weights=None):
+    """MultimodalTransformer.forward of 08_multimodal_eddi_fusion.py:348-449: per outcome, the three modality logits are
+    fused with weights  w_m = (old_w_m | 0.33) + beta * (max_m' EDDI_m' - EDDI_m), where EDDI_m is computed INSIDE the
+    forward from the batch's thresholded modality predictions over `sensitive` (the weights are constants for autograd).
+    labels f32 [B,3] / sensitive int [B] may be None (EDDI = 0).  Returns (logits [B,3], weights [3][3], eddi [3][3])."""
+    ids, mask, age, gender, eth, ins, lab, text = batch8
+    d = behrt_demo(sd, ids, mask, age, gender, eth, ins, num_layers=6, num_heads=6)       # 08:264-265
+    l = behrt_lab(sd, lab)
+    proj = {}
+    for m, e in (("demo", d), ("lab", l), ("text", text)):
+        proj[m] = torch.relu(F.linear(e, sd[f"{m}_projector.0.weight"].float(), sd[f"{m}_projector.0.bias"].float()))
+    logits, weights, eddis = [], [], []
+    for oi, o in enumerate(("mort", "los", "mv")):
+        raw = {m: F.linear(proj[m], sd[f"classifier_{m}_{o}.weight"].float(), sd[f"classifier_{m}_{o}.bias"].float())
+               for m in ("demo", "lab", "text")}
+        if labels is not None and sensitive is not None:
+            y = np.asarray(labels[:, oi])
+            e = [eddi_08(y, torch.sigmoid(raw[m].detach()).numpy().squeeze(), np.asarray(sensitive)) for m in ("demo", "lab", "text")]
+        else:
+            e = [0.0, 0.0, 0.0]
+        top = max(e)
+        base = old_weights[oi] if old_weights is not None else (0.33, 0.33, 0.33)
+        w = [base[k] + beta * (top - e[k]) for k in range(3)]
+        logits.append(raw["demo"] * w[0] + raw["lab"] * w[1] + raw["text"] * w[2])
+        weights.append(w)
+        eddis.append(e)
+    return torch.cat(logits, dim=1), weights, eddis
+
+
+def eddi_fusion_loss(logits, labels, pos_weight, loss_gamma=1.0, target=1.0, gamma=1.0):
+    """train_step objective of 08:475-479: three FocalLoss(gamma=1, pos_weight_i) + loss_gamma * mean((mort - target)^2)."""
+    return text_classifier_loss(logits, labels, pos_weight, gamma) + loss_gamma * ((logits[:, 0:1] - target) ** 2).mean()
 
 
 def text_classifier(sd, x):

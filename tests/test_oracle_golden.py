@@ -328,3 +328,43 @@ def test_host_metric_formulas_from_counts_match_reference(golden_dir):
     w2 = M.weights_from_modality_counts(counts, w1, 1.0, verbose=False)
     np.testing.assert_allclose([[w1[n][m] for m in M.MODALITIES] for n in names], g["weights_epoch1"], atol=1e-14)
     np.testing.assert_allclose([[w2[n][m] for m in M.MODALITIES] for n in names], g["weights_epoch2"], atol=1e-14)
+
+
+def test_eddi_fusion_oracle_vs_reference_golden(golden_dir):
+    """Per-batch EDDI-weighted logit fusion (08_multimodal_eddi_fusion.py; B200 implementation: next
+    round): oracle forward with the in-forward EDDI (integer error counts -> weights bit-exact in float64), the focal +
+    (mortality logit - target)^2 objective and autograd gradients against the unmodified reference."""
+    import os
+    import torch
+    from fairmultimodal_b200 import synth
+    from oracle import fame_oracle as O
+    g = np.load(os.path.join(golden_dir, "eddi_fusion.npz"))
+    L = 24
+    w = synth.synth_state_dict(synth.eddi_fusion_shapes(lab_tokens=L), 23)
+    for k in w:
+        if k.startswith("classifier_") and k.endswith("weight"):
+            w[k] = w[k] * float(g["head_scale"])
+    sd = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in w.items()}
+    co = synth.make_cohort(g["labels"].shape[0], lab_tokens=L, chunks=0, with_tokens=False, seed=int(g["cohort_seed"]))
+    t = lambda k: torch.from_numpy(co[k])
+    batch8 = (t("demo_dummy_ids"), t("demo_attn_mask"), t("age_ids"), t("gender_ids"), t("ethnicity_ids"), t("insurance_ids"),
+              t("lab_features"), torch.from_numpy(g["text"]))
+    labels = t("labels")
+    old = [tuple(r) for r in g["old_weights"]]
+    plain, w0, e0 = O.eddi_fusion_forward(sd, batch8)
+    np.testing.assert_allclose(plain.detach().numpy(), g["logits_plain"], atol=3e-5, rtol=1e-4)
+    assert w0 == [[0.33, 0.33, 0.33]] * 3 and e0 == [[0.0, 0.0, 0.0]] * 3
+    logits, wts, eddi = O.eddi_fusion_forward(sd, batch8, co["labels"], co["gender_ids"], beta=0.3, old_weights=old)
+    np.testing.assert_allclose(np.array(eddi), g["eddi"], atol=1e-15)              # integer counts -> exact
+    np.testing.assert_allclose(np.array(wts), g["weights"], atol=1e-15)
+    np.testing.assert_allclose(logits.detach().numpy(), g["logits"], atol=3e-5, rtol=1e-4)
+    loss = O.eddi_fusion_loss(logits, labels, torch.from_numpy(g["pos_weight"]), loss_gamma=1.0, target=1.0, gamma=1.0)
+    assert abs(loss.item() - float(g["loss"])) < 2e-5 and abs(loss.item() - float(g["epoch_loss"])) < 2e-5
+    loss.backward()
+    names = [str(n) for n in g["gnorm_names"]]
+    got = np.array([sd[n].grad.norm().item() if sd[n].grad is not None else 0.0 for n in names])
+    # query / key projections of the length-1 demographic sequences: exactly zero here, 1e-7 noise in torch's sdpa backward
+    np.testing.assert_allclose(got, g["gnorm"], rtol=5e-3, atol=1e-5 * float(g["gnorm"].max()))
+    for k in g.files:
+        if k.startswith("grad."):
+            np.testing.assert_allclose(sd[k[5:]].grad.numpy(), g[k], rtol=5e-3, atol=1e-5)
