@@ -190,6 +190,23 @@ def eddi_fusion_shapes(lab_tokens=542, hidden=768, demo_layers=6):
     return out
 
 
+def average_fusion_shapes(num_diseases=10, num_ages=5, num_segments=2, num_adm=4, num_disch=6, num_genders=2, num_eth=5,
+                          num_ins=5, hidden=768):
+    """state_dict layout of 07_multimodal_average_fusion.py's MultimodalTransformer (07:156-238): BEHRT = a 12-layer BERT
+    + SEVEN embedding tables (age, segment, admission location, discharge location, gender, ethnicity, insurance),
+    ts_linear / text_linear 768 -> 256 and a 512 -> 512 -> 3 classifier."""
+    out = OrderedDict()
+    out.update(bert_shapes("BEHRT.bert.", num_diseases + num_ages + num_segments + num_adm + num_disch + 2, hidden))
+    for n, k in (("age", num_ages), ("segment", num_segments), ("admission_loc", num_adm), ("discharge_loc", num_disch),
+                 ("gender", num_genders), ("ethnicity", num_eth), ("insurance", num_ins)):
+        out[f"BEHRT.{n}_embedding.weight"] = (k, hidden)
+    out["ts_linear.weight"], out["ts_linear.bias"] = (256, hidden), (256,)
+    out["text_linear.weight"], out["text_linear.bias"] = (256, hidden), (256,)
+    out["classifier.0.weight"], out["classifier.0.bias"] = (512, 512), (512,)
+    out["classifier.3.weight"], out["classifier.3.bias"] = (3, 512), (3,)
+    return out
+
+
 def synth_tensor(name, shape, seed):
     rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
     x = rng.standard_normal(shape, dtype=np.float32)

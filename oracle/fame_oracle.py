@@ -154,6 +154,24 @@ def sigmoid_fusion_forward(sd, batch8):
     return F.linear(hid, sd["classifier.3.weight"].float(), sd["classifier.3.bias"].float()), agg
 
 
+def average_fusion_forward(sd, ids, mask, codes7, text):
+    """MultimodalTransformer.forward of 07_multimodal_average_fusion.py:221-238 with its BEHRTModel (156-203), eval
+    mode.  codes7 = (age, segment, admission_loc, discharge_loc, gender, ethnicity, insurance) int64 [B] each.
+    Returns (logits [B,3], fused_embedding_pre_relu [B,512])."""
+    names = ("age", "segment", "admission_loc", "discharge_loc", "gender", "ethnicity", "insurance")
+    cls = bert_encode(sd, "BEHRT.bert.", ids, mask)[:, 0, :]
+    extra = 0
+    for n, c in zip(names, codes7):
+        tab = sd[f"BEHRT.{n}_embedding.weight"].float()
+        extra = extra + tab[c.clamp(0, tab.shape[0] - 1)]
+    emb = cls + extra / 7.0
+    ts_pre = F.linear(emb, sd["ts_linear.weight"].float(), sd["ts_linear.bias"].float())
+    tx_pre = F.linear(text, sd["text_linear.weight"].float(), sd["text_linear.bias"].float())
+    comb = torch.cat([torch.relu(ts_pre), torch.relu(tx_pre)], dim=1)
+    hid = torch.relu(F.linear(comb, sd["classifier.0.weight"].float(), sd["classifier.0.bias"].float()))
+    return F.linear(hid, sd["classifier.3.weight"].float(), sd["classifier.3.bias"].float()), torch.cat([ts_pre, tx_pre], dim=1)
+
+
 def eddi_08(y_true, y_prob, sensitive, threshold=0.5):
     """compute_eddi of 08_multimodal_eddi_fusion.py:45-59 (np.unique groups; NaN-free here; sum, not nansum)."""
     pred = (y_prob > threshold).astype(int)

@@ -368,3 +368,32 @@ def test_eddi_fusion_oracle_vs_reference_golden(golden_dir):
     for k in g.files:
         if k.startswith("grad."):
             np.testing.assert_allclose(sd[k[5:]].grad.numpy(), g[k], rtol=5e-3, atol=1e-5)
+
+
+def test_average_fusion_oracle_vs_reference_golden(golden_dir):
+    """Concat-fusion ablation over a seven-table demographic encoder (07_multimodal_average_fusion.py; B200
+    implementation: next round; note: plain Adam without clipping, 07:720): oracle forward (incl. the id clamp), summed
+    focal loss and autograd gradients against the unmodified reference."""
+    import os
+    import torch
+    from fairmultimodal_b200 import synth
+    from oracle import fame_oracle as O
+    g = np.load(os.path.join(golden_dir, "average_fusion.npz"))
+    sizes = dict(num_diseases=10, num_ages=5, num_segments=2, num_adm=4, num_disch=6, num_genders=2, num_eth=5, num_ins=5)
+    sd = {k: torch.from_numpy(v).clone().requires_grad_(True)
+          for k, v in synth.synth_state_dict(synth.average_fusion_shapes(**sizes), 29).items()}
+    B = g["labels"].shape[0]
+    ids, mask = torch.zeros((B, 1), dtype=torch.long), torch.ones((B, 1), dtype=torch.long)
+    codes = [torch.from_numpy(c) for c in g["codes"]]
+    logits, pre = O.average_fusion_forward(sd, ids, mask, codes, torch.from_numpy(g["text"]))
+    np.testing.assert_allclose(logits.detach().numpy(), g["logits_eval"], atol=3e-5, rtol=1e-4)
+    np.testing.assert_allclose(pre.detach().numpy(), g["pre_relu_eval"], atol=3e-5, rtol=1e-4)
+    loss = O.text_classifier_loss(logits, torch.from_numpy(g["labels"]), torch.from_numpy(g["pos_weight"]), gamma=1.0)
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    loss.backward()
+    names = [str(n) for n in g["gnorm_names"]]
+    got = np.array([sd[n].grad.norm().item() if sd[n].grad is not None else 0.0 for n in names])
+    np.testing.assert_allclose(got, g["gnorm"], rtol=5e-3, atol=1e-5 * float(g["gnorm"].max()))
+    for k in g.files:
+        if k.startswith("grad."):
+            np.testing.assert_allclose(sd[k[5:]].grad.numpy(), g[k], rtol=5e-3, atol=1e-6)
