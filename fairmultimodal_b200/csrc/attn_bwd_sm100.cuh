@@ -19,7 +19,7 @@
 #pragma once
 #include "dropout.cuh"
 #include "sm100_ptx.cuh"
-#include "attn_flash_sm100.cuh"   // kFaBoxBytes, ex2_approx (via attn_sm100.cuh)
+#include "attn_common.cuh"
 
 namespace fame {
 

@@ -30,7 +30,7 @@
 // (2) fetching the key-mask bytes one block ahead (0.45 ms: the extra live registers spill in the softmax loop).
 #pragma once
 #include "sm100_ptx.cuh"
-#include "attn_flash_sm100.cuh"   // FaParams, kFaBoxBytes, ex2_approx (via attn_sm100.cuh)
+#include "attn_common.cuh"
 
 namespace fame {
 

@@ -6,8 +6,6 @@
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
 
-#include "attn_sm100.cuh"
-#include "attn_flash_sm100.cuh"
 #include "attn_pair_sm100.cuh"
 #include "attn_bwd_sm100.cuh"
 #include "backward.cuh"
@@ -17,12 +15,8 @@
 #include "rowwise.cuh"
 #include "skinny_gemm.cuh"
 
-// which kernel algo == 0 (auto) picks for head_dim 64, seq <= 512: 1 = full-row TMEM kernel, 0 = flash kernel
 #ifndef FAME_USE_SKINNY_GEMM
 #define FAME_USE_SKINNY_GEMM 1
-#endif
-#ifndef FAME_ATTN_AUTO_FULLROW
-#define FAME_ATTN_AUTO_FULLROW 0  /* measured on B200, 256 x 12 heads x 512: flash 0.69 ms vs full-row 0.81 ms */
 #endif
 
 namespace {
@@ -107,34 +101,6 @@ int launch_status() {
 }
 
 #include "gemm_host.inc"
-
-template <int D>
-static int launch_flash(const fame_attn_fwd_args* a, const CUtensorMap& tq, fame_stream_t stream) {
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(fame::attn_fwd_flash_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             fame::FaCfg<D>::kSmemBytes);
-        if (e != cudaSuccess) return cuda_fail(e);
-        attr_set[dev] = true;
-    }
-    fame::FaParams p;
-    p.key_mask = a->key_mask;
-    p.ctx = reinterpret_cast<__nv_bfloat16*>(a->ctx);
-    p.ld_ctx = a->ld_ctx;
-    p.batch = a->batch;
-    p.seq = a->seq;
-    p.heads = a->heads;
-    p.q_col0 = 0;
-    p.k_col0 = a->heads * D;
-    p.v_col0 = 2 * a->heads * D;
-    p.scale_log2e = a->scale * 1.4426950408889634f;
-    p.lse = nullptr;
-    dim3 grid((a->seq + 127) / 128, a->heads, a->batch);
-    fame::attn_fwd_flash_kernel<D><<<grid, fame::kFaThreads, fame::FaCfg<D>::kSmemBytes, stream>>>(tq, p);
-    return launch_status();
-}
 
 template <int D, bool kDrop>
 static int launch_pair_t(const fame_attn_fwd_args* a, const CUtensorMap& tq, int sm_count, fame_stream_t stream) {
@@ -353,12 +319,7 @@ int fame_attn_fwd(const fame_attn_fwd_args* a, void*, size_t, fame_stream_t stre
     if (a == nullptr || a->qkv == nullptr || a->ctx == nullptr) return FAME_ERR_NULLPTR;
     if ((a->head_dim != 64 && a->head_dim != 96) || a->seq <= 0 || a->heads <= 0 || a->batch < 0)
         return FAME_ERR_SHAPE;
-    if (a->algo < 0 || a->algo > 3) return FAME_ERR_SHAPE;
-    if (a->lse != nullptr && a->algo != 0 && a->algo != 3) return FAME_ERR_SHAPE;   // only the persistent kernel saves it
-    if (a->kv_len != nullptr && a->algo != 0 && a->algo != 3) return FAME_ERR_SHAPE;
-    if (a->drop.thresh16 != 0 && a->algo != 0 && a->algo != 3) return FAME_ERR_SHAPE;
-    const bool fullrow_ok = a->head_dim == fame::kAttnD && a->seq <= fame::kAttnMaxS;
-    if (a->algo == 1 && !fullrow_ok) return FAME_ERR_SHAPE;
+    if (a->algo != 0 && a->algo != 3) return FAME_ERR_SHAPE;   // one kernel: the persistent two-tile kernel
     const int64_t width = 3ll * a->heads * a->head_dim;
     if (a->ld_qkv < width || a->ld_ctx < (int64_t)a->heads * a->head_dim) return FAME_ERR_SHAPE;
     if ((a->ld_qkv & 7) || (a->ld_ctx & 7) || !aligned16(a->qkv) || !aligned16(a->ctx)) return FAME_ERR_ALIGN;
@@ -371,31 +332,7 @@ int fame_attn_fwd(const fame_attn_fwd_args* a, void*, size_t, fame_stream_t stre
     CUtensorMap tq;
     rc = encode_bf16_2d(&tq, a->qkv, (uint64_t)a->batch * a->seq, (uint64_t)width, (uint64_t)a->ld_qkv, 128);
     if (rc != FAME_OK) return rc;
-    if (a->algo == 0 || a->algo == 3)
-        return a->head_dim == 64 ? launch_pair<64>(a, tq, d->sm_count, stream) : launch_pair<96>(a, tq, d->sm_count, stream);
-    const bool use_fullrow = a->algo == 1;
-    if (!use_fullrow) return a->head_dim == 64 ? launch_flash<64>(a, tq, stream) : launch_flash<96>(a, tq, stream);
-
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(fame::attn_fwd_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             fame::kAttnSmemBytes);
-        if (e != cudaSuccess) return cuda_fail(e);
-        attr_set[dev] = true;
-    }
-    fame::AttnParams p;
-    p.key_mask = a->key_mask;
-    p.ctx = reinterpret_cast<__nv_bfloat16*>(a->ctx);
-    p.ld_ctx = a->ld_ctx;
-    p.batch = a->batch;
-    p.seq = a->seq;
-    p.heads = a->heads;
-    p.scale_log2e = a->scale * 1.4426950408889634f;
-    dim3 grid((a->seq + fame::kAttnBQ - 1) / fame::kAttnBQ, a->heads, a->batch);
-    fame::attn_fwd_d64_kernel<<<grid, fame::kAttnThreads, fame::kAttnSmemBytes, stream>>>(tq, p);
-    return launch_status();
+    return a->head_dim == 64 ? launch_pair<64>(a, tq, d->sm_count, stream) : launch_pair<96>(a, tq, d->sm_count, stream);
 }
 
 int fame_mask_kv_len(const uint8_t* key_mask, int32_t batch, int32_t seq, int32_t* kv_len, fame_stream_t stream) {

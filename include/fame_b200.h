@@ -191,16 +191,16 @@ typedef struct {
     int64_t ld_ctx;
     int32_t batch, seq, heads, head_dim;
     float scale;
-    int32_t algo; /* 0 = auto (= 3); 1 = full-row TMEM kernel (head_dim 64, seq <= 512); 2 = streaming flash kernel,
-                     one 128-query tile per CTA; 3 = persistent kernel, two 128-query tiles per CTA */
+    int32_t algo; /* 0 (or 3, its former explicit name): the persistent kernel, two 128-query tiles per CTA.  The
+                     round-1 alternatives 1 / 2 were removed: FAME_ERR_SHAPE */
     float* lse;   /* optional f32 [batch, heads, seq]: log2-domain log-sum-exp of each row of scaled scores, saved for
-                     fame_attn_bwd_pds (P = 2^(s * scale * log2 e - lse)); algo 0 / 3 only; may be NULL */
+                     fame_attn_bwd_pds (P = 2^(s * scale * log2 e - lse)); may be NULL */
     const int32_t* kv_len; /* optional int32 [batch] from fame_mask_kv_len: 1 + index of the last attended key of each
                      sequence.  Key blocks (128 keys) that lie entirely beyond it hold only masked keys (probability
                      exactly 0) and are not loaded, multiplied or exponentiated; results are identical with and
-                     without it.  algo 0 / 3 only; may be NULL */
+                     without it.  may be NULL */
     fame_dropout_cfg drop; /* dropout of the attention probabilities (training): mask row = (sequence, head, query),
-                     column = key; thresh16 = 0: none.  algo 0 / 3 only */
+                     column = key; thresh16 = 0: none */
 } fame_attn_fwd_args;
 int fame_attn_fwd(const fame_attn_fwd_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
 

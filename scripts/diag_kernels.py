@@ -114,7 +114,6 @@ def run_attn():
         # between key blocks: exercises the in-TMEM rescale of the accumulator)
         (12, 64, 40, 512, True, 3, 1.0), (8, 96, 40, 542, False, 3, 1.0), (12, 64, 4, 512, False, 3, 3.0),
         (8, 96, 3, 542, True, 3, 3.0), (12, 64, 40, 640, False, 3, 2.5),
-        (12, 64, 3, 512, True, 2, 1.0), (8, 96, 2, 542, True, 2, 1.0), (12, 64, 3, 512, True, 1, 1.0),
     ]:
         qkv = (torch.randn(B * S, 3 * H * D, device=dev) * mag).bfloat16()
         mask = None
@@ -129,8 +128,7 @@ def run_attn():
             s = s.masked_fill(mask[:, None, None, :] == 0, float("-inf"))
         ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * S, H * D)
         ok &= _err_report(f"attn algo{algo} H{H} D{D} B{B} S{S} masked{int(masked)}", ctx, ref, 2e-2)
-    for (H, D, B, S, algo) in [(12, 64, 256, 512, 2), (12, 64, 256, 512, 3), (8, 96, 256, 542, 2), (8, 96, 256, 542, 3),
-                               (8, 96, 32, 542, 3)]:
+    for (H, D, B, S, algo) in [(12, 64, 256, 512, 3), (8, 96, 256, 542, 3), (8, 96, 32, 542, 3)]:
         qkv = torch.randn(B * S, 3 * H * D, device=dev).bfloat16()
         out = torch.empty(B * S, H * D, device=dev, dtype=torch.bfloat16)
         for _ in range(3):

@@ -133,30 +133,43 @@ def test_gemm_rejects_bad_shapes():
         ops.gemm_bias_act(x, w)                    # K % 8 != 0
 
 
-@pytest.mark.parametrize("H,D,B,S,masked,algo", [
-    # full-row TMEM kernel (head_dim 64, seq <= 512)
-    (12, 64, 1, 128, False, 1), (12, 64, 2, 512, False, 1), (12, 64, 3, 512, True, 1), (12, 64, 2, 300, True, 1),
-    (12, 64, 2, 77, False, 1), (12, 64, 2, 1, False, 1),
-    # streaming flash kernel: BERT heads (64) and lab-encoder heads (96; L = 542 is the real cohort's token count)
-    (12, 64, 2, 512, True, 2), (12, 64, 2, 300, True, 2), (12, 64, 2, 1, False, 2), (12, 64, 2, 1000, True, 2),
-    (8, 96, 3, 542, False, 2), (8, 96, 2, 542, True, 2), (8, 96, 2, 12, False, 2), (8, 96, 1, 1300, False, 2),
-    (8, 96, 5, 128, False, 0), (12, 64, 4, 256, True, 0),
+@pytest.mark.parametrize("H,D,B,S,masked", [
+    # BERT heads (head_dim 64): the note encoder's hot shape (12 x 64, 512 tokens, padded chunks) and odd lengths
+    (12, 64, 1, 128, False), (12, 64, 2, 512, False), (12, 64, 3, 512, True), (12, 64, 2, 300, True),
+    (12, 64, 2, 77, False), (12, 64, 2, 1, False), (12, 64, 2, 1000, True), (12, 64, 4, 256, True),
+    (12, 64, 40, 512, True),                       # more work items than one wave of 148 persistent CTAs
+    # lab-encoder heads (head_dim 96; L = 542 is the real cohort's token count: 5 key blocks with a ragged tail)
+    (8, 96, 3, 542, False), (8, 96, 2, 542, True), (8, 96, 2, 12, False), (8, 96, 1, 1300, False),
+    (8, 96, 5, 128, False), (8, 96, 40, 542, False),
 ])
-def test_attention(H, D, B, S, masked, algo):
+def test_attention(H, D, B, S, masked):
+    """attn_fwd_pair_kernel (the only forward attention kernel) against fp32 torch softmax(QK^T / sqrt(d)) V, with
+    the saved log-sum-exp checked as well."""
     from fairmultimodal_b200 import ops
     torch.manual_seed(S + B)
     qkv = torch.randn(B * S, 3 * H * D, device="cuda").bfloat16()
-    mask = None
+    mask = kv_len = None
     if masked:
         lens = torch.randint(1, S + 1, (B,), device="cuda")
         mask = (torch.arange(S, device="cuda")[None, :] < lens[:, None]).to(torch.uint8).contiguous()
-    ctx = ops.attn_fwd(qkv, B, S, H, D, key_mask=mask, algo=algo)
+        kv_len = ops.mask_kv_len(mask)                  # as bert.encode passes it on the hot path
+    lse = torch.empty(B, H, S, device="cuda")
+    ctx = ops.attn_fwd(qkv, B, S, H, D, key_mask=mask, kv_len=kv_len, lse=lse)
     q, k, v = qkv.float().view(B, S, 3, H, D).permute(2, 0, 3, 1, 4)
     s = (q @ k.transpose(-1, -2)) * D ** -0.5
     if mask is not None:
         s = s.masked_fill(mask[:, None, None, :] == 0, float("-inf"))
     ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * S, H * D)
     _close(ctx, ref, 2e-2)
+    assert (lse - torch.logsumexp(s, -1) * 1.4426950408889634).abs().max().item() <= 2e-2
+
+
+def test_attention_rejects_removed_algos():
+    from fairmultimodal_b200 import _lib, ops
+    qkv = torch.zeros(128, 3 * 12 * 64, device="cuda", dtype=torch.bfloat16)
+    for algo in (1, 2):
+        with pytest.raises(_lib.FameError):
+            ops.attn_fwd(qkv, 1, 128, 12, 64, algo=algo)
 
 
 @pytest.mark.parametrize("H,D,B,S", [(12, 64, 40, 512), (8, 96, 7, 542), (12, 64, 3, 700), (12, 64, 200, 512)])
