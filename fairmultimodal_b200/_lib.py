@@ -101,7 +101,7 @@ class FusionFwdArgs(C.Structure):
         ("sig_w", C.c_void_p), ("w3_t", C.c_void_p), ("b3", C.c_void_p), ("w4", C.c_void_p), ("b4", C.c_void_p),
         ("wc", C.c_void_p), ("bc", C.c_void_p), ("proj", C.c_void_p), ("gated", C.c_void_p),
         ("pre_relu", C.c_void_p), ("logits", C.c_void_p), ("mod_logits", C.c_void_p), ("sig_out", C.c_void_p),
-        ("B", C.c_int32),
+        ("B", C.c_int32), ("w_mod_dev", C.c_void_p),
     ]
 
 
@@ -171,7 +171,7 @@ FLAT_OPS = {
     "fame_mask_kv_len": [_P, _I32, _I32, _P],
     "fame_layernorm_bwd": [_P, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P],
     "fame_dropout_apply": [_P, _I32, _I64, _I32, _I32, _P],
-    "fame_focal_loss_fwd_bwd": [_P, _P, _P, _F, _F, _I32, _P, _P],
+    "fame_focal_loss_fwd_bwd": [_P, _P, _P, _F, _F, _I32, _P, _P, _P],
     "fame_relu_fwd": [_P, _I64],
     "fame_relu_bwd": [_P, _P, _I64],
     "fame_gelu_fwd": [_P, _P, _I64],
@@ -184,7 +184,7 @@ FLAT_OPS = {
     "fame_demo_add_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32],
     "fame_sgemm_small": [_P, _I64, _I64, _P, _I64, _I64, _P, _I64, _I32, _I32, _I32, _F, _I32],
     "fame_fusion_bwd_hidden": [_P, _P, _P, _P, _I32],
-    "fame_fusion_bwd_gate": [_P, _P, _P, _F, _F, _F, _F, _P, _P, _I32],
+    "fame_fusion_bwd_gate": [_P, _P, _P, _F, _F, _F, _F, _P, _P, _I32, _P],
     "fame_grad_sumsq": [_P, _I64, _P],
     "fame_clip_adamw": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _I32, _P, _P, _P, _P],
     "fame_cast_bf16": [_P, _P, _I64],

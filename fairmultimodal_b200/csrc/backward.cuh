@@ -428,10 +428,11 @@ __global__ void fusion_bwd_hidden_kernel(const float* __restrict__ dlogits, cons
 }
 __global__ void fusion_bwd_gate_kernel(const float* __restrict__ dgated, const float* __restrict__ proj,
                                        const float* __restrict__ sig_w, float w0, float w1, float w2, float lambda_l1,
-                                       float* __restrict__ dproj, float* __restrict__ dsig, int B) {
+                                       float* __restrict__ dproj, float* __restrict__ dsig, int B,
+                                       const float* __restrict__ w_dev) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= 768) return;
-    const float wm = k < 256 ? w0 : (k < 512 ? w1 : w2);
+    const float wm = w_dev != nullptr ? __ldg(w_dev + k / 256) : (k < 256 ? w0 : (k < 512 ? w1 : w2));
     const float sw = sig_w[k];
     const float s = 1.0f / (1.0f + expf(-sw));
     float acc = 0.f;

@@ -474,6 +474,7 @@ int fame_fusion_fwd(const fame_fusion_fwd_args* a, void* workspace, size_t works
     p.wp_t = a->wp_t; p.bp = a->bp; p.sig_w = a->sig_w; p.w3_t = a->w3_t; p.b3 = a->b3; p.w4 = a->w4; p.b4 = a->b4;
     p.wc = a->wc; p.bc = a->bc; p.proj = a->proj; p.gated = a->gated; p.pre_relu = a->pre_relu;
     p.logits = a->logits; p.mod_logits = a->mod_logits; p.sig_out = a->sig_out; p.B = a->B;
+    p.w_mod_dev = a->w_mod_dev;
     const int grid = (a->B + fame::kFuRows - 1) / fame::kFuRows;
     if (a->B <= kFusionSmallMaxB) {
         float* ws = reinterpret_cast<float*>(workspace);

@@ -38,6 +38,8 @@ struct FusionParams {
     float* mod_logits;     // [3][B][3] nullable
     float* sig_out;        // [768] sigmoid(sig_w), nullable
     int B;
+    const float* w_mod_dev;  // optional device copy of w_mod, read at run time (CUDA-graph replays follow updates)
+    __device__ __forceinline__ float wmod(int m) const { return w_mod_dev != nullptr ? __ldg(w_mod_dev + m) : w_mod[m]; }
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
@@ -109,7 +111,7 @@ fusion_fwd_kernel(const FusionParams p) {
 #pragma unroll
         for (int r = 0; r < kFuRows; ++r) {
             xin[(m * kFuRows + r) * 768 + t] = pr[m][r];
-            const float gv = (p.w_mod[m] * pr[m][r]) * sg;
+            const float gv = (p.wmod(m) * pr[m][r]) * sg;
             g[r * 768 + m * 256 + t] = gv;
             if (r < nrow) {
                 if (p.proj != nullptr) p.proj[(long long)(row0 + r) * 768 + m * 256 + t] = pr[m][r];
@@ -269,7 +271,7 @@ fusion_small_proj_kernel(const FusionParams p, float* __restrict__ proj, float* 
         const float pr = fmaxf(v[0] + __ldg(p.bp + c), 0.f);
         const float sg = 1.0f / (1.0f + expf(-__ldg(p.sig_w + c)));
         proj[(long long)(row0 + r) * 768 + c] = pr;
-        gated[(long long)(row0 + r) * 768 + c] = (p.w_mod[m] * pr) * sg;
+        gated[(long long)(row0 + r) * 768 + c] = (p.wmod(m) * pr) * sg;
     }
 }
 
@@ -544,9 +546,12 @@ loss_fwd_bwd_kernel(const LossGradParams p) {
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0 && p.loss_out != nullptr) {
         const float l1 = p.lambda_l1 * s_l1;
-        p.loss_out[0] = s_bce + p.lambda_edd * (10.0f * s_leddi) + l1;
-        p.loss_out[1] = s_bce;
-        p.loss_out[2] = s_leddi;
+        // a sensitive-attribute code outside 0..7 was seen by the statistics pass (on any rank): its patient is in no
+        // subgroup sum, so the loss is not the reference's -- report NaN instead of a silently different number
+        const float bad = p.stats[103] != 0 ? __int_as_float(0x7fc00000) : 0.f;
+        p.loss_out[0] = s_bce + p.lambda_edd * (10.0f * s_leddi) + l1 + bad;
+        p.loss_out[1] = s_bce + bad;
+        p.loss_out[2] = s_leddi + bad;
         p.loss_out[3] = l1;
     }
     if (p.dlogits == nullptr) return;
@@ -570,7 +575,7 @@ loss_fwd_bwd_kernel(const LossGradParams p) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 const long long c = q.code[a][u];
-                code[a] = (int)(c < 0 ? 0 : (c >= kLossSlots ? kLossSlots - 1 : c));
+                code[a] = (c < 0 || c >= kLossSlots) ? -1 : (int)c;   // out of range: member of no subgroup
             }
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -579,7 +584,7 @@ loss_fwd_bwd_kernel(const LossGradParams p) {
                 float g = (-pwv[i] * y * (1.0f - pr) + (1.0f - y) * pr) * inv3B;
                 float dRde = 0.f;
 #pragma unroll
-                for (int a = 0; a < 3; ++a) dRde += coef[i][a][code[a]] + cst[i][a];
+                for (int a = 0; a < 3; ++a) dRde += (code[a] >= 0 ? coef[i][a][code[a]] : 0.f) + cst[i][a];
                 const float d = pr - y;
                 const float sgn = d > 0.f ? 1.0f : (d < 0.f ? -1.0f : 0.f);
                 gz[u][i] = g + k_edd * dRde * sgn * pr * (1.0f - pr);
@@ -609,8 +614,12 @@ loss_fwd_bwd_kernel(const LossGradParams p) {
 __global__ void __launch_bounds__(256)
 focal_loss_fwd_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
                           const float* __restrict__ pos_weight, float gamma, float alpha, float inv_batch, int n,
-                          double* __restrict__ loss_out, float* __restrict__ dlogits) {
+                          double* __restrict__ loss_out, float* __restrict__ dlogits,
+                          const long long* __restrict__ batch_total_dev) {
     __shared__ double part[8];
+    // data parallel: the mean runs over the GLOBAL batch (all-reduced patient count in device memory), so that the
+    // SUM of the ranks' losses / gradients is the single-process result on the concatenated batch
+    if (batch_total_dev != nullptr) inv_batch = 1.0f / (float)(*batch_total_dev);
     double acc = 0.0;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
         const int i = idx % 3;

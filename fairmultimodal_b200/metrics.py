@@ -226,14 +226,16 @@ def calibrate_thresholds(model, dataloader, device):
     return thresholds_from_hist(c.hist)
 
 
-def evaluate_from_logits(logits, labels, attrs, thresholds, verbose=True, counts=None, rank_group=None):
+def evaluate_from_logits(logits, labels, attrs, thresholds, verbose=True, counts=None, rank_group=None, ranks=None):
     """Metric half of evaluate_model_multi (10_FAME.py:511-552) + the EDDI tail of run_experiment (887-915) on
     device tensors.  Returns (metrics, fairness_details, eddi).  `counts`: a precomputed (e.g. all-reduced) count
-    vector; `rank_group`: process group over which the AUROC / AP rank counting of `logits` is sharded."""
+    vector; `rank_group`: process group over which the AUROC / AP rank counting of `logits` is sharded; `ranks`:
+    precomputed [(auroc, ap)] per outcome (then `logits` is not touched at all)."""
     th = [thresholds[n] if isinstance(thresholds, dict) else thresholds for n in OUTCOMES]
     vec = counts if counts is not None else ops.eval_counts(logits, labels, attrs, th)
     c = Counts(vec)
-    ranks = rank_metrics(logits, labels, group=rank_group)
+    if ranks is None:
+        ranks = rank_metrics(logits, labels, group=rank_group)
     metrics, fair, eddi = {}, {}, {}
     for o, name in enumerate(OUTCOMES):
         tp, fn, fp, tn = (int(x) for x in c.tot[o])

@@ -292,7 +292,7 @@ def demo_add(cls, ld_cls, ids, tables):
     return out
 
 
-def fusion_fwd(emb, packed, w_mod, want_mod_logits=False, want_intermediates=False):
+def fusion_fwd(emb, packed, w_mod, want_mod_logits=False, want_intermediates=False, w_mod_dev=None):
     """emb = (demo, lab, text) f32 [B,768]; packed = dict of fp32 fusion weights (see modules._pack_fusion).
     Returns dict(logits, sig, [mod_logits], [proj, gated, pre_relu])."""
     B = emb[0].shape[0]
@@ -318,6 +318,8 @@ def fusion_fwd(emb, packed, w_mod, want_mod_logits=False, want_intermediates=Fal
         out["pre_relu"] = torch.empty((B, 512), device=dev, dtype=torch.float32)
         a.proj, a.gated, a.pre_relu = out["proj"].data_ptr(), out["gated"].data_ptr(), out["pre_relu"].data_ptr()
     a.B = B
+    if w_mod_dev is not None:        # f32 [3] on the device: read by the kernels at run time (overrides w_mod)
+        a.w_mod_dev = _cuda(w_mod_dev, "w_mod_dev", torch.float32).data_ptr()
     ws_bytes = 0 if want_intermediates else _lib.load().fame_fusion_fwd_workspace_bytes(B)
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8) if ws_bytes else None
     _call("fame_fusion_fwd", a, B * (3 * 768 * 4.0 + 3 * 4.0) + 4.0 * (3 * 768 * 256 + 768 * 512), ws=ws)

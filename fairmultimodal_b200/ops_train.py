@@ -197,11 +197,11 @@ def fusion_bwd_hidden(dlogits, w4, pre):
     return dhid
 
 
-def fusion_bwd_gate(dgated, proj, sig_w, w_mod, lambda_l1, dsig):
+def fusion_bwd_gate(dgated, proj, sig_w, w_mod, lambda_l1, dsig, w_mod_dev=None):
     B = dgated.shape[0]
     dproj = torch.empty((B, 768), device=dgated.device, dtype=torch.float32)
     _flat("fame_fusion_bwd_gate", dgated.data_ptr(), proj.data_ptr(), sig_w.data_ptr(), float(w_mod[0]), float(w_mod[1]),
-          float(w_mod[2]), float(lambda_l1), dproj.data_ptr(), dsig.data_ptr(), B)
+          float(w_mod[2]), float(lambda_l1), dproj.data_ptr(), dsig.data_ptr(), B, _p(w_mod_dev))
     return dproj
 
 
@@ -224,14 +224,15 @@ def cast_bf16(x, y):
     _flat("fame_cast_bf16", x.data_ptr(), y.data_ptr(), x.numel())
 
 
-def focal_loss_fwd_bwd(logits, labels, pos_weight, gamma=2.0, alpha=1.0, want_grad=True):
-    """sum_i mean_b FocalLoss(gamma, alpha, pos_weight_i)(logits[:, i], labels[:, i]) -> (loss f64 [1], dlogits | None)."""
+def focal_loss_fwd_bwd(logits, labels, pos_weight, gamma=2.0, alpha=1.0, want_grad=True, batch_total=None):
+    """sum_i mean_b FocalLoss(gamma, alpha, pos_weight_i)(logits[:, i], labels[:, i]) -> (loss f64 [1], dlogits | None).
+    batch_total (device int64 [1], optional): global batch size of a data-parallel step (the mean runs over it)."""
     B = logits.shape[0]
     loss = torch.zeros(1, device=logits.device, dtype=torch.float64)
     dl = torch.empty((B, 3), device=logits.device, dtype=torch.float32) if want_grad else None
     keep = (logits.float().contiguous(), labels.float().contiguous(), pos_weight.float().contiguous())
     _flat("fame_focal_loss_fwd_bwd", keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(), float(gamma), float(alpha),
-          B, loss.data_ptr(), _p(dl))
+          B, loss.data_ptr(), _p(dl), _p(batch_total))
     return loss, dl
 
 

@@ -153,8 +153,17 @@ def forward_backward(model, batch8, labels, pos_weight, gamma=1.0, alpha=None, g
     w = _head_weights(st.f)
     drop = ds.site("sigfusion.head", ds.p_fusion) if ds is not None else None
     h = _head_forward(embs, w, drop)
+    btot = None
+    if group is not None:
+        # N ranks == the single-process step on the concatenated batch: the focal mean runs over the GLOBAL batch (the
+        # gradient all-reduce below is a SUM), and the returned loss is the global one
+        import torch.distributed as dist
+        btot = torch.full((1,), labels.shape[0], device=labels.device, dtype=torch.int64)
+        dist.all_reduce(btot, group=group)
     loss, dlogits = T.focal_loss_fwd_bwd(h["logits"], labels.float().contiguous(), pos_weight, gamma,
-                                         1.0 if alpha is None else alpha)
+                                         1.0 if alpha is None else alpha, batch_total=btot)
+    if group is not None:
+        dist.all_reduce(loss, group=group)
     torch.cuda.current_stream().wait_stream(post)
     red = train._GradReducer(st, group)
     g = st.gr

@@ -71,13 +71,28 @@ def _layout_key(name, names=FAME_NAMES):
     return _R_REST
 
 
+def dropout_base_seed():
+    """Seed of the dropout hash: follows torch.manual_seed (so runs / folds with different seeds draw different masks,
+    as the reference's Philox stream does) and the data-parallel rank (the mask row index is rank-local: without the
+    rank every shard of the global batch would draw the SAME masks)."""
+    s = torch.initial_seed() & 0xFFFFFFFF
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            s ^= (dist.get_rank() * 0x9E3779B1) & 0xFFFFFFFF
+    except Exception:
+        pass
+    return (s ^ 0x5EED) & 0xFFFFFFFF
+
+
 class DropSites:
     """Dropout sites of one training step: name -> _lib.DropoutCfg (seed per site, shared device step counter)."""
 
-    def __init__(self, model, step_dev, base_seed=0x5EED, lab_module=None, head_dropout=None, demo_module=None):
+    def __init__(self, model, step_dev, base_seed=None, lab_module=None, head_dropout=None, demo_module=None):
         """FAME model by default; with lab_module / head_dropout given: a model that has only the lab tower and one
-        nn.Dropout in its head (behrt_combined.BEHRTModel_Combined)."""
+        nn.Dropout in its head (behrt_combined.BEHRTModel_Combined).  base_seed: default = dropout_base_seed()."""
         from . import _lib
+        base_seed = dropout_base_seed() if base_seed is None else base_seed
         self._lib, self.step_ptr, self.base, self.cache = _lib, step_dev.data_ptr(), base_seed, {}
         active = model.training
         if lab_module is None:
@@ -191,6 +206,11 @@ class FlatTrainState:
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         self.hyper_dev = torch.zeros(2, device=dev, dtype=torch.float32)
         self._hyper_host = None
+        # EDDI modality weights of the fusion head, read by the kernels at run time: update_dynamic_weights_all_tasks
+        # changes them every epoch (10_FAME.py:805-830) and a captured step must not be re-captured for that
+        self.w_mod_dev = torch.full((3,), 0.33, device=dev, dtype=torch.float32)
+        self._w_mod_host = (0.33, 0.33, 0.33)
+        self.last_stats = None
         self.graphs = {}
         self._build_transposed_shadows(dev)
         self.refresh_bf16()
@@ -292,6 +312,28 @@ class FlatTrainState:
             self.hyper_dev.copy_(torch.tensor([lr, weight_decay], dtype=torch.float32))
             self._hyper_host = (lr, weight_decay)
 
+    def set_w_mod(self, w_mod):
+        w = tuple(float(x) for x in w_mod)
+        if w != self._w_mod_host:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("modality weights changed during CUDA-graph capture")
+            self.w_mod_dev.copy_(torch.tensor(w, dtype=torch.float32))
+            self._w_mod_host = w
+
+    def state_dict(self):
+        """Optimizer state for checkpoints (the nn.Module's own state_dict() holds the parameters; a torch AdamW built
+        on model.parameters() never steps here, so ITS state_dict is empty): Adam moments, step count, dropout step."""
+        return {"m": self.m.clone(), "v": self.v.clone(), "step": int(self.step_dev.item()),
+                "layout": dict(self.offsets), "n": int(self.n)}
+
+    def load_state_dict(self, sd):
+        if int(sd["n"]) != int(self.n) or dict(sd["layout"]) != dict(self.offsets):
+            raise ValueError("optimizer state was saved for a different parameter layout")
+        self.m.copy_(sd["m"])
+        self.v.copy_(sd["v"])
+        self.step = int(sd["step"])
+        self.step_dev.fill_(int(sd["step"]))
+
     def clip_and_step(self, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0):
         """clip_grad_norm_(max_norm) + AdamW on the flat buffers (graph-capturable: lr / weight decay / step count are
         read from device memory).  The bf16 shadow is refreshed by the same kernel."""
@@ -329,6 +371,11 @@ def release_graphs(model):
 def get_state(model) -> FlatTrainState:
     st = getattr(model, "_fame_train_state", None)
     if st is None or st.model is not model or not st.aliased():
+        if st is not None and st.model is model:
+            import warnings
+            warnings.warn("the model's parameters no longer alias the flat training buffers (model.to(...) or a "
+                          "re-assigned parameter): rebuilding them -- Adam moments, step count and captured graphs "
+                          "restart from zero (save / restore them with FlatTrainState.state_dict())")
         st = FlatTrainState(model)
         object.__setattr__(model, "_fame_train_state", st)
     return st
@@ -614,7 +661,7 @@ def _fusion_pack(st):
         b4=f("fusion_mlp.3.bias"))
 
 
-def _fusion_backward(st, fo, embs, dlogits, w_mod, lambda_l1, d_fus=None):
+def _fusion_backward(st, fo, embs, dlogits, w_mod, lambda_l1, d_fus=None, w_mod_dev=None):
     """Returns (d demo_emb, d lab_emb) f32 [B,768]; writes every head gradient into the flat buffer."""
     B = dlogits.shape[0]
     dev = dlogits.device
@@ -630,7 +677,8 @@ def _fusion_backward(st, fo, embs, dlogits, w_mod, lambda_l1, d_fus=None):
     T.colsum(dhid, g("fusion_mlp.0.bias"))
     dgated = torch.empty((B, 768), device=dev, dtype=torch.float32)
     T.sgemm(dhid, 512, 1, f("fusion_mlp.0.weight"), 768, 1, dgated, B, 768, 512)
-    dproj = T.fusion_bwd_gate(dgated, fo["proj"], f("sig_weights"), w_mod, lambda_l1, g("sig_weights"))
+    dproj = T.fusion_bwd_gate(dgated, fo["proj"], f("sig_weights"), w_mod, lambda_l1, g("sig_weights"),
+                              w_mod_dev=w_mod_dev)
     demb = []
     for m, pn in enumerate(_PROJ):
         dpm = dproj[:, 256 * m:256 * (m + 1)]                                   # [B,256] view, row stride 768
@@ -651,10 +699,13 @@ def _lab_budget(group=None):
 
 
 # ------------------------------------------------------------------------------------------------ one optimisation step
-def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, group=None, want_outputs=False):
+def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, group=None, want_outputs=False,
+                     debug=None):
     """Forward + loss + backward for one batch; gradients land in the flat buffer.  Returns loss_out f32 [4] (device)
-    = (total, bce, leddi, l1) of the GLOBAL batch."""
+    = (total, bce, leddi, l1) of the GLOBAL batch.  debug: optional dict that receives the per-patient tensors a
+    parity test compares (embeddings, dlogits, d loss / d embeddings)."""
     st = get_state(model)
+    st.set_w_mod(w_mod)
     (ids, mask, age, gender, eth, ins, lab, text, labels) = batch
     # off the critical path, on the third stream while the forward runs: zero the gradient buffer (53 us), refresh the
     # transposed bf16 shadows the demographic backward reads (77 us); the backward waits for this stream below
@@ -691,7 +742,8 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
         pk["bc"] = torch.stack([c.bias.detach().float() for c in cls]).contiguous()
     else:
         pk["wc"] = pk["bc"] = pk["b4"]                                        # unused (mod_logits not requested)
-    fo = ops.fusion_fwd((demo, labe, text), pk, w_mod, want_mod_logits=want_outputs, want_intermediates=True)
+    fo = ops.fusion_fwd((demo, labe, text), pk, w_mod, want_mod_logits=want_outputs, want_intermediates=True,
+                        w_mod_dev=st.w_mod_dev)
     d_fus = ds.site("fusion.hidden", ds.p_fusion) if ds is not None else None
     if d_fus is not None:
         # fusion_mlp = Linear, ReLU, Dropout, Linear (10_FAME.py:255): the fused kernel's logits skip the dropout, so
@@ -706,6 +758,7 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
     if group is not None:
         import torch.distributed as dist
         dist.all_reduce(stats, group=group)                                    # 104 int64: global-batch statistics
+    st.last_stats = stats                               # stats[103] != 0: a bad attribute code -> NaN loss (train_step raises)
     loss, dlogits = ops.loss_fwd_bwd(fo["logits"], labels, attrs, pos_weight, stats, st.f("sig_weights"), lambda_edd,
                                      lambda_l1)
     if group is not None:
@@ -716,7 +769,10 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
     # fusion head, lives in the 'rest' region and travels with the last demographic bucket)
     red = _GradReducer(st, group)
     main.wait_stream(post)                              # gradient buffer zeroed, transposed shadows current
-    ddemo, dlab = _fusion_backward(st, fo, (demo, labe, text), dlogits, w_mod, lambda_l1, d_fus)
+    ddemo, dlab = _fusion_backward(st, fo, (demo, labe, text), dlogits, w_mod, lambda_l1, d_fus, w_mod_dev=st.w_mod_dev)
+    if debug is not None:
+        debug.update(demo=demo, lab=labe, dlogits=dlogits, ddemo=ddemo, dlab=dlab, logits=fo["logits"],
+                     proj=fo["proj"], pre_relu=fo["pre_relu"])
     # the demographic tower owns 88 % of the gradient bytes: its buckets cross NVLink while the tensor-core-bound lab
     # backward runs (side stream, or simply first when single-stream)
     if side is not None:
@@ -768,10 +824,14 @@ def train_step(model, dataloader, optimizer, device, criterion, beta=1.0, lambda
         loss = optimisation_step(model, batch, pw, lambda_edd, lambda_l1, w_mod, hp, group=group)
         acc += loss[:2]                                                        # accumulate on device, sync once
     running_loss, running_bce = acc.tolist()
+    if running_loss != running_loss and st.last_stats is not None and int(st.last_stats[103].item()) != 0:
+        raise ValueError("sensitive-attribute code outside 0..7 in a training batch (age / ethnicity / insurance ids): "
+                         "the LEDDI subgroup statistics cannot represent it")
     return running_loss, running_bce
 
 
 USE_CUDA_GRAPH = True
+MAX_STEP_GRAPHS = 4
 
 
 def optimisation_step(model, batch, pw, lambda_edd, lambda_l1, w_mod, hp, group=None, use_graph=None):
@@ -792,12 +852,18 @@ def optimisation_step(model, batch, pw, lambda_edd, lambda_l1, w_mod, hp, group=
 
     if not use_graph:
         return eager(batch)
-    key = (tuple((tuple(x.shape), x.dtype) for x in batch), tuple(w_mod), lambda_edd, lambda_l1, hp["betas"], hp["eps"],
+    st.set_w_mod(w_mod)                         # device buffer: NOT part of the key (it changes every epoch)
+    key = (tuple((tuple(x.shape), x.dtype) for x in batch), lambda_edd, lambda_l1, hp["betas"], hp["eps"],
            pw.data_ptr(), group is not None, DropSites(model, st.step_dev).key())
     entry = st.graphs.get(key)
     if entry is None:
+        # bounded cache, least recently used first out: each captured step owns a private pool with all saved
+        # activations (0.5 - 1 GB at 32 patients); a run sees two shapes per loader (full and ragged last batch)
+        while len(st.graphs) >= MAX_STEP_GRAPHS:
+            st.graphs.pop(next(iter(st.graphs)))
         st.graphs[key] = {"graph": None}
         return eager(batch)
+    st.graphs[key] = st.graphs.pop(key)         # most recently used last
     if entry["graph"] is None:
         static = [torch.empty_like(x) for x in batch]
         g = torch.cuda.CUDAGraph()

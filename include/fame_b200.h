@@ -285,6 +285,9 @@ typedef struct {
     float* mod_logits;    /* [3][B][3] "modality_logits" */
     float* sig_out;       /* [768]   "sigmoid_weights" */
     int32_t B;
+    const float* w_mod_dev; /* optional f32 [3] in DEVICE memory: when non-NULL the kernels read the modality weights
+                             from it at run time and ignore w_mod -- a captured CUDA graph of the training step then
+                             follows update_dynamic_weights_all_tasks (10_FAME.py:805-830) without re-capture */
 } fame_fusion_fwd_args;
 int fame_fusion_fwd(const fame_fusion_fwd_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
 /* Workspace needed when proj / gated / pre_relu are not all requested (small batches run as three launches whose
@@ -422,8 +425,10 @@ int fame_sgemm_small(const float* a, int64_t sam, int64_t sak, const float* b, i
 /* Fusion head backward, elementwise stages (10_FAME.py:287-296): hidden-layer ReLU mask; gate / sig_weights / L1. */
 int fame_fusion_bwd_hidden(const float* dlogits, const float* w4, const float* pre, float* dhid, int32_t B,
                            fame_stream_t stream);
+/* w_dev: optional f32 [3] in device memory overriding (w0, w1, w2), as fame_fusion_fwd_args.w_mod_dev. */
 int fame_fusion_bwd_gate(const float* dgated, const float* proj, const float* sig_w, float w0, float w1, float w2,
-                         float lambda_l1, float* dproj, float* dsig, int32_t B, fame_stream_t stream);
+                         float lambda_l1, float* dproj, float* dsig, int32_t B, const float* w_dev,
+                         fame_stream_t stream);
 /* K9: *out += sum g^2 (float64); then clip_grad_norm_(max_norm) + one AdamW step over flat f32 buffers. */
 int fame_grad_sumsq(const float* g, int64_t n, double* out, fame_stream_t stream);
 int fame_clip_adamw(float* p, const float* g, float* m, float* v, int64_t n, const double* sumsq, float max_norm, float lr,
@@ -457,9 +462,12 @@ int fame_attn_bwd_pds(const void* qkv, int64_t ld_qkv, const void* dctx, int64_t
 /* Text-only baseline (02_BioClinicalBERT.py): FocalLoss(gamma, alpha, pos_weight_i) summed over the three
  * outcomes, each a batch mean (18-38, 143-147): *loss_out += loss (float64, caller zeroes it); dlogits [batch, 3] =
  * d loss / d logits (may be NULL).  fame_relu_fwd / fame_relu_bwd: ReLU of the classifier's 256-wide hidden layer, in
- * place, and its backward mask (dh = pre > 0 ? dh : 0). */
+ * place, and its backward mask (dh = pre > 0 ? dh : 0).  batch_total_dev (optional, device int64 [1]): the GLOBAL
+ * batch size when `batch` is one data-parallel rank's shard -- the mean then runs over it, so the SUM over ranks of
+ * loss / gradients equals the single-process result on the concatenated batch. */
 int fame_focal_loss_fwd_bwd(const float* logits, const float* labels, const float* pos_weight, float gamma, float alpha,
-                            int32_t batch, double* loss_out, float* dlogits, fame_stream_t stream);
+                            int32_t batch, double* loss_out, float* dlogits, const int64_t* batch_total_dev,
+                            fame_stream_t stream);
 int fame_relu_fwd(float* x, int64_t n, fame_stream_t stream);
 int fame_relu_bwd(float* dh, const float* pre, int64_t n, fame_stream_t stream);
 int fame_transpose_bf16_table(const void* table, int32_t n_entries, int32_t total_tiles, fame_stream_t stream);

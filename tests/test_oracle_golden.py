@@ -330,6 +330,38 @@ def test_host_metric_formulas_from_counts_match_reference(golden_dir):
     np.testing.assert_allclose([[w2[n][m] for m in M.MODALITIES] for n in names], g["weights_epoch2"], atol=1e-14)
 
 
+def test_experiment_log_text_matches_reference(golden_dir, capsys):
+    """The stdout of evaluate_model_multi and update_dynamic_weights_all_tasks is part of the reference's contract
+    (the experiment log).  Host half only (counts from the numpy restatement of the count kernel, rank metrics
+    taken from the golden file): the text equals what the unmodified reference printed
+    (oracle/make_golden_wrappers.py); the GPU suite repeats this through the real entry points."""
+    import os
+    import re
+    from fairmultimodal_b200 import metrics as M
+    from oracle import count_vector as CV
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    w = np.load(os.path.join(golden_dir, "metric_wrappers.npz"))
+    attrs = [g["age"], g["eth"], g["ins"]]
+    np.testing.assert_array_equal(w["thresholds"], g["thresholds"])
+    for prefix, th in (("multi", dict(zip(M.OUTCOMES, w["thresholds"].tolist()))), ("single", 0.5)):
+        tl = [th[n] for n in M.OUTCOMES] if isinstance(th, dict) else [th] * 3
+        vec = CV.eval_count_vector(g["logits"], g["labels"], attrs, tl)
+        ranks = list(zip(w[f"{prefix}_aucroc"].tolist(), w[f"{prefix}_auprc"].tolist()))
+        capsys.readouterr()
+        M.evaluate_from_logits(None, None, None, th, verbose=True, counts=vec, ranks=ranks)
+        # evaluate_model_multi adds nothing to the text of evaluate_from_logits
+        assert capsys.readouterr().out == str(w[f"{prefix}_stdout"])
+    counts = {m: M.Counts(CV.eval_count_vector(g["mod_logits"][:, 3 * i:3 * i + 3], g["labels"], attrs, (0.5,) * 3))
+              for i, m in enumerate(M.MODALITIES)}
+    w0 = {n: {m: 0.33 for m in M.MODALITIES} for n in M.OUTCOMES}
+    capsys.readouterr()
+    M.weights_from_modality_counts(counts, w0, 1.0, verbose=True)
+    flt = re.compile(r"np\.float64\(([^)]*)\)")
+    got, ref = capsys.readouterr().out, str(w["weights1_stdout"])
+    assert flt.sub("#", got) == flt.sub("#", ref)
+    np.testing.assert_allclose([float(x) for x in flt.findall(got)], [float(x) for x in flt.findall(ref)], atol=1e-12)
+
+
 def test_eddi_fusion_oracle_vs_reference_golden(golden_dir):
     """Per-batch EDDI-weighted logit fusion (08_multimodal_eddi_fusion.py; B200 implementation: next
     round): oracle forward with the in-forward EDDI (integer error counts -> weights bit-exact in float64), the focal +
