@@ -166,8 +166,12 @@ class BertModelB200(nn.Module):
         return x32
 
     @torch.no_grad()
-    def encode(self, input_ids, attention_mask=None):
-        """Last hidden state as bf16 [batch*seq, hidden] (row-major, sequence-major)."""
+    def encode(self, input_ids, attention_mask=None, cls_only=False):
+        """Last hidden state as bf16 [batch*seq, hidden] (row-major, sequence-major); with cls_only the hidden state
+        of token 0 of every sequence, bf16 [batch, hidden] -- all the reference reads from the note encoder
+        (`last_hidden_state[:, 0, :]`, 10_FAME.py:141).  In that mode the LAST layer computes keys / values for every
+        token but the query, the attention, the attention output, both LayerNorms and the feed-forward block for the
+        CLS rows only (the other rows of the last layer feed nothing): same numbers, 1/12 less work."""
         if not input_ids.is_cuda:
             raise RuntimeError("BertModelB200 runs on a B200 only: move inputs to cuda (no CPU fallback)")
         c = self.config
@@ -184,7 +188,10 @@ class BertModelB200(nn.Module):
                 kv_len = ops.mask_kv_len(mask)      # once per batch: the 12 layers skip all-padding key blocks
         e = pk["emb"]
         x = ops.bert_embed(input_ids.to(torch.int64), e["word"], e["pos"], e["type0"], e["g"], e["b"], eps, S)
-        for l in pk["layers"]:
+        n_layers = len(pk["layers"])
+        for li, l in enumerate(pk["layers"]):
+            if cls_only and li == n_layers - 1 and S > 1 and H // nh == 64:
+                return self._last_layer_cls(x, l, B, S, mask, eps)
             if S == 1:
                 # one key per sequence: softmax == 1 exactly, so the context is the value projection itself and
                 # Q / K never influence the output (the demographic encoder's shape, 10_FAME.py:199, 715-716)
@@ -199,7 +206,21 @@ class BertModelB200(nn.Module):
             h = ops.gemm_bias_act(x, l["w1"], l["b1"], act=ops.ACT_GELU_ERF)
             t = ops.gemm_bias_act(h, l["w2"], l["b2"], residual=x)
             x = ops.layernorm(t, l["ln2"][0], l["ln2"][1], eps, out=t)
-        return x
+        return x.view(B, S, H)[:, 0, :] if cls_only else x
+
+    def _last_layer_cls(self, x, l, B, S, mask, eps):
+        """Last encoder layer for the CLS rows only: K / V projection of all tokens, then one query per sequence."""
+        c = self.config
+        H, nh = c.hidden_size, c.num_attention_heads
+        x_cls = x.view(B, S, H)[:, 0, :]                                     # [B, H] view, row stride S * H
+        kv = ops.gemm_bias_act(x, l["wqkv"][H:], l["bqkv"][H:])              # [B*S, 2H]: keys | values
+        q = ops.gemm_bias_act(x_cls, l["wqkv"][:H], l["bqkv"][:H])           # [B, H]
+        ctx = ops.attn_cls(q, kv, B, S, nh, H // nh, 0, H, key_mask=mask)
+        t = ops.gemm_bias_act(ctx, l["wo"], l["bo"])
+        y = ops.layernorm(t, l["ln1"][0], l["ln1"][1], eps, out=t, residual=x_cls)
+        h = ops.gemm_bias_act(y, l["w1"], l["b1"], act=ops.ACT_GELU_ERF)
+        t = ops.gemm_bias_act(h, l["w2"], l["b2"], residual=y)
+        return ops.layernorm(t, l["ln2"][0], l["ln2"][1], eps, out=t)
 
     def forward(self, input_ids=None, attention_mask=None):
         """HF-style call: returns an object with ``last_hidden_state`` [batch, seq, hidden] (float32)."""

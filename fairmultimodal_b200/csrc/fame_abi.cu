@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
 
+#include "attn_cls.cuh"
 #include "attn_pair_sm100.cuh"
 #include "attn_bwd_sm100.cuh"
 #include "backward.cuh"
@@ -343,6 +344,33 @@ int fame_mask_kv_len(const uint8_t* key_mask, int32_t batch, int32_t seq, int32_
     if (rc != FAME_OK) return rc;
     if (batch == 0) return FAME_OK;
     fame::mask_kv_len_kernel<<<(batch + 7) / 8, 256, 0, stream>>>(key_mask, batch, seq, kv_len);
+    return launch_status();
+}
+
+int fame_attn_cls(const void* q, int64_t ld_q, const void* kv, int64_t ld_kv, int32_t k_col0, int32_t v_col0,
+                  const uint8_t* key_mask, void* ctx, int64_t ld_ctx, int32_t batch, int32_t seq, int32_t heads,
+                  int32_t head_dim, float scale, fame_stream_t stream) {
+    if (q == nullptr || kv == nullptr || ctx == nullptr) return FAME_ERR_NULLPTR;
+    if (head_dim != fame::kAcD || seq <= 0 || heads <= 0 || batch < 0 || k_col0 < 0 || v_col0 < 0) return FAME_ERR_SHAPE;
+    if (seq > 12000) return FAME_ERR_SHAPE;                        // the probability row lives in shared memory
+    const int64_t width = (int64_t)heads * head_dim;
+    if (ld_q < width || ld_ctx < width || ld_kv < (k_col0 > v_col0 ? k_col0 : v_col0) + width) return FAME_ERR_SHAPE;
+    if ((ld_q & 7) || (ld_kv & 7) || (ld_ctx & 7) || (k_col0 & 7) || (v_col0 & 7)) return FAME_ERR_ALIGN;
+    if (!aligned16(q) || !aligned16(kv) || !aligned16(ctx)) return FAME_ERR_ALIGN;
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    if (batch == 0) return FAME_OK;
+    if (batch > 65535) return FAME_ERR_SHAPE;
+    fame::AttnClsParams p;
+    p.q = reinterpret_cast<const __nv_bfloat16*>(q);
+    p.kv = reinterpret_cast<const __nv_bfloat16*>(kv);
+    p.key_mask = key_mask;
+    p.ctx = reinterpret_cast<__nv_bfloat16*>(ctx);
+    p.ld_q = ld_q; p.ld_kv = ld_kv; p.ld_ctx = ld_ctx;
+    p.k_col0 = k_col0; p.v_col0 = v_col0; p.seq = seq; p.heads = heads;
+    p.scale_log2e = scale * 1.4426950408889634f;
+    fame::attn_cls_kernel<<<dim3(heads, batch), fame::kAcThreads, (size_t)seq * sizeof(float), stream>>>(p);
     return launch_status();
 }
 

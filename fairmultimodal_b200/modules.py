@@ -43,13 +43,16 @@ class BioClinicalBERT_FT(nn.Module):
         return cls(bert)
 
     def encode_chunks(self, input_ids, attention_mask):
-        """bf16 last hidden state [chunks*seq, hidden] (kept on device; CLS rows are every seq-th row)."""
+        """bf16 last hidden state of EVERY token [chunks*seq, hidden] (kept on device; CLS rows are every seq-th
+        row).  The reference never reads the other rows: encode_cls is the hot path."""
         return self.BioBert.encode(input_ids, attention_mask)
 
+    def encode_cls(self, input_ids, attention_mask):
+        """bf16 CLS hidden state [chunks, hidden] (on device): what forward returns, before the cast to float32."""
+        return self.BioBert.encode(input_ids, attention_mask, cls_only=True)
+
     def forward(self, input_ids, attention_mask):
-        C, S = input_ids.shape
-        h = self.BioBert.encode(input_ids, attention_mask)
-        return h.view(C, S, -1)[:, 0, :].float()
+        return self.encode_cls(input_ids, attention_mask).float()
 
 
 def pool_chunks(cls_rows, offsets, mode="mean", ldx=None, cols=None):

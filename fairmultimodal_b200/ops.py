@@ -112,7 +112,7 @@ def gemm_bias_act(x, w, bias=None, residual=None, act=ACT_NONE, out=None, out_dt
     a.y_dtype = DT_F32 if out.dtype == torch.float32 else DT_BF16
     a.M, a.N, a.K, a.act = M, N, K, act
     _set_drop(a.drop, drop)
-    _call("fame_gemm_bias_act", a, 2.0 * M * N * K, f"{N}x{K}")
+    _call("fame_gemm_bias_act", a, 2.0 * M * N * K, f"{'sk' if M <= 32 and K % 32 == 0 else 'tc'}:{M}x{N}x{K}")
     return out
 
 
@@ -215,6 +215,24 @@ def attn_fwd(qkv, batch, seq, heads, head_dim, key_mask=None, scale=None, out=No
         a.kv_len = None
     _set_drop(a.drop, drop)
     _call("fame_attn_fwd", a, 4.0 * batch * heads * seq * seq * head_dim)
+    return out
+
+
+def attn_cls(q, kv, batch, seq, heads, head_dim, k_col0, v_col0, key_mask=None, scale=None):
+    """Attention of ONE query per sequence: q bf16 [batch, heads*head_dim] (the query projection of the CLS rows), kv
+    bf16 [batch*seq, *] holding K at columns k_col0.. and V at v_col0.. -> ctx bf16 [batch, heads*head_dim]."""
+    _cuda(q, "q", torch.bfloat16)
+    _cuda(kv, "kv", torch.bfloat16)
+    out = torch.empty((batch, heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    mp = None
+    if key_mask is not None:
+        _cuda(key_mask, "key_mask", torch.uint8)
+        if not key_mask.is_contiguous() or key_mask.numel() != batch * seq:
+            raise _lib.FameError("key_mask must be contiguous uint8 [batch, seq]")
+        mp = key_mask.data_ptr()
+    _call_flat("fame_attn_cls", 4.0 * batch * seq * heads * head_dim, q.data_ptr(), _rowmajor(q, "q"), kv.data_ptr(),
+               _rowmajor(kv, "kv"), k_col0, v_col0, mp, out.data_ptr(), _rowmajor(out, "ctx"), batch, seq, heads,
+               head_dim, float(scale) if scale is not None else head_dim ** -0.5)
     return out
 
 

@@ -50,7 +50,8 @@ def gemm_ex(a, b, y, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldy=No
     ops._set_drop(g.drop, drop)
     if pre_act is not None:
         g.pre_act, g.ld_pre = pre_act.data_ptr(), pre_act.stride(0)
-    ops._call("fame_gemm_ex", g, 2.0 * M * N * K * nb0 * nb1, tag)
+    skinny = M <= SKINNY_MAX_ROWS and not a_mn and not b_mn and nb0 == 1 and nb1 == 1 and K % 32 == 0 and split_k == 0 and n_valid == 0
+    ops._call("fame_gemm_ex", g, 2.0 * M * N * K * nb0 * nb1, f"{'sk' if skinny else 'tc'}:{tag}:{M}x{N}x{K}")
     return y
 
 

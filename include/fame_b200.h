@@ -209,6 +209,17 @@ int fame_attn_fwd(const fame_attn_fwd_args* a, void* workspace, size_t workspace
  * shared by the 12 layers. */
 int fame_mask_kv_len(const uint8_t* key_mask, int32_t batch, int32_t seq, int32_t* kv_len, fame_stream_t stream);
 
+/* fame_attn_cls: attention for ONE query row per sequence (head_dim 64) -- the last encoder layer of the note
+ * encoder, whose output the reference reads at token 0 only (`last_hidden_state[:, 0, :]`, 10_FAME.py:141; attention
+ * per HF modeling_bert.py:192-206 with the key-padding mask of HF:709-713).  q bf16 [batch, heads * 64] (row stride
+ * ld_q): the query projection of the CLS rows; kv bf16 [batch * seq, >= max(k_col0, v_col0) + heads * 64] (row stride
+ * ld_kv): key / value projections of ALL tokens, head h at columns k_col0 + 64 h / v_col0 + 64 h; key_mask uint8
+ * [batch, seq] or NULL; ctx bf16 [batch, heads * 64] (row stride ld_ctx).  A sequence whose keys are all masked gets a
+ * zero row, like fame_attn_fwd.  HBM-bound streaming kernel (reads K and V once), no tensor cores. */
+int fame_attn_cls(const void* q, int64_t ld_q, const void* kv, int64_t ld_kv, int32_t k_col0, int32_t v_col0,
+                  const uint8_t* key_mask, void* ctx, int64_t ld_ctx, int32_t batch, int32_t seq, int32_t heads,
+                  int32_t head_dim, float scale, fame_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K5  fame_segment_mean:  out[p,:] = mean_{c in [offsets[p], offsets[p+1])} x[c*ldx : c*ldx+cols]; zeros if empty.
  * The CLS gather is folded in through ldx (= seq_len*hidden when x is the encoder's last hidden state).

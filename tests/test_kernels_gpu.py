@@ -259,3 +259,35 @@ def test_segment_reduce_bit_exact(mode):
     cls = hs.view(-1, 16, 768)[:, 0].float().cpu().numpy()
     ref = np.stack([f(cls[offs[i]:offs[i + 1]], axis=0) if counts[i] else np.zeros(768, np.float32) for i in range(len(counts))])
     np.testing.assert_array_equal(out, ref)
+
+
+@pytest.mark.parametrize("B,S,masked", [(3, 512, True), (2, 512, False), (5, 77, True), (2, 1, False), (260, 128, True)])
+def test_attention_cls_query(B, S, masked):
+    """fame_attn_cls (one query per sequence, K / V of all tokens; the note encoder's last layer) against fp32 torch,
+    including an all-masked sequence (zero row) and strided q (CLS rows of a [B*S, H] tensor)."""
+    from fairmultimodal_b200 import ops
+    H, D = 12, 64
+    torch.manual_seed(S + B)
+    x = torch.randn(B * S, H * D, device="cuda").bfloat16()              # queries are rows 0, S, 2S, ... of this
+    kv = torch.randn(B * S, 2 * H * D, device="cuda").bfloat16()
+    mask = None
+    if masked:
+        lens = torch.randint(1, S + 1, (B,), device="cuda")
+        mask = (torch.arange(S, device="cuda")[None, :] < lens[:, None])
+        if B > 2:
+            mask[1] = False                                                # nothing attended: zero row
+        mask = mask.to(torch.uint8).contiguous()
+    q = x.view(B, S, H * D)[:, 0, :]
+    ctx = ops.attn_cls(q, kv, B, S, H, D, 0, H * D, key_mask=mask)
+    qf = q.float().view(B, H, 1, D)
+    k = kv[:, :H * D].float().view(B, S, H, D).permute(0, 2, 1, 3)
+    v = kv[:, H * D:].float().view(B, S, H, D).permute(0, 2, 1, 3)
+    s = (qf @ k.transpose(-1, -2)) * D ** -0.5
+    if mask is not None:
+        s = s.masked_fill(mask[:, None, None, :] == 0, float("-inf"))
+    pr = torch.softmax(s, -1)
+    pr = torch.where(torch.isnan(pr), torch.zeros_like(pr), pr)
+    ref = (pr @ v).reshape(B, H * D)
+    _close(ctx, ref, 1e-2)
+    if masked and B > 2:
+        assert ctx[1].abs().max().item() == 0.0

@@ -97,3 +97,21 @@ def test_full_size_properties():
     d = model(ids2, mask)
     assert torch.equal(d, a)
     assert torch.isfinite(a).all()
+
+
+def test_cls_only_last_layer_equals_full_encoder():
+    """The hot path computes the last layer for the CLS rows only (the reference reads last_hidden_state[:, 0, :],
+    10_FAME.py:141).  It must agree with the CLS rows of the all-token encoder: identical up to the last layer, and
+    there the only arithmetic difference is the attention (fp32 probabilities on the one-query kernel, bf16 P on the
+    tensor-core kernel)."""
+    from fairmultimodal_b200 import modules, synth
+    sd = {k: torch.from_numpy(v) for k, v in
+          synth.synth_state_dict(synth.bert_shapes("BioBert.", synth.VOCAB, layers=3), 11).items()}
+    model = modules.BioClinicalBERT_FT.from_state_dict(sd, num_hidden_layers=3).cuda()
+    for seq in (512, 200):
+        co = synth.make_cohort(5, lab_tokens=4, chunks=4, seq_len=seq, seed=seq + 1)
+        ids, mask = torch.from_numpy(co["input_ids"]).cuda(), torch.from_numpy(co["attention_mask"]).cuda()
+        full = model.encode_chunks(ids, mask).view(ids.shape[0], seq, -1)[:, 0, :].float()
+        cls = model.encode_cls(ids, mask).float()
+        assert cls.shape == full.shape
+        assert (cls - full).abs().max().item() <= 1e-2 * full.abs().max().item()
