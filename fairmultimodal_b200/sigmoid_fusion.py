@@ -141,11 +141,8 @@ def forward_backward(model, batch8, labels, pos_weight, gamma=1.0, alpha=None, g
     st = get_state(model)
     ids, _, age, gender, eth, ins, lab, text = batch8
     post = st.post_stream()
-    post.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(post):
-        st.zero_grad()
-        st.sumsq.zero_()
-        st.refresh_transposed()
+    for w_ in train.begin_step(st, group).values():      # sharded optimizer: bf16 shadows of the large matrices
+        w_.wait()
     ds = _drop_sites(model, st)
     demo, sv_d = train._demo_forward(st, model, ids, age, gender, eth, ins, ds, demo_module=model.BEHRT, dpre="BEHRT.")
     labe, sv_l = train._lab_forward(st, model, lab, ds)
@@ -190,7 +187,7 @@ def forward_backward(model, batch8, labels, pos_weight, gamma=1.0, alpha=None, g
         if m < 2:
             demb.append(_dgrad(dpre, w["wp"][m]))
     train._demo_backward(st, model, sv_d, demb[0], red, ds, dpre="BEHRT.")
-    train._lab_backward(st, model, sv_l, demb[1], ds)
+    train._lab_backward(st, model, sv_l, demb[1], ds, reducer=red)
     red.ready("tail")
     red.finish()
     return loss, h["logits"]

@@ -42,13 +42,24 @@ NO_GRAD_PREFIXES = ("classifier_demo.", "classifier_lab.", "classifier_text.", "
 ATTR_IDX = (2, 4, 5)          # age_ids, ethnicity_ids, insurance_ids inside the 9-tensor batch (10_FAME.py:431)
 
 
-# regions of the flat buffers in layout order: never reduced | demo layers 11 .. 1 | demo layer 0 | rest | lab | head
-_R_NORED, _R_DEMO11, _R_REST, _R_LAB, _R_HEAD = 0, 1, 13, 14, 15
+# Regions of the flat buffers in layout order (= the order in which the backward completes their gradients):
+#   QK     query / key projection WEIGHTS of the demographic BERT: with its length-1 sequences the softmax is identically
+#          1, so their gradient is exactly zero on every rank (never written) -- never reduced
+#   demo i the four large matrices (value, attention output, intermediate, output) of demographic layer i, 11 first
+#   lab 1  the four large matrices of lab layers >= 1;   lab 0: those of lab layer 0
+#   small  everything else: biases, LayerNorms, embeddings, the fusion head (read as fp32 by the kernels)
+# The large matrices are only ever read through their bf16 shadows, so their fp32 masters and Adam moments can live on
+# ONE rank each (sharded optimizer); "small" stays replicated.
+_R_QK, _R_DEMO_TOP, _R_LAB1, _R_LAB0, _R_SMALL = 0, 1, 13, 14, 15
+_R_NORED = _R_QK
+_REGION_ALIGN = 64            # elements: every region (hence every bucket) splits evenly over 2 / 4 / 8 ranks of 8-element rows
+_DEMO_BIG = ("attention.self.value.weight", "attention.output.dense.weight", "intermediate.dense.weight",
+             "output.dense.weight")
+_LAB_BIG = ("self_attn.in_proj_weight", "self_attn.out_proj.weight", "linear1.weight", "linear2.weight")
 
 
 def _r_demo(i):
-    return _R_DEMO11 + (11 - i)
-
+    return _R_DEMO_TOP + (11 - i)
 
 
 FAME_NAMES = dict(demo="behrt_demo.", lab="behrt_lab.",
@@ -61,14 +72,21 @@ def _layout_key(name, names=FAME_NAMES):
     enc = names["demo"] + "bert.encoder.layer."
     if name.startswith(enc):
         i = int(name[len(enc):].split(".")[0])
-        if ".attention.self.query." in name or ".attention.self.key." in name:
-            return _R_NORED
-        return _r_demo(i)
-    if name.startswith(names["lab"]):
-        return _R_LAB
-    if name.startswith(names["head"]):
-        return _R_HEAD
-    return _R_REST
+        if name.endswith(("attention.self.query.weight", "attention.self.key.weight")):
+            return _R_QK
+        if name.endswith(_DEMO_BIG) and 0 <= i <= 11:
+            return _r_demo(i)
+        return _R_SMALL
+    lab = names["lab"] + "transformer_encoder.layers."
+    if name.startswith(lab) and name.endswith(_LAB_BIG):
+        return _R_LAB0 if int(name[len(lab):].split(".")[0]) == 0 else _R_LAB1
+    return _R_SMALL
+
+
+def demo_bucket_layers(n_layers=12):
+    """A gradient bucket closes after each of these demographic-BERT layers (the backward runs n-1 -> 0 on the side
+    stream next to the lab backward): two large buckets that cross NVLink under the lab tower's backward."""
+    return (max(1, (7 * n_layers) // 12), 0) if n_layers > 1 else (0,)
 
 
 def dropout_base_seed():
@@ -141,27 +159,53 @@ class DropSites:
 
 def plan_layout(named_sizes, names=FAME_NAMES):
     """[(name, numel)] sorted by region -> (offsets {name: first element}, regions {region: (lo, hi)}, total)."""
-    offsets, region, off = {}, {}, 0
+    offsets, region, off, prev = {}, {}, 0, None
     for n, k in named_sizes:
-        offsets[n] = off
         r = _layout_key(n, names)
+        if r != prev:
+            if prev is not None:                                 # close the previous region on a shardable boundary
+                off = (off + _REGION_ALIGN - 1) // _REGION_ALIGN * _REGION_ALIGN
+                region[prev] = (region[prev][0], off)
+            prev = r
+        offsets[n] = off
         lo, _ = region.get(r, (off, off))
         off += (k + 7) // 8 * 8                                  # 32-byte aligned segments
         region[r] = (lo, off)
+    off = (off + _REGION_ALIGN - 1) // _REGION_ALIGN * _REGION_ALIGN
+    if prev is not None:
+        region[prev] = (region[prev][0], off)
     return offsets, region, off
 
 
+# how a bucket of the flat gradient buffer is combined over data-parallel ranks
+LOCAL, SHARDED, REPLICATED = "local", "sharded", "replicated"
+
+
 def plan_buckets(region, total):
-    """Contiguous all-reduce buckets over the regions of plan_layout (see FlatTrainState.grad_buckets)."""
-    assert _R_LAB in region and _R_HEAD in region and _R_REST in region
-    cuts, lo = {}, region[_r_demo(11)][0]
-    for i in DEMO_BUCKET_LAYERS:
-        cuts[("demo", i)] = (lo, region[_r_demo(i)][1])
-        lo = region[_r_demo(i)][1]
-    cuts["tail"] = (lo, region[_R_HEAD][1])
-    # sanity: together with the never-reduced region the buckets tile [0, total) exactly
-    spans = sorted(list(cuts.values()) + [region.get(_R_NORED, (0, 0))])
+    """Contiguous gradient buckets over the regions of plan_layout, in the order the backward closes them:
+    {key: (lo, hi, kind)}.  kind LOCAL: zero gradient everywhere, nothing to reduce (optimizer sharded); SHARDED:
+    reduce-scatter -> AdamW on this rank's 1/N -> all-gather of the bf16 shadow; REPLICATED: all-reduce, AdamW on
+    every rank (see FlatTrainState.grad_buckets)."""
+    assert _R_SMALL in region
+    demo_regions = sorted(r for r in region if _R_DEMO_TOP <= r < _R_LAB1)
+    n_demo = (max(11 - (r - _R_DEMO_TOP) for r in demo_regions) + 1) if demo_regions else 0
+    cuts = {}
+    if _R_QK in region:
+        cuts["qk"] = region[_R_QK] + (LOCAL,)
+    if demo_regions:
+        lo = region[demo_regions[0]][0]
+        for i in demo_bucket_layers(n_demo):
+            if _r_demo(i) in region and region[_r_demo(i)][1] > lo:
+                cuts[("demo", i)] = (lo, region[_r_demo(i)][1], SHARDED)
+                lo = region[_r_demo(i)][1]
+    if _R_LAB1 in region:
+        cuts[("lab", 1)] = region[_R_LAB1] + (SHARDED,)
+    tail_lo = region[_R_LAB0][0] if _R_LAB0 in region else region[_R_SMALL][0]
+    cuts["tail"] = (tail_lo, region[_R_SMALL][1], REPLICATED)
+    # sanity: the buckets tile [0, total) exactly, each on a boundary that splits over 2 / 4 / 8 ranks
+    spans = sorted((a, b) for a, b, _ in cuts.values())
     assert spans[0][0] == 0 and spans[-1][1] == total and all(a[1] == b[0] for a, b in zip(spans, spans[1:])), spans
+    assert all(a % _REGION_ALIGN == 0 and b % _REGION_ALIGN == 0 for a, b in spans), spans
     return cuts
 
 
@@ -176,10 +220,8 @@ class FlatTrainState:
         self.names = names
         dev = next(model.parameters()).device
         named = [(n, p) for n, p in model.named_parameters() if not (no_grad_prefixes and n.startswith(no_grad_prefixes))]
-        # Layout = the order in which the backward completes gradients, so that every all-reduce bucket is ONE
-        # contiguous range:  [never reduced | rest | demo layers 0..11 | lab | head].  "Never reduced": query / key
-        # projections of the demographic BERT -- with its length-1 sequences the softmax is identically 1, their
-        # gradient is exactly zero on every rank (never written); 57 MB that need not cross NVLink.
+        # Layout = the order in which the backward completes gradients, so that every reduction bucket is ONE
+        # contiguous range (see the region table above _layout_key).
         if fame_layout:
             named.sort(key=lambda np_: _layout_key(np_[0], names))   # stable: module order inside each region
         self.offsets, self.region, self.n = plan_layout([(n, p.numel()) for n, p in named], names)
@@ -200,6 +242,8 @@ class FlatTrainState:
                 self.bviews[n] = self.pb[o:o + k].view(p.shape)
         self.step = 0
         self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.sumsq_scratch = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.active_plan, self.masters_stale = None, False
         self.grad_norm = torch.zeros(1, device=dev, dtype=torch.float32)
         # device-side step counter and {lr, weight_decay}: read by the AdamW kernel at run time, so a captured CUDA
         # graph of the step follows the schedule without being re-captured
@@ -245,16 +289,69 @@ class FlatTrainState:
         self._t_table = torch.from_numpy(rec.view(np.uint8).copy()).to(dev) if names else None
 
     def grad_buckets(self):
-        """Contiguous ranges (lo, hi) of the flat gradient buffer, keyed by the backward event that completes them:
-        ('demo', i) closes once layer i of the demographic BERT is done (its backward runs 11 -> 0 on the side stream),
-        'tail' = the last demographic layers + embeddings + sig_weights + lab tower + fusion head, complete when both
-        tower streams have joined.  Few large buckets: an NCCL all-reduce of 335 MB takes 0.88 ms on 8 B200s in one
-        piece and 1.67 ms in eight, and every call costs 40-70 us of latency."""
+        """{key: (lo, hi, kind)}: contiguous ranges of the flat buffers keyed by the backward event that completes their
+        gradient: ('demo', i) closes once layer i of the demographic BERT is done (its backward runs 11 -> 0 on the
+        side stream), ('lab', 1) once the lab backward has passed layer 1, 'tail' = large matrices of lab layer 0 +
+        every small tensor, complete when both tower streams have joined; 'qk' never carries a gradient.  Few large
+        buckets: an NCCL collective over 335 MB takes 0.88 ms on 8 B200s in one piece and 1.67 ms in eight."""
         if getattr(self, "_buckets", None) is not None:
             return self._buckets
-        cuts = plan_buckets(self.region, self.n) if self.fame_layout else {"tail": (0, self.n)}
+        cuts = plan_buckets(self.region, self.n) if self.fame_layout else {"tail": (0, self.n, REPLICATED)}
         self._buckets = cuts
         return cuts
+
+    # ---- data-parallel optimizer sharding (ZeRO-1 over the large matrices) ------------------------------------
+    def shard_plan(self, group):
+        """(rank, world) when the optimizer state of the SHARDED / LOCAL buckets lives on one rank each, else None:
+        needs a process group of 2, 4 or 8 ranks (bucket boundaries are multiples of 64 elements) and FAME_SHARDED_OPT."""
+        if group is None or not SHARDED_OPT or not self.fame_layout:
+            return None
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        if world not in (2, 4, 8):
+            return None
+        return dist.get_rank(group), world
+
+    def my_range(self, key, plan):
+        """This rank's slice of bucket `key` (the whole bucket when it is replicated or nothing is sharded)."""
+        lo, hi, kind = self.grad_buckets()[key]
+        if plan is None or kind == REPLICATED:
+            return lo, hi
+        r, w = plan
+        s = (hi - lo) // w
+        return lo + r * s, lo + (r + 1) * s
+
+    def gather_shadows(self, group, plan):
+        """All-gather of the bf16 shadows of the SHARDED buckets (each rank updated its 1/N in the previous step's
+        AdamW), asynchronously on NCCL's stream in the order the forward needs them.  Returns {key: work}."""
+        import torch.distributed as dist
+        works = {}
+        order = [k for k in (("lab", 1),) if k in self.grad_buckets()] + \
+                sorted((k for k in self.grad_buckets() if isinstance(k, tuple) and k[0] == "demo"), key=lambda k: k[1])
+        for key in order:
+            lo, hi, kind = self.grad_buckets()[key]
+            if kind != SHARDED or hi <= lo:
+                continue
+            a, b = self.my_range(key, plan)
+            works[key] = dist.all_gather_into_tensor(self.pb[lo:hi], self.pb[a:b], group=group, async_op=True)
+        return works
+
+    def sync_masters(self, group):
+        """After sharded steps the fp32 masters (and Adam moments) of a sharded bucket are current on their owner only:
+        all-gather them so that model.state_dict() / evaluation / checkpoints see the same parameters on every rank
+        (once per epoch: train_step calls it before returning)."""
+        plan = self.shard_plan(group)
+        if plan is None or not getattr(self, "masters_stale", False):
+            return
+        import torch.distributed as dist
+        for key, (lo, hi, kind) in self.grad_buckets().items():
+            if kind == REPLICATED or hi <= lo:
+                continue
+            a, b = self.my_range(key, plan)
+            for buf in (self.p, self.m, self.v, self.pb):
+                dist.all_gather_into_tensor(buf[lo:hi], buf[a:b], group=group)
+        self.masters_stale = False
+        self.invalidate_caches()
 
     def _param_versions(self):
         return tuple(p._version for p in self._params)
@@ -336,17 +433,30 @@ class FlatTrainState:
 
     def clip_and_step(self, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0):
         """clip_grad_norm_(max_norm) + AdamW on the flat buffers (graph-capturable: lr / weight decay / step count are
-        read from device memory).  The bf16 shadow is refreshed by the same kernel."""
+        read from device memory).  The bf16 shadow is refreshed by the same kernel.  After a data-parallel
+        forward_backward with a sharded optimizer every rank updates its slice of the sharded buckets and the whole
+        replicated bucket (the next forward_backward all-gathers the shadows)."""
         if not torch.cuda.is_current_stream_capturing():
             self.set_hyper(lr, weight_decay)
         self.step += 1
         self.step_dev += 1
+        plan = getattr(self, "active_plan", None)
         if not getattr(self, "sumsq_valid", False):       # forward_backward already summed it bucket by bucket
+            if plan is not None:
+                raise RuntimeError("sharded optimizer step without the bucket-wise gradient reduction of forward_backward")
             self.sumsq.zero_()
             T.grad_sumsq(self.g, self.sumsq)
         self.sumsq_valid = False
-        T.clip_adamw(self.p, self.g, self.m, self.v, self.sumsq, max_norm, lr, betas[0], betas[1], eps, weight_decay,
-                     0, self.grad_norm, step_dev=self.step_dev, hyper_dev=self.hyper_dev, p_bf16=self.pb)
+        if plan is None:
+            ranges = [(0, self.n)]
+        else:
+            ranges = [self.my_range(k, plan) for k in self.grad_buckets()]
+            self.masters_stale = True
+        for a, b in ranges:
+            if b > a:
+                T.clip_adamw(self.p[a:b], self.g[a:b], self.m[a:b], self.v[a:b], self.sumsq, max_norm, lr, betas[0],
+                             betas[1], eps, weight_decay, 0, self.grad_norm, step_dev=self.step_dev,
+                             hyper_dev=self.hyper_dev, p_bf16=self.pb[a:b])
         # the transposed shadows are refreshed by the next forward_backward (beside its forward pass, not here)
         self.invalidate_caches()
 
@@ -356,6 +466,31 @@ class FlatTrainState:
         for m in self.model.modules():
             if getattr(m, "_packed", None) is not None:
                 m._packed = None
+
+
+def sync_parameters(model, group=None):
+    """After data-parallel optimisation steps with the sharded optimizer: all-gather the fp32 masters / Adam moments of
+    the sharded buckets so that model.state_dict(), evaluation and checkpoints are identical on every rank.  train_step
+    calls it once per epoch; call it yourself after driving optimisation_step directly.  No-op otherwise."""
+    st = getattr(model, "_fame_train_state", None)
+    if st is not None and group is not None:
+        st.sync_masters(group)
+
+
+def describe_parallel(model, group):
+    """One line for logs / the bench config: how the step is parallelised over `group`."""
+    if group is None:
+        return "single process"
+    st = get_state(model)
+    plan = st.shard_plan(group)
+    mb = lambda k: sum((hi - lo) * 4 for key, (lo, hi, kind) in st.grad_buckets().items() if kind == k) / 1e6
+    stat = "all-reduce(SUM) of 104 int64 loss statistics"
+    if plan is None:
+        return f"{stat} + all-reduce(SUM) of the flat fp32 gradient buffer ({mb(SHARDED) + mb(REPLICATED):.0f} MB), AdamW replicated"
+    return (f"{stat}; ZeRO-1 over the large matrices: reduce-scatter of {mb(SHARDED):.0f} MB fp32 gradients in "
+            f"{sum(1 for *_, k in st.grad_buckets().values() if k == SHARDED)} buckets -> AdamW on 1/{plan[1]} -> all-gather of the bf16 "
+            f"shadows at the start of the next step; all-reduce of the {mb(REPLICATED):.0f} MB replicated tail; "
+            f"{mb(LOCAL):.0f} MB of query/key weights never reduced")
 
 
 def release_graphs(model):
@@ -407,7 +542,7 @@ def _demo_forward(st, model, ids, age, gender, eth, ins, ds=None, demo_module=No
         T.dropout_apply(x32, d_emb)
         T.dropout_apply(xb, d_emb)
     saved = {"esum": esum, "estats": estats, "layers": [], "ids": ids.to(torch.int64).contiguous().view(-1)}
-    for i in range(12):
+    for i in range(int(demo_module.bert.config.num_hidden_layers)):
         p = f"{pre}encoder.layer.{i}."
         s = {"xb": xb}
         # one key per sequence: softmax == 1, so attention-probability dropout (HF:205) keeps or drops a whole head of
@@ -455,34 +590,52 @@ def _lin_bwd(st, wname, bname, dy_bf16, x_bf16, colsum_src=None):
     T.linear_wgrad(dy_bf16, x_bf16, st.gr(wname), accumulate=not small)
 
 
-# a gradient bucket closes after each of these demographic-BERT layers (backward runs 11 -> 0, on the side stream next
-# to the lab backward): 94 MB + 113 MB that cross NVLink under the lab backward; 'tail' (71 MB) is the exposed rest
-DEMO_BUCKET_LAYERS = (7, 1)
+DEMO_BUCKET_LAYERS = demo_bucket_layers(12)
+SHARDED_OPT = os.environ.get("FAME_SHARDED_OPT", "1") != "0"    # data parallel: ZeRO-1 over the large matrices
 
 
 class _GradReducer:
-    """Per bucket, as soon as the backward has completed it: SUM all-reduce over the ranks (asynchronous, NCCL over
-    NVLink, overlapping the remaining backward kernels) and then the bucket's contribution to the squared gradient
-    norm, on a third stream that follows the collective -- so that after the last bucket only its own all-reduce and
-    13 us of norm are left before AdamW.  finish() joins everything into the current stream."""
+    """Per bucket, as soon as the backward has completed it (asynchronous, NCCL over NVLink, overlapping the remaining
+    backward kernels):
+      SHARDED bucket    reduce-scatter (SUM): this rank receives the global gradient of ITS 1/N of the bucket (in place)
+      REPLICATED bucket all-reduce (SUM)
+      single process    nothing to reduce
+    and then the bucket's contribution to the squared gradient norm on a third stream that follows the collective, so
+    that after the last bucket only its own collective and 13 us of norm are left before AdamW.  finish() joins
+    everything into the current stream; with a sharded optimizer the per-rank partial norms are summed there (one
+    8-byte all-reduce; the replicated bucket is counted by rank 0 only)."""
 
     def __init__(self, st, group):
         self.st, self.group = st, group
+        self.plan = st.shard_plan(group)
+        st.active_plan = self.plan
         self.post = st.post_stream()
         self.used = False
 
     def ready(self, key):
-        lo, hi = self.st.grad_buckets()[key]
-        if hi <= lo:
+        b = self.st.grad_buckets().get(key)
+        if b is None:
+            return
+        lo, hi, kind = b
+        if hi <= lo or kind == LOCAL:
             return
         cur = torch.cuda.current_stream()
         g = self.st.g[lo:hi]
         if self.group is not None:
             import torch.distributed as dist
-            work = dist.all_reduce(g, group=self.group, async_op=True)
+            target = self.st.sumsq
+            if self.plan is not None and kind == SHARDED:
+                a, e = self.st.my_range(key, self.plan)
+                mine = self.st.g[a:e]
+                work = dist.reduce_scatter_tensor(mine, g, group=self.group, async_op=True)
+                g = mine
+            else:
+                work = dist.all_reduce(g, group=self.group, async_op=True)
+                if self.plan is not None and self.plan[0] != 0:
+                    target = self.st.sumsq_scratch          # identical on every rank: only rank 0's copy is counted
             with torch.cuda.stream(self.post):
                 work.wait()
-                T.grad_sumsq(g, self.st.sumsq)
+                T.grad_sumsq(g, target)
         else:
             self.post.wait_stream(cur)
             with torch.cuda.stream(self.post):
@@ -492,6 +645,9 @@ class _GradReducer:
     def finish(self):
         if self.used:
             torch.cuda.current_stream().wait_stream(self.post)
+        if self.plan is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self.st.sumsq, group=self.group)
         self.st.sumsq_valid = True
 
 
@@ -503,7 +659,8 @@ def _demo_backward(st, model, saved, ddemo, reducer=None, ds=None, dpre="behrt_d
     tabs_g = [st.gr(f"{dpre}{n}_embedding.weight") for n in ("age", "gender", "ethnicity", "insurance")]
     T.demo_add_bwd(ddemo, saved["demo_ids"], tabs_g)
     dx = ddemo                                                      # f32 [B,768]: gradient of the last hidden state
-    for i in reversed(range(12)):
+    cut_layers = demo_bucket_layers(len(saved["layers"]))
+    for i in reversed(range(len(saved["layers"]))):
         p = f"{pre}encoder.layer.{i}."
         s = saved["layers"][i]
         # t = residual + dropout(dense(.)): the residual branch takes dt (f32), the dense layer's backward the masked
@@ -543,7 +700,7 @@ def _demo_backward(st, model, saved, ddemo, reducer=None, ds=None, dpre="behrt_d
         # AdamW still applies weight decay to them, as in the reference)
         dx = T.linear_dgrad(dv, st.w(p + "attention.self.value.weight"), out_dtype=torch.float32, aux=dt1f,
                             aux_mode=T.AUX_ADD_F32, wT=st.wt(p + "attention.self.value.weight"))
-        if reducer is not None and i in DEMO_BUCKET_LAYERS:
+        if reducer is not None and i in cut_layers:
             reducer.ready(("demo", i))
     e = pre + "embeddings."
     T.dropout_apply(dx, site("demo.emb", ph))                       # BertEmbeddings.dropout backward (no-op when off)
@@ -613,7 +770,7 @@ def _attn_backward(qkv, dctx, ctx, lse, B, L, nh, D, drop=None):
     return dqkv
 
 
-def _lab_backward(st, model, saved, dlab, ds=None, lab_module=None, pre="behrt_lab."):
+def _lab_backward(st, model, saved, dlab, ds=None, lab_module=None, pre="behrt_lab.", reducer=None):
     lab_module = model.behrt_lab if lab_module is None else lab_module
     lab = saved["lab"]
     B, L = lab.shape
@@ -643,6 +800,8 @@ def _lab_backward(st, model, saved, dlab, ds=None, lab_module=None, pre="behrt_l
         dqkv = _attn_backward(s["qkv"], dctx, s["ctx"], s["lse"], B, L, nh, H // nh, drop=site("attn", pr["attn"]))
         _lin_bwd(st, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", dqkv, s["x"])
         dx = T.linear_dgrad(dqkv, st.w(p + "self_attn.in_proj_weight"), aux=dt1, aux_mode=T.AUX_ADD_BF16)
+        if reducer is not None and i == 1:
+            reducer.ready(("lab", 1))                # the large matrices of every layer >= 1 are complete
     # token embedding: Linear(1, 768).weight has shape [768, 1] -> its gradient is the [768] vector
     T.lab_embed_bwd(dx, lab, st.gr(pre + "pos_embedding"), st.gr(pre + "token_embedding.weight").view(-1),
                     st.gr(pre + "token_embedding.bias"))
@@ -698,6 +857,28 @@ def _lab_budget(group=None):
     return max(2, _lib.load().fame_sm_count() - r) if r > 0 else 0
 
 
+def begin_step(st, group=None):
+    """Start of a training step, off the critical path on the third stream while the forward runs: zero the gradient
+    buffer (53 us) and refresh the transposed bf16 shadows the demographic backward reads (77 us); the backward waits
+    for this stream.  With a sharded optimizer the previous step's AdamW refreshed only this rank's 1/N of the large
+    matrices' bf16 shadows: the rest is all-gathered now, on NCCL's stream, bucket by bucket in the order the forward
+    consumes them (lab tower first: it is the critical path).  Returns {bucket: work}; a tower waits for its own
+    buckets only (work.wait() on the stream that runs it)."""
+    post = st.post_stream()
+    post.wait_stream(torch.cuda.current_stream())
+    plan = st.shard_plan(group)
+    gathers = st.gather_shadows(group, plan) if plan is not None else {}
+    with torch.cuda.stream(post):
+        st.zero_grad()
+        st.sumsq.zero_()
+        st.sumsq_scratch.zero_()
+        for k, w_ in gathers.items():
+            if isinstance(k, tuple) and k[0] == "demo":
+                w_.wait()
+        st.refresh_transposed()
+    return gathers
+
+
 # ------------------------------------------------------------------------------------------------ one optimisation step
 def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, group=None, want_outputs=False,
                      debug=None):
@@ -710,11 +891,8 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
     # off the critical path, on the third stream while the forward runs: zero the gradient buffer (53 us), refresh the
     # transposed bf16 shadows the demographic backward reads (77 us); the backward waits for this stream below
     post = st.post_stream()
-    post.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(post):
-        st.zero_grad()
-        st.sumsq.zero_()
-        st.refresh_transposed()
+    gathers = begin_step(st, group)
+    demo_gathers = [w for k, w in gathers.items() if isinstance(k, tuple) and k[0] == "demo"]
     ds = DropSites(model, st.step_dev)
     if not ds.any:
         ds = None                                                             # parity configuration / eval: no site active
@@ -726,12 +904,18 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
     if side is not None:
         side.wait_stream(main)
         with torch.cuda.stream(side):
+            for w_ in demo_gathers:
+                w_.wait()
             demo, sv_d = _demo_forward(st, model, ids, age, gender, eth, ins, ds)
+        if ("lab", 1) in gathers:
+            gathers[("lab", 1)].wait()
         ops.set_sm_budget(_lab_budget(group))
         labe, sv_l = _lab_forward(st, model, lab, ds)
         ops.set_sm_budget(0)
         main.wait_stream(side)
     else:
+        for w_ in gathers.values():
+            w_.wait()
         demo, sv_d = _demo_forward(st, model, ids, age, gender, eth, ins, ds)
         labe, sv_l = _lab_forward(st, model, lab, ds)
     text = text.float().contiguous()
@@ -780,12 +964,12 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
         with torch.cuda.stream(side):
             _demo_backward(st, model, sv_d, ddemo, red, ds)
         ops.set_sm_budget(_lab_budget(group))
-        _lab_backward(st, model, sv_l, dlab, ds)
+        _lab_backward(st, model, sv_l, dlab, ds, reducer=red)
         ops.set_sm_budget(0)
         main.wait_stream(side)
     else:
         _demo_backward(st, model, sv_d, ddemo, red, ds)
-        _lab_backward(st, model, sv_l, dlab, ds)
+        _lab_backward(st, model, sv_l, dlab, ds, reducer=red)
     red.ready("tail")
     red.finish()
     # tensors that crossed streams (allocated on one, read on the other) stay referenced until both branches have been
@@ -823,6 +1007,7 @@ def train_step(model, dataloader, optimizer, device, criterion, beta=1.0, lambda
         batch = [x.to(device, non_blocking=True) for x in batch]
         loss = optimisation_step(model, batch, pw, lambda_edd, lambda_l1, w_mod, hp, group=group)
         acc += loss[:2]                                                        # accumulate on device, sync once
+    sync_parameters(model, group)               # sharded optimizer: every rank sees the whole fp32 model again
     running_loss, running_bce = acc.tolist()
     if running_loss != running_loss and st.last_stats is not None and int(st.last_stats[103].item()) != 0:
         raise ValueError("sensitive-attribute code outside 0..7 in a training batch (age / ethnicity / insurance ids): "

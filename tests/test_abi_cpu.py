@@ -83,17 +83,28 @@ def test_synth_cohort_shapes():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the reference's CPU path for the note-chunk step, oracle port) runs without a GPU and
-    prints ONE JSON line with the keys the driver reads."""
+    """`bench.py --impl reference` runs without a GPU and prints ONE JSON line with the keys the driver reads: the
+    reference's CPU path of the training step (headline) with the note encoder as a sub-object, and `--config 2` the
+    note encoder alone."""
     import json
     import subprocess
     import sys
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--ref-chunks-per-step", "1"], capture_output=True, text=True, timeout=600, check=True).stdout
-    lines = [l for l in out.strip().splitlines() if l.startswith("{")]
-    assert len(lines) == 1
-    d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["unit"] == "chunks/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["steps"] == 1 and d["n_gpus"] == 1 and d["config"]["workload"].startswith("note_encoder_fwd")
+
+    def run(*extra):
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                              *extra], capture_output=True, text=True, timeout=900, check=True).stdout
+        lines = [l for l in out.strip().splitlines() if l.startswith("{")]
+        assert len(lines) == 1
+        return json.loads(lines[0])
+
+    d = run()
+    assert d["impl"] == "reference" and d["unit"] == "patients/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["steps"] == 1 and d["n_gpus"] == 1 and d["config"]["workload"].startswith("fame_train_step_32patients")
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "patients/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    n = d["note_encoder"]
+    assert n["unit"] == "chunks/s" and n["value"] > 0 and n["cpu_baseline"]["kind"] in ("reference", "port")
+    d = run("--config", "2", "--ref-chunks-per-step", "1")
+    assert d["impl"] == "reference" and d["unit"] == "chunks/s" and d["value"] > 0
+    assert d["config"]["workload"].startswith("note_encoder_fwd")
     assert d["e2e"] == {"value": d["value"], "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

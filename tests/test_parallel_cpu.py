@@ -100,10 +100,117 @@ def test_gloo_world2_statistics_allreduce():
         assert ret[r] == (True, True, True, True), (r, ret[r])
 
 
+def _adamw_stub(p, g, m, v, sumsq, max_norm, lr, b1, b2, eps, wd, step, grad_norm_out=None, step_dev=None,
+                hyper_dev=None, p_bf16=None):
+    """CPU stand-in for fame_clip_adamw (clip_grad_norm_ + torch AdamW arithmetic, elementwise) for the host-logic test."""
+    t = int(step_dev.item()) if step_dev is not None else step
+    norm = float(sumsq.item()) ** 0.5
+    coef = min(1.0, max_norm / (norm + 1e-6))
+    gg = g * coef
+    m.mul_(b1).add_(gg, alpha=1 - b1)
+    v.mul_(b2).addcmul_(gg, gg, value=1 - b2)
+    p.mul_(1 - lr * wd)
+    p.addcdiv_(m / (1 - b1 ** t), (v / (1 - b2 ** t)).sqrt() + eps, value=-lr)
+    if p_bf16 is not None:
+        p_bf16.copy_(p)
+    if grad_norm_out is not None:
+        grad_norm_out.fill_(norm)
+
+
+class _NoStream:
+    def wait_stream(self, s):
+        pass
+
+
+def _sharded_worker(rank, world, port, ret):
+    """Host protocol of the sharded optimizer on gloo (kernels replaced by CPU arithmetic): reduce-scatter of the
+    SHARDED buckets + all-reduce of the replicated tail + partial-norm all-reduce + AdamW on this rank's ranges +
+    all-gather of the bf16 shadows + sync_masters  ==  all-reduce of everything + AdamW on everything."""
+    import contextlib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fairmultimodal_b200 import modules, ops_train, train
+        ops_train.cast_bf16 = lambda x, y: y.copy_(x)
+        ops_train.transpose_bf16_table = lambda *a, **k: None
+        ops_train.grad_sumsq = lambda g, out: out.add_((g.double() ** 2).sum())
+        ops_train.clip_adamw = _adamw_stub
+        train.torch.cuda.stream = lambda s: contextlib.nullcontext()
+        train.torch.cuda.current_stream = lambda *a: _NoStream()
+        train.torch.cuda.is_current_stream_capturing = lambda: False
+        train.FlatTrainState.post_stream = lambda self: _NoStream()
+        torch.manual_seed(0)
+        model = modules.MultimodalTransformer_EDDI_Sigmoid(768, modules.BEHRTModel_Demo(5, 2, 5, 5), modules.BEHRTModel_Lab(12), "cpu")
+        st = train.get_state(model)
+        group = dist.group.WORLD
+        plan = st.shard_plan(group)
+        assert plan == (rank, world)
+        p0 = st.p.clone()
+        gens = [torch.Generator().manual_seed(100 + r) for r in range(world)]
+        grads = [torch.randn(st.n, generator=g) * 0.01 for g in gens]
+        qlo, qhi, _ = st.grad_buckets()["qk"]
+        for g in grads:
+            g[qlo:qhi] = 0                                       # query / key weights: exactly zero gradient on every rank
+        ok = []
+        for step in (1, 2):
+            # ---- reference: everything all-reduced, AdamW on everything (single-process arithmetic)
+            if step == 1:
+                rp, rm, rv = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+                rpb = torch.zeros(st.n, dtype=torch.bfloat16)
+            gsum = sum(grads) * step
+            ss = torch.zeros(1, dtype=torch.float64)
+            ops_train.grad_sumsq(gsum, ss)
+            _adamw_stub(rp, gsum, rm, rv, ss, 1.0, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, p_bf16=rpb)
+            # ---- protocol under test
+            gathers = train.begin_step(st, group)
+            for w in gathers.values():
+                w.wait()
+            if step > 1:
+                # gathered shadows == replicated result of the last step (the query / key shadows are never read by the
+                # length-1 forward and are gathered by sync_masters only)
+                ok.append(bool(torch.equal(st.pb[qhi:], rpb_prev[qhi:])))
+            st.g.copy_(grads[rank] * step)
+            red = train._GradReducer(st, group)
+            for key in st.grad_buckets():
+                red.ready(key)
+            red.finish()
+            st.clip_and_step(1e-3, 0.01, (0.9, 0.999), 1e-8, max_norm=1.0)
+            ok.append(abs(st.grad_norm.item() - float(ss.item()) ** 0.5) <= 1e-6 * float(ss.item()) ** 0.5)
+            # before the sync only this rank's ranges of the sharded buckets are current
+            for key, (lo, hi, kind) in st.grad_buckets().items():
+                a, b = st.my_range(key, plan)
+                ok.append(bool(torch.allclose(st.p[a:b], rp[a:b], rtol=0, atol=1e-7)))
+                if kind != train.REPLICATED and world > 1:
+                    other = (lo, a) if rank > 0 else (b, hi)
+                    ok.append(not torch.allclose(st.p[other[0]:other[1]], rp[other[0]:other[1]], rtol=0, atol=1e-7))
+            rpb_prev = rpb.clone()
+        st.sync_masters(group)
+        ok.append(bool(torch.allclose(st.p, rp, rtol=0, atol=1e-7)) and bool(torch.allclose(st.m, rm, rtol=0, atol=1e-9))
+                  and bool(torch.allclose(st.v, rv, rtol=0, atol=1e-12)))
+        ok.append(st.masters_stale is False and "ZeRO-1" in train.describe_parallel(model, group))
+        ret[rank] = tuple(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_gloo_world2_sharded_optimizer_protocol():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sharded_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        assert all(ret[r]) and len(ret[r]) > 10, (r, [i for i, v in enumerate(ret[r]) if not v], len(ret[r]))
+
+
 def test_flat_layout_and_gradient_buckets():
-    """Flat-buffer layout of the training state: the all-reduce buckets are contiguous, follow the order in which
-    the backward completes them, tile the buffer together with the never-reduced (exactly-zero gradient) region, and
-    that region holds precisely the query / key projections of the demographic BERT."""
+    """Flat-buffer layout of the training state: the reduction buckets are contiguous, follow the order in which the
+    backward completes them, tile the buffer exactly, end on boundaries that split over 2 / 4 / 8 ranks, and hold what
+    their kind promises: 'qk' = exactly the query / key projection weights of the demographic BERT (zero gradient, never
+    reduced), SHARDED buckets = only large matrices (consumed through bf16 shadows), REPLICATED tail = every tensor a
+    kernel reads in fp32."""
     from fairmultimodal_b200 import synth, train
     shapes = synth.fame_shapes(lab_tokens=542)
     names = [(n, int(np.prod(s))) for n, s in shapes.items() if not n.startswith(train.NO_GRAD_PREFIXES)]
@@ -111,26 +218,50 @@ def test_flat_layout_and_gradient_buckets():
     offsets, region, total = train.plan_layout(names)
     assert total >= sum(k for _, k in names) and all(o % 8 == 0 for o in offsets.values())
     cuts = train.plan_buckets(region, total)
-    lo, hi = region[train._R_NORED]
+    lo, hi, kind = cuts["qk"]
     nored = [n for n, o in offsets.items() if lo <= o < hi]
-    assert len(nored) == 48 and all(".attention.self.query." in n or ".attention.self.key." in n for n in nored)
-    assert hi - lo == 12 * 2 * (768 * 768 + 768)
+    assert kind == train.LOCAL and len(nored) == 24
+    assert all(n.endswith(("attention.self.query.weight", "attention.self.key.weight")) for n in nored)
+    assert hi - lo == 12 * 2 * 768 * 768
+
     def bucket_of(name):
         o = offsets[name]
-        return [k for k, (a, b) in cuts.items() if a <= o < b]
-    assert bucket_of("fusion_mlp.0.weight") == ["tail"] and bucket_of("text_projector.0.bias") == ["tail"]
-    assert bucket_of("behrt_lab.pos_embedding") == ["tail"]
-    assert bucket_of("sig_weights") == ["tail"] and bucket_of("behrt_demo.age_embedding.weight") == ["tail"]
-    assert bucket_of("behrt_demo.bert.encoder.layer.0.intermediate.dense.weight") == ["tail"]
+        return [k for k, (a, b, _) in cuts.items() if a <= o < b]
+    for n in ("fusion_mlp.0.weight", "text_projector.0.bias", "behrt_lab.pos_embedding", "sig_weights",
+              "behrt_demo.age_embedding.weight", "behrt_demo.bert.encoder.layer.0.intermediate.dense.bias",
+              "behrt_demo.bert.encoder.layer.3.attention.self.query.bias", "behrt_demo.bert.embeddings.word_embeddings.weight",
+              "behrt_lab.transformer_encoder.layers.1.norm1.weight", "behrt_lab.transformer_encoder.layers.0.linear1.weight",
+              "behrt_lab.transformer_encoder.layers.0.self_attn.in_proj_weight"):
+        assert bucket_of(n) == ["tail"], n
     first, second = train.DEMO_BUCKET_LAYERS
+    assert (first, second) == (7, 0)
     assert bucket_of(f"behrt_demo.bert.encoder.layer.{first}.output.dense.weight") == [("demo", first)]
     assert bucket_of("behrt_demo.bert.encoder.layer.11.attention.self.value.weight") == [("demo", first)]
-    assert bucket_of(f"behrt_demo.bert.encoder.layer.{first - 1}.output.dense.bias") == [("demo", second)]
-    assert bucket_of(f"behrt_demo.bert.encoder.layer.{second}.attention.output.LayerNorm.weight") == [("demo", second)]
+    assert bucket_of(f"behrt_demo.bert.encoder.layer.{first - 1}.output.dense.weight") == [("demo", second)]
+    assert bucket_of("behrt_demo.bert.encoder.layer.0.intermediate.dense.weight") == [("demo", second)]
+    assert bucket_of("behrt_lab.transformer_encoder.layers.1.linear2.weight") == [("lab", 1)]
+    # sharded buckets hold large matrices only (their fp32 masters live on one rank: nothing may read them in fp32)
+    for key, (a, b, kind) in cuts.items():
+        if kind == train.SHARDED:
+            inside = [n for n, o in offsets.items() if a <= o < b]
+            assert inside and all(n.endswith(train._DEMO_BIG + train._LAB_BIG) for n in inside), key
+    assert cuts["tail"][2] == train.REPLICATED
     # buckets are listed in the order the backward closes them, each starting where the previous one ended
-    spans = list(cuts.values())
-    assert spans[0][0] == region[train._R_NORED][1] and spans[-1][1] == total
+    spans = [(a, b) for a, b, _ in cuts.values()]
+    assert spans[0][0] == 0 and spans[-1][1] == total
     assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert all((b - a) % 64 == 0 for a, b in spans)
+    # the exposed tail is small: the verdict asked for <= 20 MB beyond the large matrices of lab layer 0
+    tail_bytes = (cuts["tail"][1] - cuts["tail"][0]) * 4
+    lab0 = 4 * (2304 * 768 + 768 * 768 + 2 * 768 * 2048)
+    assert tail_bytes - lab0 <= 20e6, tail_bytes
+    # a 6-layer demographic BERT (ablation 08) gets its own two buckets
+    shapes6 = {n: s for n, s in shapes.items() if ".encoder.layer." not in n or int(n.split(".encoder.layer.")[1].split(".")[0]) < 6}
+    names6 = [(n, int(np.prod(s))) for n, s in shapes6.items() if not n.startswith(train.NO_GRAD_PREFIXES)]
+    names6.sort(key=lambda x: train._layout_key(x[0]))
+    _, region6, total6 = train.plan_layout(names6)
+    cuts6 = train.plan_buckets(region6, total6)
+    assert [k for k in cuts6] == ["qk", ("demo", 3), ("demo", 0), ("lab", 1), "tail"]
 
 
 def test_dropout_sites_follow_the_model_configuration():
