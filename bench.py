@@ -70,44 +70,101 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed regions."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed regions only (`with sampler.region():` around every timed
+    loop): NVML from a background thread every ~3 ms while a region is open.  Falls back to one nvidia-smi loop over
+    the whole run when NVML cannot be loaded."""
+    NAMES = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
-
-    def start(self):
+        self.index, self.sm, self.mx, self.reasons, self.active, self.stop_flag = index, [], 0, set(), False, False
+        self.nvml = self.handle = self.thread = self.smi = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.nvml = None
+            self._start_smi()
+
+    def _loop(self):
+        n = self.nvml
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                    r = int(reasons(self.handle))
+                    for name, bit in self.NAMES:
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.003)
+            else:
+                time.sleep(0.0005)
+
+    def _start_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.lines = []
+        try:
+            self.smi = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                         "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.smi.stdout], daemon=True).start()
+        except Exception:
+            self.smi = None
+
+    def region(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            self.active = True
+            try:
+                yield
+            finally:
+                self.active = False
+        return cm()
 
     def stop(self):
-        if self.proc is None:
+        self.stop_flag = True
+        if self.nvml is None:
+            if self.smi is None:
+                return None
+            time.sleep(0.12)
+            self.smi.terminate()
+            for l in self.lines:
+                f = [x.strip() for x in l.split(",")]
+                try:
+                    self.sm.append(float(f[0])); self.mx = max(self.mx, float(f[1]))
+                except (ValueError, IndexError):
+                    continue
+                for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+        if not self.sm:
             return None
-        time.sleep(0.12)
-        self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for l in self.lines:
-            f = [x.strip() for x in l.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx = max(mx, float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
-            return None
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": "nvml, inside the timed regions only" if self.nvml is not None else "nvidia-smi, whole run"}
+
+
+class _NoSampler:
+    def region(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def stop(self):
+        return None
 
 
 def host_threads():
@@ -260,6 +317,19 @@ def _kernel_table(trace, steps):
     tot = sum(v[0] for v in by.values()) or 1.0
     table = {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[2] / steps, "share": v[0] / tot}
              for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])}
+    # the tcgen05 GEMM by role (forward layers / data gradients / weight gradients / the attention backward's batched
+    # products): time and achieved TFLOP/s of each group
+    roles = {}
+    for name, tag, a, b, work in trace:
+        if name in ("fame_gemm_bias_act", "fame_gemm_ex") and tag.startswith("tc"):
+            parts = tag.split(":")
+            role = parts[1] if len(parts) == 3 and parts[1] else "fwd"
+            d = roles.setdefault(role, [0.0, 0.0, 0])
+            d[0] += a.elapsed_time(b); d[1] += work; d[2] += 1
+    if roles:
+        table["gemm_bf16_tcgen05_kernel"]["by_role"] = {
+            r: {"ms_per_step": v[0] / steps, "launches_per_step": v[2] / steps, "tflops": v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0}
+            for r, v in sorted(roles.items(), key=lambda kv: -kv[1][0])}
     return by, table
 
 
@@ -294,7 +364,7 @@ def _max_over_ranks(vals, world, dev):
 
 
 # ====================================================================================================== note encoder
-def bench_note_encoder(args, world, rank, dev, barrier, pk):
+def bench_note_encoder(args, world, rank, dev, barrier, pk, sampler):
     import torch
 
     from fairmultimodal_b200 import modules, ops, synth
@@ -325,21 +395,23 @@ def bench_note_encoder(args, world, rank, dev, barrier, pk):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     l0 = ops.LAUNCHES
-    e0.record()
-    for i in range(args.steps):
-        step_resident(i)
-    e1.record()
-    barrier()
+    with sampler.region():
+        e0.record()
+        for i in range(args.steps):
+            step_resident(i)
+        e1.record()
+        barrier()
     launches = ops.LAUNCHES - l0
     ms = e0.elapsed_time(e1)
     for i in range(2):
         step_e2e(i)
     barrier()
-    e0.record()
-    for i in range(args.steps):
-        step_e2e(i)
-    e1.record()
-    barrier()
+    with sampler.region():
+        e0.record()
+        for i in range(args.steps):
+            step_e2e(i)
+        e1.record()
+        barrier()
     ms_e2e = e0.elapsed_time(e1)
     # third pass, outside both timed regions: CUDA events around every launch (roofline of the dominant kernel)
     tsteps = min(args.steps, 5)
@@ -398,7 +470,7 @@ def _train_batches(B, L, n_batches, rank, dev):
     return host, devb, pw
 
 
-def bench_train(args, world, rank, dev, barrier, pk):
+def bench_train(args, world, rank, dev, barrier, pk, sampler):
     """FAME training step (forward + BCE/LEDDI loss + backward + clip + AdamW), 32 patients per GPU, L = 542."""
     import torch
     import torch.distributed as dist
@@ -425,11 +497,12 @@ def bench_train(args, world, rank, dev, barrier, pk):
             step(i, from_host)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        e0.record()
-        for i in range(args.steps):
-            step(i, from_host)
-        e1.record()
-        barrier()
+        with sampler.region():
+            e0.record()
+            for i in range(args.steps):
+                step(i, from_host)
+            e1.record()
+            barrier()
         res[name] = e0.elapsed_time(e1)
     # trace pass (eager, outside the timed regions): CUDA events around every launch, on the stream it is launched on
     tsteps = 3
@@ -476,7 +549,7 @@ def bench_train(args, world, rank, dev, barrier, pk):
 
 
 # ====================================================================================================== config 3
-def bench_config3(args, world, rank, dev, barrier, pk):
+def bench_config3(args, world, rank, dev, barrier, pk, sampler):
     """BASELINE configs[2]: BEHRT structured encoder + demographics, 1024 patients, forward + backward, one GPU."""
     import torch
 
@@ -500,11 +573,12 @@ def bench_config3(args, world, rank, dev, barrier, pk):
             step(i, from_host)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        e0.record()
-        for i in range(args.steps):
-            step(i, from_host)
-        e1.record()
-        barrier()
+        with sampler.region():
+            e0.record()
+            for i in range(args.steps):
+                step(i, from_host)
+            e1.record()
+            barrier()
         res[name] = e0.elapsed_time(e1)
     l0 = ops.LAUNCHES
     ops.start_trace()
@@ -534,7 +608,7 @@ def bench_config3(args, world, rank, dev, barrier, pk):
 
 
 # ====================================================================================================== config 5
-def bench_config5(args, world, rank, dev, barrier, pk):
+def bench_config5(args, world, rank, dev, barrier, pk, sampler):
     """BASELINE configs[4]: 46 k patients x U{1..16} chunks evaluation sweep over N GPUs."""
     import torch.distributed as dist
 
@@ -547,8 +621,9 @@ def bench_config5(args, world, rank, dev, barrier, pk):
     l0 = ops.LAUNCHES
     for name, resident in (("resident", True), ("e2e", False)):
         barrier()
-        r, ms = sw.run(resident=resident)
-        barrier()
+        with sampler.region():
+            r, ms = sw.run(resident=resident)
+            barrier()
         keys = sorted(ms)
         out[name] = dict(zip(keys, _max_over_ranks([ms[k] for k in keys], world, dev)))
         out["result"] = r
@@ -668,22 +743,20 @@ def run_ours(args):
             parallel.shutdown()
 
     pk = peaks()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler = ClockSampler(local) if rank == 0 else _NoSampler()
     if args.config == 3:
-        line = bench_config3(args, world, rank, dev, barrier, pk)
+        line = bench_config3(args, world, rank, dev, barrier, pk, sampler)
     elif args.config == 5:
-        line = bench_config5(args, world, rank, dev, barrier, pk)
+        line = bench_config5(args, world, rank, dev, barrier, pk, sampler)
     elif args.config == 2:
-        note = bench_note_encoder(args, world, rank, dev, barrier, pk)
+        note = bench_note_encoder(args, world, rank, dev, barrier, pk, sampler)
         line = dict(note, n_gpus=world, higher_is_better=True, vs_baseline=None, data="synthetic")
     else:
-        line = bench_train(args, world, rank, dev, barrier, pk)
+        line = bench_train(args, world, rank, dev, barrier, pk, sampler)
         line.update(n_gpus=world, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic")
         if not args.skip_note_encoder:
-            line["note_encoder"] = bench_note_encoder(args, world, rank, dev, barrier, pk)
-    clocks = sampler.stop() if rank == 0 else None
+            line["note_encoder"] = bench_note_encoder(args, world, rank, dev, barrier, pk, sampler)
+    clocks = sampler.stop()
     if rank == 0:
         line["clocks"] = clocks
         if world == 1 and args.config in (2, 4):

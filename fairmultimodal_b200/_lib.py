@@ -95,6 +95,14 @@ class DemoAddArgs(C.Structure):
     ]
 
 
+class EmbedMeanArgs(C.Structure):
+    _fields_ = [
+        ("cls", C.c_void_p), ("ld_cls", C.c_int64), ("cls_dtype", C.c_int32), ("n_tables", C.c_int32),
+        ("ids", C.c_void_p * 8), ("table", C.c_void_p * 8), ("dtable", C.c_void_p * 8), ("n_rows", C.c_int32 * 8),
+        ("out", C.c_void_p), ("dout", C.c_void_p), ("batch", C.c_int32), ("hidden", C.c_int32),
+    ]
+
+
 class FusionFwdArgs(C.Structure):
     _fields_ = [
         ("emb", C.c_void_p * 3), ("wp_t", C.c_void_p), ("bp", C.c_void_p), ("w_mod", C.c_float * 3),
@@ -205,6 +213,8 @@ OP_TABLE = {
     "fame_lab_embed": LabEmbedArgs,
     "fame_seq_mean": SeqMeanArgs,
     "fame_demo_add": DemoAddArgs,
+    "fame_embed_mean_add": EmbedMeanArgs,
+    "fame_embed_mean_add_bwd": EmbedMeanArgs,
     "fame_fusion_fwd": FusionFwdArgs,
     "fame_loss_stats": LossStatsArgs,
     "fame_loss_fwd_bwd": LossFwdBwdArgs,
@@ -221,6 +231,7 @@ STRUCT_NAMES = {
     "fame_gemm_args": GemmArgs, "fame_layernorm_args": LayerNormArgs, "fame_bert_embed_args": BertEmbedArgs,
     "fame_attn_fwd_args": AttnFwdArgs, "fame_segment_mean_args": SegmentMeanArgs,
     "fame_lab_embed_args": LabEmbedArgs, "fame_seq_mean_args": SeqMeanArgs, "fame_demo_add_args": DemoAddArgs,
+    "fame_embed_mean_args": EmbedMeanArgs,
     "fame_fusion_fwd_args": FusionFwdArgs, "fame_loss_stats_args": LossStatsArgs,
     "fame_loss_fwd_bwd_args": LossFwdBwdArgs, "fame_eval_counts_args": EvalCountsArgs,
     "fame_rank_counts_args": RankCountsArgs, "fame_sigmoid_probs_args": SigmoidProbsArgs,

@@ -10,6 +10,7 @@
 #include "attn_pair_sm100.cuh"
 #include "attn_bwd_sm100.cuh"
 #include "backward.cuh"
+#include "embed_mean.cuh"
 #include "gemm_sm100.cuh"
 #include "heads.cuh"
 #include "metrics.cuh"
@@ -466,6 +467,37 @@ int fame_demo_add(const fame_demo_add_args* a, void*, size_t, fame_stream_t stre
     else FAME_DEMO_ADD(false);
 #undef FAME_DEMO_ADD
     return launch_status();
+}
+
+static int embed_mean_launch(const fame_embed_mean_args* a, bool backward, fame_stream_t stream) {
+    if (a == nullptr) return FAME_ERR_NULLPTR;
+    if (a->n_tables < 1 || a->n_tables > fame::kEmMaxTables || a->batch < 0 || a->hidden <= 0) return FAME_ERR_SHAPE;
+    if (backward ? a->dout == nullptr : (a->cls == nullptr || a->out == nullptr)) return FAME_ERR_NULLPTR;
+    if (!backward && a->cls_dtype != FAME_DT_BF16 && a->cls_dtype != FAME_DT_F32) return FAME_ERR_SHAPE;
+    fame::EmbedMeanParams p = {};
+    for (int k = 0; k < a->n_tables; ++k) {
+        if (a->ids[k] == nullptr || a->n_rows[k] <= 0) return FAME_ERR_NULLPTR;
+        if (backward ? a->dtable[k] == nullptr : a->table[k] == nullptr) return FAME_ERR_NULLPTR;
+        p.ids[k] = reinterpret_cast<const long long*>(a->ids[k]);
+        p.table[k] = a->table[k];
+        p.dtable[k] = a->dtable[k];
+        p.rows[k] = a->n_rows[k];
+    }
+    DeviceInfo* d = nullptr;
+    int rc = device_info(&d);
+    if (rc != FAME_OK) return rc;
+    if (a->batch == 0) return FAME_OK;
+    p.cls = a->cls; p.ld_cls = a->ld_cls; p.cls_f32 = a->cls_dtype == FAME_DT_F32; p.n_tables = a->n_tables;
+    p.out = a->out; p.dout = a->dout; p.hidden = a->hidden;
+    if (backward) fame::embed_mean_add_bwd_kernel<<<a->batch, 128, 0, stream>>>(p);
+    else fame::embed_mean_add_kernel<<<a->batch, 128, 0, stream>>>(p);
+    return launch_status();
+}
+int fame_embed_mean_add(const fame_embed_mean_args* a, void*, size_t, fame_stream_t stream) {
+    return embed_mean_launch(a, false, stream);
+}
+int fame_embed_mean_add_bwd(const fame_embed_mean_args* a, void*, size_t, fame_stream_t stream) {
+    return embed_mean_launch(a, true, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ K7

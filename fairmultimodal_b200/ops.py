@@ -310,6 +310,45 @@ def demo_add(cls, ld_cls, ids, tables):
     return out
 
 
+def embed_mean_add(cls, ld_cls, ids, tables):
+    """out[b] = cls_row[b] + mean over the n = len(tables) <= 8 code tables of table_k[clamp(ids_k[b])] (f32 [B, hidden])."""
+    _cuda(cls, "cls")
+    if cls.dtype not in (torch.bfloat16, torch.float32):
+        raise _lib.FameError("embed_mean_add: cls must be bf16 or f32")
+    n = len(tables)
+    if not 1 <= n <= 8 or len(ids) != n:
+        raise _lib.FameError("embed_mean_add: 1..8 tables with one id vector each")
+    B, hidden = ids[0].numel(), tables[0].shape[1]
+    out = torch.empty((B, hidden), device=cls.device, dtype=torch.float32)
+    a = _lib.EmbedMeanArgs()
+    a.cls, a.ld_cls, a.cls_dtype, a.n_tables = cls.data_ptr(), ld_cls, DT_F32 if cls.dtype == torch.float32 else DT_BF16, n
+    keep = []
+    for k in range(n):
+        i = _cuda(ids[k], "ids", torch.int64).contiguous()
+        t = _cuda(tables[k], "table", torch.float32).contiguous()
+        keep += [i, t]
+        a.ids[k], a.table[k], a.n_rows[k] = i.data_ptr(), t.data_ptr(), t.shape[0]
+    a.out, a.batch, a.hidden = out.data_ptr(), B, hidden
+    _call("fame_embed_mean_add", a, B * hidden * (4.0 + 4.0 * n + 4.0))
+    return out
+
+
+def embed_mean_add_bwd(dout, ids, dtables):
+    """dtable_k[clamp(ids_k[b])] += dout[b] / n into the (zeroed) f32 gradient tables."""
+    n = len(dtables)
+    B, hidden = dout.shape
+    a = _lib.EmbedMeanArgs()
+    a.n_tables = n
+    keep = []
+    for k in range(n):
+        i = _cuda(ids[k], "ids", torch.int64).contiguous()
+        keep.append(i)
+        a.ids[k], a.dtable[k], a.n_rows[k] = i.data_ptr(), _cuda(dtables[k], "dtable", torch.float32).data_ptr(), dtables[k].shape[0]
+    a.dout = _cuda(dout, "dout", torch.float32).contiguous().data_ptr()
+    a.batch, a.hidden = B, hidden
+    _call("fame_embed_mean_add_bwd", a, B * hidden * 4.0 * (1 + 2 * n))
+
+
 def fusion_fwd(emb, packed, w_mod, want_mod_logits=False, want_intermediates=False, w_mod_dev=None):
     """emb = (demo, lab, text) f32 [B,768]; packed = dict of fp32 fusion weights (see modules._pack_fusion).
     Returns dict(logits, sig, [mod_logits], [proj, gated, pre_relu])."""

@@ -517,8 +517,13 @@ def get_state(model) -> FlatTrainState:
 
 
 # ------------------------------------------------------------------------------------------------ demo tower
-def _demo_forward(st, model, ids, age, gender, eth, ins, ds=None, demo_module=None, dpre="behrt_demo."):
-    """BEHRTModel_Demo.forward for training (sequence length 1): returns (demo_emb f32 [B,768], saved)."""
+DEMO_TABLES = ("age", "gender", "ethnicity", "insurance")
+
+
+def _demo_forward(st, model, ids, age, gender, eth, ins, ds=None, demo_module=None, dpre="behrt_demo.", codes=None,
+                  table_names=DEMO_TABLES):
+    """BEHRTModel_Demo.forward for training (sequence length 1): returns (demo_emb f32 [B,768], saved).  codes /
+    table_names: other sets of code tables (ablation 07: seven of them); default = the four of 10_FAME.py."""
     demo_module = model.behrt_demo if demo_module is None else demo_module
     pre = dpre + "bert."
     B, S = ids.shape
@@ -566,10 +571,13 @@ def _demo_forward(st, model, ids, age, gender, eth, ins, ds=None, demo_module=No
                                 want_f32=True, stats=st2)
         s.update(v=v, t1=t1, st1=st1, x1b=x1b, pre=pa_, h=h, t2=t2, st2=st2)
         saved["layers"].append(s)
-    did = [age, gender, eth, ins]
-    tabs = [st.f(f"{dpre}{n}_embedding.weight") for n in ("age", "gender", "ethnicity", "insurance")]
+    did = [age, gender, eth, ins] if codes is None else list(codes)
+    tabs = [st.f(f"{dpre}{n}_embedding.weight") for n in table_names]
     saved["demo_ids"] = [t.to(torch.int64).contiguous() for t in did]
-    return ops.demo_add(x32, H, saved["demo_ids"], tabs), saved
+    saved["table_names"] = tuple(table_names)
+    if len(tabs) == 4:
+        return ops.demo_add(x32, H, saved["demo_ids"], tabs), saved
+    return ops.embed_mean_add(x32, H, saved["demo_ids"], tabs), saved
 
 
 FUSE_BIAS_GRAD = os.environ.get("FAME_FUSE_BIAS_GRAD", "1") != "0"
@@ -656,8 +664,11 @@ def _demo_backward(st, model, saved, ddemo, reducer=None, ds=None, dpre="behrt_d
     ph = ds.p_demo_hidden if ds is not None else 0.0
     pa = ds.p_demo_attn if ds is not None else 0.0
     site = (lambda n, p, g=0: ds.site(n, p, g)) if ds is not None else (lambda n, p, g=0: None)
-    tabs_g = [st.gr(f"{dpre}{n}_embedding.weight") for n in ("age", "gender", "ethnicity", "insurance")]
-    T.demo_add_bwd(ddemo, saved["demo_ids"], tabs_g)
+    tabs_g = [st.gr(f"{dpre}{n}_embedding.weight") for n in saved.get("table_names", DEMO_TABLES)]
+    if len(tabs_g) == 4:
+        T.demo_add_bwd(ddemo, saved["demo_ids"], tabs_g)
+    else:
+        ops.embed_mean_add_bwd(ddemo, saved["demo_ids"], tabs_g)
     dx = ddemo                                                      # f32 [B,768]: gradient of the last hidden state
     cut_layers = demo_bucket_layers(len(saved["layers"]))
     for i in reversed(range(len(saved["layers"]))):

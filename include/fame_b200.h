@@ -273,6 +273,28 @@ typedef struct {
 } fame_demo_add_args;
 int fame_demo_add(const fame_demo_add_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
 
+/* fame_embed_mean_add / fame_embed_mean_add_bwd: the same with n_tables (1..8) code tables -- the structured encoder of
+ * the average-fusion ablation adds the mean of SEVEN clamped embedding rows (age, segment, admission location,
+ * discharge location, gender, ethnicity, insurance) to the CLS state (07_multimodal_average_fusion.py:183-203):
+ *   forward   out[b] = cls[b] + (sum_k table_k[clamp(ids_k[b], 0, n_rows_k - 1)]) / n_tables
+ *   backward  dtable_k[clamp(ids_k[b])] += dout[b] / n_tables   (f32 atomics into caller-zeroed gradient tables)
+ * The forward reads cls / table / out; the backward reads dout / dtable.  Unused slots are ignored. */
+typedef struct {
+    const void* cls;         /* forward: [batch, hidden] bf16 or f32, row stride ld_cls */
+    int64_t ld_cls;
+    int32_t cls_dtype;       /* FAME_DT_BF16 or FAME_DT_F32 */
+    int32_t n_tables;        /* 1..8 */
+    const int64_t* ids[8];   /* [batch] each */
+    const float* table[8];   /* forward: [n_rows[k], hidden] */
+    float* dtable[8];        /* backward: [n_rows[k], hidden] */
+    int32_t n_rows[8];
+    float* out;              /* forward: [batch, hidden] */
+    const float* dout;       /* backward: [batch, hidden] */
+    int32_t batch, hidden;
+} fame_embed_mean_args;
+int fame_embed_mean_add(const fame_embed_mean_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
+int fame_embed_mean_add_bwd(const fame_embed_mean_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K7 fame_fusion_fwd: EDDI-weighted, sigmoid-gated modality fusion and heads (10_FAME.py:276-308), fp32.
  * Weights wp_t / w3_t are the TRANSPOSED projector / fusion_mlp.0 matrices ([in, out]); hidden sizes are the

@@ -52,7 +52,7 @@ def bert_encode(sd, prefix, input_ids, attention_mask, num_layers=12, num_heads=
     H = x.shape[-1]
     D = H // num_heads
     # additive key bias: 0 for attended keys, -inf otherwise (HF:709-713 builds the equivalent sdpa mask)
-    bias = torch.zeros(B, 1, 1, S)
+    bias = torch.zeros(B, 1, 1, S, device=input_ids.device)
     bias = bias.masked_fill(attention_mask[:, None, None, :] == 0, float("-inf"))
     for i in range(num_layers):
         p = f"encoder.layer.{i}."

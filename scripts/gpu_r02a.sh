@@ -4,7 +4,7 @@
 set -u
 TAG=${1:-r02a}
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -60 > gpurun_out/pytest_${TAG}.log; tail -15 gpurun_out/pytest_${TAG}.log
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest_${TAG}.log 2>&1; tail -8 gpurun_out/pytest_${TAG}.log
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; echo "bench exit=$?"
 tail -3 gpurun_out/bench_${TAG}.err
 timeout 600 python bench.py --config 3 --steps 5 --warmup 3 > gpurun_out/bench_c3_${TAG}.json 2> gpurun_out/bench_c3_${TAG}.err; echo "config3 exit=$?"
