@@ -546,14 +546,16 @@ def _demo_forward(st, model, ids, age, gender, eth, ins, ds=None, demo_module=No
     if d_emb is not None:                                   # BertEmbeddings.dropout (HF:111): same mask on both copies
         T.dropout_apply(x32, d_emb)
         T.dropout_apply(xb, d_emb)
-    saved = {"esum": esum, "estats": estats, "layers": [], "ids": ids.to(torch.int64).contiguous().view(-1)}
+    # attention-probability dropout of a length-1 sequence keeps or drops one whole head: one draw per head_dim columns
+    hshift = (H // int(demo_module.bert.config.num_attention_heads)).bit_length() - 1
+    saved = {"esum": esum, "estats": estats, "layers": [], "ids": ids.to(torch.int64).contiguous().view(-1), "hshift": hshift}
     for i in range(int(demo_module.bert.config.num_hidden_layers)):
         p = f"{pre}encoder.layer.{i}."
         s = {"xb": xb}
         # one key per sequence: softmax == 1, so attention-probability dropout (HF:205) keeps or drops a whole head of
         # the value projection: one draw per (patient, head) = per 64 columns
         v = ops.gemm_bias_act(xb, st.w(p + "attention.self.value.weight"), st.f(p + "attention.self.value.bias"),
-                              drop=site(f"demo.{i}.attn", pa, 6))
+                              drop=site(f"demo.{i}.attn", pa, hshift))
         t1 = ops.gemm_bias_act(v, st.w(p + "attention.output.dense.weight"), st.f(p + "attention.output.dense.bias"),
                                residual=x32, out_dtype=torch.float32, drop=site(f"demo.{i}.h1", ph))
         st1 = torch.empty((B, 2), device=dev, dtype=torch.float32)
@@ -705,7 +707,7 @@ def _demo_backward(st, model, saved, ddemo, reducer=None, ds=None, dpre="behrt_d
             _lin_bwd(st, p + "attention.output.dense.weight", p + "attention.output.dense.bias", dt1m, s["v"])
         # s["v"] is the context = head-dropped value projection; its gradient passes the same per-head mask
         dv = T.linear_dgrad(dt1m, st.w(p + "attention.output.dense.weight"),
-                            wT=st.wt(p + "attention.output.dense.weight"), drop=site(f"demo.{i}.attn", pa, 6))
+                            wT=st.wt(p + "attention.output.dense.weight"), drop=site(f"demo.{i}.attn", pa, saved.get("hshift", 6)))
         _lin_bwd(st, p + "attention.self.value.weight", p + "attention.self.value.bias", dv, s["xb"])
         # one key per sequence: softmax == 1, so query / key receive exactly zero gradient (their .grad stays 0 and
         # AdamW still applies weight decay to them, as in the reference)

@@ -504,8 +504,17 @@ def test_train_step_with_dropout():
     assert torch.isfinite(g1).all() and torch.isfinite(loss1).all()
     assert not torch.equal(loss0, loss1)
     assert (loss1[1] - loss0[1]).abs().item() < 0.5                             # BCE of the same order
-    cos = torch.nn.functional.cosine_similarity(g0, g1, dim=0).item()
-    assert cos > 0.3, cos                                                       # same direction on average
+    # same direction ON AVERAGE: a single draw at 16 patients can even point away from the dropout-free gradient (the
+    # LEDDI term changes with the sign of each subgroup's error gap; measured per-draw cosine -0.29 .. 0.62, mean of 24
+    # draws 0.75: scripts/diag_dropout_grad.py), so the mean over 12 step counters is compared
+    acc = g1.clone()
+    for k in range(1, 12):
+        st.step_dev.fill_(k)
+        train.forward_backward(model, batch, pw, 0.8, 0.01, w)
+        acc += st.g
+    st.step_dev.fill_(0)
+    cos = torch.nn.functional.cosine_similarity(g0, acc, dim=0).item()
+    assert cos > 0.5, cos
     st.step_dev += 1
     loss2, _ = train.forward_backward(model, batch, pw, 0.8, 0.01, w)
     assert not torch.equal(loss1, loss2)                                        # new step -> new masks
@@ -584,7 +593,10 @@ def test_full_step_parity_at_bench_shape(B):
     for name, got, ref in (("dlogits", dbg["dlogits"], o["fused_logits"].grad), ("ddemo", dbg["ddemo"], o["demo_embedding"].grad),
                            ("dlab", dbg["dlab"], o["lab_embedding"].grad)):
         got, ref = got.cpu()[same], ref[same]
-        row_err[name] = ((got - ref).abs().amax(dim=1) / ref.abs().amax(dim=1).clamp_min(1e-12)).max().item() if n_same else 0.0
+        # per-patient relative error; the denominator of a patient whose own gradient is tiny (a confident, correct
+        # prediction: sigmoid(z) - y ~ 0) is floored at 10 % of the largest row, else bf16 noise in z reads as percent
+        floor = 0.1 * ref.abs().max().item() if n_same else 1.0
+        row_err[name] = ((got - ref).abs().amax(dim=1) / ref.abs().amax(dim=1).clamp_min(floor)).max().item() if n_same else 0.0
     print(f"[B={B} L={L}] logits rel {rel_logit:.2e} (max abs {dz.max().item():.2e}); |d total| {d_loss:.2e} |d bce| {d_bce:.2e} "
           f"|d leddi| {d_leddi:.2e}; grad-norm rel {norm_rel:.2e}; cosine {cos}; rel err {rel}; "
           f"ReLU-pattern rows {n_same}/{B}; matched-row max rel err {row_err}")
