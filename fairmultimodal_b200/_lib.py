@@ -201,6 +201,7 @@ FLAT_OPS = {
     "fame_wgrad_small": [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "fame_attn_delta": [_P, _P, _I64, _P, _I32, _I32, _I32, _I32],
     "fame_attn_bwd_pds": [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _F, _P],
+    "fame_attn_bwd_fused": [_P, _I64, _P, _I64, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _F, _P],
 }
 
 # name -> args struct for every `int fame_<op>(const args*, void* ws, size_t ws_bytes, stream)` entry point

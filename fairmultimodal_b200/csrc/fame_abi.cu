@@ -9,6 +9,7 @@
 #include "attn_cls.cuh"
 #include "attn_pair_sm100.cuh"
 #include "attn_bwd_sm100.cuh"
+#include "attn_bwd_fused_sm100.cuh"
 #include "backward.cuh"
 #include "embed_mean.cuh"
 #include "gemm_sm100.cuh"
@@ -169,6 +170,36 @@ static int launch_attn_bwd_pds(const CUtensorMap& tq, const CUtensorMap& tdo, co
     fame::attn_bwd_pds_kernel<D, kDrop><<<grid, fame::kAbThreads, fame::AbCfg<D>::kSmemBytes, stream>>>(tq, tdo, p, (int)items,
                                                                                                 qtiles);
     return launch_status();
+}
+
+template <int D, bool kKV, bool kDrop>
+static int launch_attn_bwd_fused(const CUtensorMap& tq128, const CUtensorMap& td128, const CUtensorMap& tq64,
+                                 const CUtensorMap& td64, const fame::AfParams& p, int sm_count, fame_stream_t stream) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(fame::attn_bwd_fused_kernel<D, kKV, kDrop>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, fame::AfCfg<D>::kSmemBytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+        attr_set[dev] = true;
+    }
+    const int rtiles = (p.seq + 127) / 128;
+    const long long items = (long long)p.batch * p.heads * rtiles;
+    if (items > 0x7fffffffll) return FAME_ERR_SHAPE;
+    const int sms = persistent_sms(sm_count);
+    const int grid = items < sms ? (int)items : sms;
+    fame::attn_bwd_fused_kernel<D, kKV, kDrop><<<grid, fame::kAfThreads, fame::AfCfg<D>::kSmemBytes, stream>>>(
+        tq128, td128, tq64, td64, p, (int)items, rtiles);
+    return launch_status();
+}
+
+template <int D, bool kDrop>
+static int launch_attn_bwd_fused_both(const CUtensorMap& tq128, const CUtensorMap& td128, const CUtensorMap& tq64,
+                                      const CUtensorMap& td64, const fame::AfParams& p, int sm_count, fame_stream_t stream) {
+    int rc = launch_attn_bwd_fused<D, true, kDrop>(tq128, td128, tq64, td64, p, sm_count, stream);     // dK, dV
+    if (rc != FAME_OK) return rc;
+    return launch_attn_bwd_fused<D, false, kDrop>(tq128, td128, tq64, td64, p, sm_count, stream);      // dQ
 }
 
 

@@ -171,6 +171,16 @@ def attn_bwd_pds(qkv, dctx, lse, delta, batch, seq, heads, head_dim, ldp, scale,
     return p, ds
 
 
+def attn_bwd_fused(qkv, dctx, lse, delta, batch, seq, heads, head_dim, scale, drop=None):
+    """dqkv (bf16 [batch*seq, 3*heads*head_dim]: dQ | dK | dV) from the packed qkv, dO, the forward's lse and delta; the
+    probabilities and score gradients stay in TMEM (two launches: dK/dV pass, dQ pass)."""
+    dqkv = torch.empty((batch * seq, 3 * heads * head_dim), device=qkv.device, dtype=torch.bfloat16)
+    _flat("fame_attn_bwd_fused", qkv.data_ptr(), qkv.stride(0), dctx.data_ptr(), dctx.stride(0), lse.data_ptr(),
+          delta.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), batch, seq, heads, head_dim, float(scale),
+          ctypes.addressof(drop) if drop is not None and drop.thresh16 > 0 else None)
+    return dqkv
+
+
 def bert_embed_bwd(d_sum, ids, dword, dpos, dtype0, seq, pad_idx=0):
     tokens, hidden = d_sum.shape
     _flat("fame_bert_embed_bwd", d_sum.data_ptr(), ids.data_ptr(), dword.data_ptr(), dpos.data_ptr(), dtype0.data_ptr(),

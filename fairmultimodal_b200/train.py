@@ -757,19 +757,25 @@ def _lab_forward(st, model, lab, ds=None, lab_module=None, pre="behrt_lab."):
     return ops.seq_mean(x, B, L), saved
 
 
-def _attn_backward(qkv, dctx, ctx, lse, B, L, nh, D, drop=None):
-    """dqkv [T, 3*nh*D] bf16 from dctx [T, nh*D]: P and dS come out of one kernel that keeps both score products
-    (Q K^T and dO V^T) in TMEM and recomputes the softmax from the forward's row log-sum-exp (and, in training with
-    attention dropout, the forward's mask from its seed); three batched tensor-core products turn them into dV, dK,
-    dQ."""
+FUSED_ATTN_BWD = os.environ.get("FAME_FUSED_ATTN_BWD", "1") != "0"   # 0: materialise P / dS + three batched GEMMs
+
+
+def _attn_backward(qkv, dctx, ctx, lse, B, L, nh, D, drop=None, fused=None):
+    """dqkv [T, 3*nh*D] bf16 from dctx [T, nh*D].  Fused (default): fame_attn_bwd_fused -- both score products
+    (Q K^T and dO V^T), the softmax recomputed from the forward's row log-sum-exp (and, in training with attention
+    dropout, the forward's mask from its seed) and the products that consume P / dS run in one kernel per pass (dK/dV
+    pass, dQ pass); P and dS stay in TMEM.  Unfused (FAME_FUSED_ATTN_BWD=0): P and dS are written once in bf16 and three
+    batched tensor-core products turn them into dV, dK, dQ."""
     dev = qkv.device
+    delta = T.attn_delta(dctx, ctx, B, L, nh, D)
+    if FUSED_ATTN_BWD if fused is None else fused:
+        return T.attn_bwd_fused(qkv, dctx, lse, delta, B, L, nh, D, D ** -0.5, drop=drop)
     W = 3 * nh * D
     HD = nh * D
     ldp = (L + 7) // 8 * 8
     sq = (L * W, D)                 # (b0 = sequence, b1 = head) strides inside the packed qkv tensor
     sc = (L * HD, D)                # same inside ctx / dctx
     ss = (nh * L * ldp, L * ldp)    # inside the [B, nh, L, ldp] probability / score-gradient tensors
-    delta = T.attn_delta(dctx, ctx, B, L, nh, D)
     p, ds = T.attn_bwd_pds(qkv, dctx, lse, delta, B, L, nh, D, ldp, D ** -0.5, drop=drop)
     dqkv = torch.empty((B * L, W), device=dev, dtype=torch.bfloat16)
     # dV = P^T dO, dK = dS^T Q  (A MN-major: stored [query rows, key cols]; B MN-major: stored [query rows, d cols])

@@ -492,6 +492,16 @@ int fame_attn_bwd_pds(const void* qkv, int64_t ld_qkv, const void* dctx, int64_t
                       const float* delta, void* p, void* ds, int64_t ldp, int32_t batch, int32_t seq, int32_t heads,
                       int32_t head_dim, float scale, const fame_dropout_cfg* drop /* the forward's, or NULL */,
                       fame_stream_t stream);
+/* fame_attn_bwd_fused: the whole attention backward of one layer in two launches, P and dS never written to memory
+ * (10_FAME.py:212-215 under total_loss.backward(), 10_FAME.py:445): dqkv [batch * seq, ld_dqkv] bf16 receives dQ | dK | dV in
+ * the layout of the packed qkv tensor.  Pass 1 (key tiles stationary) recomputes S^T = K Q^T and dP^T = V dO^T per 64-query
+ * half block, turns them into bf16 P^T / dS^T inside TMEM and accumulates dV += P^T dO, dK += dS^T Q; pass 2 (query tiles
+ * stationary) does the same for dQ += dS K.  lse from fame_attn_fwd, delta from fame_attn_delta; drop = the forward's
+ * dropout configuration or NULL.  head_dim 64 or 96. */
+int fame_attn_bwd_fused(const void* qkv, int64_t ld_qkv, const void* dctx, int64_t ld_dctx, const float* lse,
+                        const float* delta, void* dqkv, int64_t ld_dqkv, int32_t batch, int32_t seq, int32_t heads,
+                        int32_t head_dim, float scale, const fame_dropout_cfg* drop /* the forward's, or NULL */,
+                        fame_stream_t stream);
 /* Text-only baseline (02_BioClinicalBERT.py): FocalLoss(gamma, alpha, pos_weight_i) summed over the three
  * outcomes, each a batch mean (18-38, 143-147): *loss_out += loss (float64, caller zeroes it); dlogits [batch, 3] =
  * d loss / d logits (may be NULL).  fame_relu_fwd / fame_relu_bwd: ReLU of the classifier's 256-wide hidden layer, in
