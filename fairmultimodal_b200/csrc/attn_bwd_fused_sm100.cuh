@@ -167,8 +167,14 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
             }
         }
     } else if (warp == 9) {
-        if (lane == 0 && blockIdx.x < num_items) {
+        if (blockIdx.x < num_items) {
             // ------------------------------------------------------------------------------------ MMA issuer
+            // The whole warp runs the loop (warp-uniform control flow and operands: descriptors and TMEM addresses live
+            // in uniform registers and every tcgen05.mma is ONE instruction); only the elected lane issues.  With the
+            // loop inside `if (lane == 0)` each MMA cost ~13 instructions (R2UR + an ELECT / BRA.U.ANY loop per operand
+            // set), and the single issuing thread, not the tensor pipe, paced the kernel (ncu r02: 3 300 clk per half
+            // block, tensor pipe 24 % active).
+            const bool leader = elect_one();
             constexpr uint32_t idesc_sc = make_idesc_bf16(128, 64, 0, 0);     // scores: [128 stationary rows] x [64 streamed rows]
             constexpr uint32_t idesc_ac = make_idesc_bf16(128, D, 0, 1);      // accumulators: A from TMEM, B MN-major
             const uint32_t a1_addr = smem_u32(smem_a1), a2_addr = smem_u32(smem_a2);
@@ -185,25 +191,28 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                 const uint32_t b1_addr = smem_u32(smem_b + n_st * Cfg::kStageBytes);
                 const uint32_t b2_addr = b1_addr + Cfg::kStreamBytes;
                 const uint32_t col = tmem_base + (n_g & 1) * 128;
+                const bool last = n_hb == nhb - 1;
+                if (leader) {
 #pragma unroll
-                for (int tt = 0; tt < D / 16; ++tt) {
-                    const uint32_t aoff = (tt >> 2) * kFaBoxBytes + (tt & 3) * 32;
-                    const uint32_t boff = (tt >> 2) * Cfg::kHalfBoxBytes + (tt & 3) * 32;
-                    umma_bf16_ss(col, make_smem_desc_sw128(a1_addr + aoff, 16, 1024),
-                                 make_smem_desc_sw128(b1_addr + boff, 16, 1024), idesc_sc, tt != 0);
-                }
+                    for (int tt = 0; tt < D / 16; ++tt) {
+                        const uint32_t aoff = (tt >> 2) * kFaBoxBytes + (tt & 3) * 32;
+                        const uint32_t boff = (tt >> 2) * Cfg::kHalfBoxBytes + (tt & 3) * 32;
+                        umma_bf16_ss(col, make_smem_desc_sw128(a1_addr + aoff, 16, 1024),
+                                     make_smem_desc_sw128(b1_addr + boff, 16, 1024), idesc_sc, tt != 0);
+                    }
 #pragma unroll
-                for (int tt = 0; tt < D / 16; ++tt) {
-                    const uint32_t aoff = (tt >> 2) * kFaBoxBytes + (tt & 3) * 32;
-                    const uint32_t boff = (tt >> 2) * Cfg::kHalfBoxBytes + (tt & 3) * 32;
-                    umma_bf16_ss(col + 64, make_smem_desc_sw128(a2_addr + aoff, 16, 1024),
-                                 make_smem_desc_sw128(b2_addr + boff, 16, 1024), idesc_sc, tt != 0);
+                    for (int tt = 0; tt < D / 16; ++tt) {
+                        const uint32_t aoff = (tt >> 2) * kFaBoxBytes + (tt & 3) * 32;
+                        const uint32_t boff = (tt >> 2) * Cfg::kHalfBoxBytes + (tt & 3) * 32;
+                        umma_bf16_ss(col + 64, make_smem_desc_sw128(a2_addr + aoff, 16, 1024),
+                                     make_smem_desc_sw128(b2_addr + boff, 16, 1024), idesc_sc, tt != 0);
+                    }
+                    umma_commit(&sd_full[n_g & 1]);
+                    if (last) umma_commit(a_empty);   // the accumulating products read TMEM and the streamed tiles only
                 }
-                umma_commit(&sd_full[n_g & 1]);
                 ++n_g;
                 if (++n_st == ST) { n_st = 0; n_bph ^= 1; }
                 if (++n_hb == nhb) {
-                    umma_commit(a_empty);      // the accumulating products read TMEM and the streamed tiles only
                     n_hb = 0;
                     n_item += gridDim.x;
                 }
@@ -225,31 +234,38 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                     const uint32_t b1_addr = smem_u32(smem_b + c_st * Cfg::kStageBytes);
                     const uint32_t b2_addr = b1_addr + Cfg::kStreamBytes;
                     const uint32_t col = tmem_base + s * 128;
-                    if (kKV) {
-                        // dV_j += P^T (cols [0, 32) of the stage) . dO_ih ;  dK_j += dS^T (cols [64, 96)) . Q_ih
+                    if (leader) {
+                        if (kKV) {
+                            // dV_j += P^T (cols [0, 32) of the stage) . dO_ih ;  dK_j += dS^T (cols [64, 96)) . Q_ih
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            umma_bf16_ts(tmem_base + kColAcc0, col + kk * 8,
-                                         make_smem_desc_sw128(b2_addr + kk * 2048, Cfg::kHalfBoxBytes, 1024), idesc_ac,
-                                         (hb | kk) != 0);
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_bf16_ts(tmem_base + kColAcc0, col + kk * 8,
+                                             make_smem_desc_sw128(b2_addr + kk * 2048, Cfg::kHalfBoxBytes, 1024), idesc_ac,
+                                             (hb | kk) != 0);
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            umma_bf16_ts(tmem_base + kColAcc1, col + 64 + kk * 8,
-                                         make_smem_desc_sw128(b1_addr + kk * 2048, Cfg::kHalfBoxBytes, 1024), idesc_ac,
-                                         (hb | kk) != 0);
-                    } else {
-                        // dQ_i += dS (cols [64, 96) of the stage) . K_jh
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_bf16_ts(tmem_base + kColAcc1, col + 64 + kk * 8,
+                                             make_smem_desc_sw128(b1_addr + kk * 2048, Cfg::kHalfBoxBytes, 1024), idesc_ac,
+                                             (hb | kk) != 0);
+                        } else {
+                            // dQ_i += dS (cols [64, 96) of the stage) . K_jh
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            umma_bf16_ts(tmem_base + kColAcc0, col + 64 + kk * 8,
-                                         make_smem_desc_sw128(b1_addr + kk * 2048, Cfg::kHalfBoxBytes, 1024), idesc_ac,
-                                         (hb | kk) != 0);
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_bf16_ts(tmem_base + kColAcc0, col + 64 + kk * 8,
+                                             make_smem_desc_sw128(b1_addr + kk * 2048, Cfg::kHalfBoxBytes, 1024), idesc_ac,
+                                             (hb | kk) != 0);
+                        }
+                        umma_commit(&b_empty[c_st]);
+                        if (hb == nhb - 1) umma_commit(acc_full);
                     }
-                    umma_commit(&b_empty[c_st]);
-                    if (hb == nhb - 1) umma_commit(acc_full);
                     if (++c_st == ST) c_st = 0;
-                    if (n_item < num_items) issue_scores();
+                    // next score pair: at once while it belongs to THIS item; the first two of the next item wait for
+                    // that item's stationary tiles (a TMA round trip after this item's last score product) -- issuing
+                    // them here would hold back this item's remaining accumulating products behind that wait (ncu r02:
+                    // 13-15 % of all samples in the acc_full wait), so they are issued after the item's last product
+                    if (n_item == item) issue_scores();
                 }
+                while (n_item < num_items && n_g < g + 2) issue_scores();   // pair n needs acc(n - 2) issued: 2 stages
             }
         }
     } else {
@@ -282,21 +298,35 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                 }
                 if (kDrop) rs_r = drop_row_seed(drop_site, (uint32_t)(stat0 + srow));
             }
-            for (int hb = 0; hb < nhb; ++hb) {
-                if (((g0 + hb) & 1) != w) continue;
+            // dK/dV pass: per-COLUMN statistics (lse, delta * scale of the 64 queries of a half block), loaded by threads
+            // 0..63 of the warpgroup one half block AHEAD (the global-load latency sits off the S -> dS chain) and staged
+            // through shared memory
+            const int hb_first = ((g0 & 1) == w) ? 0 : 1;
+            float pf_lse = INFINITY, pf_dls = 0.f;
+            auto prefetch_cols = [&](int hb) {
+                pf_lse = INFINITY;
+                pf_dls = 0.f;
+                if (kKV && tw < 64 && hb < nhb) {
+                    const int qi = hb * 64 + tw;
+                    if (qi < S) {                          // +inf -> P = 0 outside the sequence
+                        pf_lse = __ldg(p.lse + stat0 + qi);
+                        pf_dls = __ldg(p.delta + stat0 + qi);
+                    }
+                }
+            };
+            prefetch_cols(hb_first);
+            for (int hb = hb_first; hb < nhb; hb += 2) {
                 const int c0 = hb * 64;                    // first streamed row (key | query) of the half block
                 float* sbuf = stats + (nproc & 1) * (3 * 64);
                 if (kKV) {
-                    // per-COLUMN statistics of the 64 queries of this half block, staged once per warpgroup
                     if (tw < 64) {
-                        const int qi = c0 + tw;
-                        const bool ok = qi < S;
-                        sbuf[tw] = ok ? __ldg(p.lse + stat0 + qi) : INFINITY;      // +inf -> P = 0 outside the sequence
-                        sbuf[64 + tw] = ok ? __ldg(p.delta + stat0 + qi) * p.scale : 0.f;
+                        sbuf[tw] = pf_lse;
+                        sbuf[64 + tw] = pf_dls * p.scale;
                     } else if (kDrop) {
                         reinterpret_cast<uint32_t*>(sbuf)[128 + tw - 64] = drop_row_seed(drop_site, (uint32_t)(stat0 + c0 + tw - 64));
                     }
                     named_bar_sync(1 + w, 128);
+                    prefetch_cols(hb + 2);
                 }
                 ++nproc;
                 mbar_wait(&sd_full[w], fph);

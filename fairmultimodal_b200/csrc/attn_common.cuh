@@ -20,7 +20,13 @@ struct FaParams {
     float* lse;               // optional [batch, heads, seq]: row log-sum-exp in log2 units of the scaled scores
     const int* kv_len;        // optional [batch]: 1 + last attended key (fully masked key blocks are skipped)
     DropCfg drop;             // dropout of the attention probabilities (kDrop instantiation only)
+    int pingpong;             // 1: the two softmax warpgroups take turns on the exponential phase (see attn_pair_sm100.cuh)
 };
+
+// named-barrier halves of a turn hand-over between two 128-thread warpgroups (256 = waiting + signalling threads)
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;

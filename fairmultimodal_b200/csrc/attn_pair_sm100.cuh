@@ -20,6 +20,11 @@
 //                                   O_t (+)= P_t . V_j (TS) -> TMEM cols [256 + t*128, .. + D)
 //   warps 0-3     : softmax warpgroup of tile 0 (thread = one query row, all 128 keys of the block)
 //   warps 4-7     : softmax warpgroup of tile 1
+// Ping-pong (p.pingpong): left alone, both warpgroups run their exponential phases at the SAME time (their score tiles
+// are issued back to back), share the MUFU pipe, finish together and then both wait while the single MMA thread issues
+// P.V and the next scores of both tiles: measured 2 475 clk per 128 x 128 tile at head_dim 64 against a MUFU floor of
+// 1 024 (ncu r01c: XU 41 % active, a quarter of all samples in the s_full wait).  Two named barriers make the
+// warpgroups take turns on the exponential loop, so that tile 1's exponentials run under tile 0's MMAs and vice versa.
 // P_t (bf16) overwrites the first 64 columns of S_t; the in-order MMA pipe guarantees S_t(j+1) is written only after
 // P_t(j) was consumed.  A commit on s_full[t] for block j also covers P.V of block j-1 (same issuing thread), so the
 // softmax warps may rescale O_t right after that wait.
@@ -37,13 +42,24 @@ namespace fame {
 constexpr int kApThreads = 320;
 constexpr float kApLazyLog2 = 8.0f;     // rescale the accumulator only when a row max grows by more than 2^8
 
-template <int D>
+// KB = keys per block.  128: one CTA per SM (512 TMEM columns).  64 (head_dim 64 only): a CTA needs 2 x 64 score + 2 x 64
+// output columns = 256 and ~100 registers per thread, so TWO CTAs share an SM -- four query tiles and sixteen softmax
+// warps in flight instead of two and eight.  With eight warps (two per scheduler) the S -> softmax -> P.V -> next S chain
+// of a tile (~2 500 clk per key block against 1 024 clk of MUFU work) is not hidden; the second CTA fills the gaps.
+template <int D, int KB = 128>
 struct ApCfg {
     static constexpr int kBoxes = (D + 63) / 64;
-    static constexpr int kTileBytes = kBoxes * kFaBoxBytes;       // 128 rows x (64 | 128) bf16 columns
-    static constexpr int kQBufs = (D <= 64) ? 2 : 1;              // Q pairs in flight
+    static constexpr int kTileBytes = kBoxes * kFaBoxBytes;       // Q tile: 128 rows x (64 | 128) bf16 columns
+    static constexpr int kKvBoxBytes = KB * 64 * 2;               // one K / V box: KB rows x 64 bf16 columns
+    static constexpr int kKvBytes = kBoxes * kKvBoxBytes;
+    static constexpr int kQBufs = (D <= 64 && KB == 128) ? 2 : 1; // Q pairs in flight
     static constexpr int kStages = (D <= 64) ? 3 : 2;             // K/V ring depth
-    static constexpr int kSmemBytes = kTileBytes * (2 * kQBufs + 2 * kStages) + 1024 /*barriers*/ + 1024 /*align*/;
+    static constexpr int kCtasPerSm = KB == 64 ? 2 : 1;
+    static constexpr int kTmemCols = KB == 64 ? 256 : 512;
+    static constexpr int kColO = 2 * KB;                          // O_t at kColO + t * kOStride
+    static constexpr int kOStride = KB == 64 ? 64 : 128;
+    static constexpr int kSmemBytes = kTileBytes * 2 * kQBufs + kKvBytes * 2 * kStages + 1024 /*barriers*/ + 1024 /*align*/;
+    static_assert(KB == 128 || (KB == 64 && D == 64), "64-key blocks are built for head_dim 64");
 };
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -56,11 +72,14 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // The row sum l (softmax denominator) and the saved log-sum-exp use the UNDROPPED exponentials; dropped entries of P
 // are zeroed before P.V and the 1 / (1 - p) scale is folded into the final 1 / l.  Mask row = (sequence, head, query),
 // mask column = key (dropout.cuh); attn_bwd_pds_kernel<D, true> regenerates the same bits.
-template <int D, bool kDrop = false>
-__global__ void __launch_bounds__(kApThreads, 1)
-attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParams p, const int num_items,
-                     const int qpairs) {
-    using Cfg = ApCfg<D>;
+template <int D, bool kDrop = false, int KB = 128>
+__global__ void __launch_bounds__(kApThreads, (KB == 64 ? 2 : 1))
+attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_kv,
+                     const FaParams p, const int num_items, const int qpairs) {
+    using Cfg = ApCfg<D, KB>;
+    constexpr int KVT = Cfg::kKvBytes;          // one K or V stage
+    constexpr int KVBOX = Cfg::kKvBoxBytes;
+    constexpr int NC = KB / 32;                 // 32-column chunks of a score block
     constexpr int NB = Cfg::kBoxes;
     constexpr int ST = Cfg::kStages;
     constexpr int QB = Cfg::kQBufs;
@@ -68,9 +87,9 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_q = smem;                          // [QB][2][TILE]
-    uint8_t* smem_k = smem_q + QB * 2 * TILE;        // [ST][TILE]
-    uint8_t* smem_v = smem_k + ST * TILE;            // [ST][TILE]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + ST * TILE);
+    uint8_t* smem_k = smem_q + QB * 2 * TILE;        // [ST][KVT]
+    uint8_t* smem_v = smem_k + ST * KVT;             // [ST][KVT]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + ST * KVT);
     uint64_t* q_full = bars;                 // [QB]
     uint64_t* q_empty = q_full + QB;         // [QB]
     uint64_t* k_full = q_empty + QB;         // [ST]
@@ -83,10 +102,11 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.seq;
-    const int nblk = (S + 127) >> 7;
+    const int nblk = (S + KB - 1) / KB;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_qkv);
+        tma_prefetch_desc(&tmap_kv);
         for (int i = 0; i < QB; ++i) {
             mbar_init(&q_full[i], 1);
             mbar_init(&q_empty[i], 1);
@@ -104,14 +124,15 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
         fence_barrier_init();
     }
     if (warp == 8) {
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, Cfg::kTmemCols);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t kColO = 256;
+    constexpr uint32_t kColO = Cfg::kColO;
+    constexpr uint32_t OST = Cfg::kOStride;
 
     // item -> (sequence b, head h, query pair qp); consecutive items share K/V of one (b, h) through L2
     auto t1_active = [&](int item) { return (item % qpairs) * 256 + 128 < S; };
@@ -119,8 +140,8 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
     // least one, so that an all-masked sequence still produces its zero rows
     auto nblk_of = [&](int item) {
         if (p.kv_len == nullptr) return nblk;
-        const int len = __ldg(p.kv_len + (item / qpairs) / p.heads);
-        return max(1, min(nblk, (len + 127) >> 7));
+        const int len = abs(__ldg(p.kv_len + (item / qpairs) / p.heads));   // sign: prefix mask or not (mask_kv_len_kernel)
+        return max(1, min(nblk, (len + KB - 1) / KB));
     };
 
     if (warp == 8) {
@@ -144,24 +165,29 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
                 const int nb_item = nblk_of(item);
                 for (int j = 0; j < nb_item; ++j) {
                     mbar_wait(&kv_empty[st], kph ^ 1);
-                    mbar_arrive_expect_tx(&k_full[st], TILE);
+                    mbar_arrive_expect_tx(&k_full[st], KVT);
 #pragma unroll
                     for (int x = 0; x < NB; ++x)
-                        tma_load_2d(smem_k + st * TILE + x * kFaBoxBytes, &tmap_qkv, &k_full[st],
-                                    p.k_col0 + h * D + x * 64, row0 + j * 128, kEvictLast);
-                    mbar_arrive_expect_tx(&v_full[st], TILE);
+                        tma_load_2d(smem_k + st * KVT + x * KVBOX, &tmap_kv, &k_full[st],
+                                    p.k_col0 + h * D + x * 64, row0 + j * KB, kEvictLast);
+                    mbar_arrive_expect_tx(&v_full[st], KVT);
 #pragma unroll
                     for (int x = 0; x < NB; ++x)
-                        tma_load_2d(smem_v + st * TILE + x * kFaBoxBytes, &tmap_qkv, &v_full[st],
-                                    p.v_col0 + h * D + x * 64, row0 + j * 128, kEvictLast);
+                        tma_load_2d(smem_v + st * KVT + x * KVBOX, &tmap_kv, &v_full[st],
+                                    p.v_col0 + h * D + x * 64, row0 + j * KB, kEvictLast);
                     if (++st == ST) { st = 0; kph ^= 1; }
                 }
             }
         }
     } else if (warp == 9) {
-        if (lane == 0 && blockIdx.x < num_items) {
+        if (blockIdx.x < num_items) {
             // ------------------------------------------------------------------------------------ MMA issuer
-            constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+            // The whole warp runs the loop (warp-uniform control flow: descriptors and TMEM addresses stay in uniform
+            // registers, every tcgen05.mma is one instruction); only the elected lane issues.  Inside `if (lane == 0)`
+            // each MMA cost ~13 instructions (R2UR + an ELECT / BRA.U.ANY loop), which put ~900 clk of issue time per
+            // tile and key block on the softmax -> MMA -> softmax chain.
+            const bool leader = elect_one();
+            constexpr uint32_t idesc_qk = make_idesc_bf16(128, KB, 0, 0);
             constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);
             // cursor over the NEXT score block to issue (runs one block ahead of the P.V products, across items)
             int n_item = blockIdx.x, n_j = 0, n_qb = 0, ks = 0;
@@ -175,16 +201,19 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
                 }
                 tc_fence_after();
                 const uint32_t q_addr = smem_u32(smem_q + (n_qb * 2 + t) * TILE);
-                const uint32_t k_addr = smem_u32(smem_k + ks * TILE);
+                const uint32_t k_addr = smem_u32(smem_k + ks * KVT);
+                if (leader) {
 #pragma unroll
-                for (int tt = 0; tt < D / 16; ++tt) {
-                    const uint32_t off = (tt >> 2) * kFaBoxBytes + (tt & 3) * 32;
-                    umma_bf16_ss(tmem_base + t * 128, make_smem_desc_sw128(q_addr + off, 16, 1024),
-                                 make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_qk, tt != 0);
+                    for (int tt = 0; tt < D / 16; ++tt) {
+                        const uint32_t off = (tt >> 2) * kFaBoxBytes + (tt & 3) * 32;
+                        const uint32_t koff = (tt >> 2) * KVBOX + (tt & 3) * 32;
+                        umma_bf16_ss(tmem_base + t * KB, make_smem_desc_sw128(q_addr + off, 16, 1024),
+                                     make_smem_desc_sw128(k_addr + koff, 16, 1024), idesc_qk, tt != 0);
+                    }
+                    umma_commit(&s_full[t]);
+                    if ((t == 1 || !n_t1) && n_j == n_nblk - 1) umma_commit(&q_empty[n_qb]);
                 }
-                umma_commit(&s_full[t]);
                 if (t == 1 || !n_t1) {          // last tile of this block: advance the cursor
-                    if (n_j == n_nblk - 1) umma_commit(&q_empty[n_qb]);
                     if (++ks == ST) { ks = 0; kph ^= 1; }
                     if (++n_j == n_nblk) {
                         n_j = 0;
@@ -207,20 +236,22 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
                 const int nb_item = nblk_of(item);
                 for (int j = 0; j < nb_item; ++j) {
                     mbar_wait(&v_full[vs], vph);
-                    const uint32_t v_addr = smem_u32(smem_v + vs * TILE);
-                    auto issue_pv = [&](int t) {
+                    const uint32_t v_addr = smem_u32(smem_v + vs * KVT);
+                    auto issue_pv = [&](int t, bool free_kv) {
+                        if (leader) {
 #pragma unroll
-                        for (int kk = 0; kk < 8; ++kk)
-                            umma_bf16_ts(tmem_base + kColO + t * 128, tmem_base + t * 128 + kk * 8,
-                                         make_smem_desc_sw128(v_addr + kk * 2048, kFaBoxBytes, 1024), idesc_pv,
-                                         (j | kk) != 0);
-                        if (j == nb_item - 1) umma_commit(&o_full[t]);
+                            for (int kk = 0; kk < KB / 16; ++kk)
+                                umma_bf16_ts(tmem_base + kColO + t * OST, tmem_base + t * KB + kk * 8,
+                                             make_smem_desc_sw128(v_addr + kk * 2048, KVBOX, 1024), idesc_pv,
+                                             (j | kk) != 0);
+                            if (j == nb_item - 1) umma_commit(&o_full[t]);
+                            if (free_kv) umma_commit(&kv_empty[vs]);
+                        }
                     };
                     mbar_wait(&p_full[0], pph0);
                     pph0 ^= 1;
                     tc_fence_after();
-                    issue_pv(0);
-                    if (!t1) umma_commit(&kv_empty[vs]);
+                    issue_pv(0, !t1);
                     const bool nx = n_item < num_items;
                     const bool c_t1 = n_t1;
                     if (nx) issue_s(0);
@@ -228,8 +259,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
                         mbar_wait(&p_full[1], pph1);
                         pph1 ^= 1;
                         tc_fence_after();
-                        issue_pv(1);
-                        umma_commit(&kv_empty[vs]);
+                        issue_pv(1, true);
                     }
                     if (nx && c_t1) issue_s(1);
                     if (++vs == ST) { vs = 0; vph ^= 1; }
@@ -242,49 +272,72 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
         const int t = warp >> 2;      // query tile (= warpgroup)
         const int r = q * 32 + lane;  // row inside the tile
         const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
-        const uint32_t s_addr = lane_base + t * 128;
-        const uint32_t o_addr = lane_base + kColO + t * 128;
+        const uint32_t s_addr = lane_base + t * KB;
+        const uint32_t o_addr = lane_base + kColO + t * OST;
         const float sc = p.scale_log2e;
         uint32_t sph = 0, oph = 0;
         const uint32_t drop_site = kDrop ? drop_site_seed(p.drop) : 0u;
+        const bool pp = p.pingpong != 0;
+        if (pp && t == 1) named_bar_arrive(1, 256);          // warpgroup 0 owns the first turn
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-            if (t == 1 && !t1_active(item)) continue;
+            if (t == 1 && !t1_active(item)) {
+                if (pp)                                      // keep the turn counts of the two warpgroups equal
+                    for (int j = nblk_of(item); j > 0; --j) {
+                        named_bar_sync(2, 256);
+                        named_bar_arrive(1, 256);
+                    }
+                continue;
+            }
             const int qp = item % qpairs, bh = item / qpairs;
             const int h = bh % p.heads, b = bh / p.heads;
             const uint32_t drop_rs = kDrop ? drop_row_seed(drop_site, (uint32_t)(bh * S + qp * 256 + t * 128 + r)) : 0u;
             float m = -INFINITY, l = 0.f;   // running reference max (log2 units, scaled) and row sum
             const int nb_item = nblk_of(item);
+            // keys [0, valid_to) are attended when the mask is absent or a prefix mask (kv_len >= 0): validity then needs
+            // no memory access on the S -> softmax -> P chain; a mask with holes (kv_len < 0, or no kv_len) is read
+            int valid_to = S;
+            bool by_len = p.key_mask == nullptr;
+            if (p.key_mask != nullptr && p.kv_len != nullptr) {
+                const int len = __ldg(p.kv_len + b);
+                if (len >= 0) {
+                    by_len = true;
+                    valid_to = min(S, len);
+                }
+            }
             for (int j = 0; j < nb_item; ++j) {
                 // validity of the 128 keys of this block: inside the sequence and not masked by the caller
-                const int key0 = j * 128;
-                uint32_t vm[4];
-                bool all_valid = (key0 + 128 <= S) && p.key_mask == nullptr;
+                const int key0 = j * KB;
+                uint32_t vm[NC];
+                bool all_valid = by_len && key0 + KB <= valid_to;
                 if (!all_valid) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < NC; ++c) {
                         const int k = key0 + c * 32 + lane;
-                        const bool ok = k < S && (p.key_mask == nullptr || p.key_mask[(long long)b * S + k] != 0);
+                        const bool ok = by_len ? k < valid_to : (k < S && p.key_mask[(long long)b * S + k] != 0);
                         vm[c] = __ballot_sync(0xffffffffu, ok);
                     }
-                    all_valid = (vm[0] & vm[1] & vm[2] & vm[3]) == 0xffffffffu;
+                    uint32_t va = vm[0];
+#pragma unroll
+                    for (int c = 1; c < NC; ++c) va &= vm[c];
+                    all_valid = va == 0xffffffffu;
                 }
                 mbar_wait(&s_full[t], sph);
                 sph ^= 1;
                 tc_fence_after();
-                uint32_t s[4][32];
+                uint32_t s[NC][32];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) tmem_ld_x32(s_addr + c * 32, s[c]);
+                for (int c = 0; c < NC; ++c) tmem_ld_x32(s_addr + c * 32, s[c]);
                 tmem_ld_wait();
                 if (!all_valid) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
+                    for (int c = 0; c < NC; ++c)
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
                             if (!((vm[c] >> i) & 1u)) s[c][i] = 0xff800000u;   // -inf
                 }
                 float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < NC; ++c)
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         mx0 = fmax3(mx0, __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
@@ -298,8 +351,9 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
                 const float alpha = (m_new == m) ? 1.0f : ex2_approx(m - m_safe);   // m == -inf -> 0
                 const unsigned long long sc2 = f32x2_pack(sc, sc), nm2 = f32x2_pack(-m_safe, -m_safe);
                 unsigned long long sum2 = 0ull;   // (0.f, 0.f)
+                if (pp) named_bar_sync(1 + t, 256);          // my turn on the MUFU pipe
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < NC; ++c) {
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
@@ -318,6 +372,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
                     }
                     tmem_st_x16(s_addr + c * 16, pk);
                 }
+                if (pp) named_bar_arrive(2 - t, 256);        // hand the turn to the other warpgroup
                 if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
                     // P.V of block j-1 is complete (covered by the s_full commit): rescale O_t in place.  Done after
                     // the exponentials so that the 128 score registers are dead by now (register pressure).
@@ -375,13 +430,14 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FaParam
             // the reads of O_t above are ordered before this warp's next p_full arrival (tcgen05.wait::ld + the
             // fence before that arrive), which is what the next item's first P.V (accumulate = 0) waits for
         }
+        if (pp && t == 0) named_bar_sync(1, 256);            // consume warpgroup 1's last hand-over
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 

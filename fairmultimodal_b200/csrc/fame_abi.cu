@@ -105,14 +105,16 @@ int launch_status() {
 
 #include "gemm_host.inc"
 
-template <int D, bool kDrop>
-static int launch_pair_t(const fame_attn_fwd_args* a, const CUtensorMap& tq, int sm_count, fame_stream_t stream) {
+template <int D, bool kDrop, int KB>
+static int launch_pair_t(const fame_attn_fwd_args* a, const CUtensorMap& tq, const CUtensorMap& tkv, int sm_count,
+                         fame_stream_t stream) {
+    using Cfg = fame::ApCfg<D, KB>;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(fame::attn_fwd_pair_kernel<D, kDrop>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, fame::ApCfg<D>::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(fame::attn_fwd_pair_kernel<D, kDrop, KB>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return cuda_fail(e);
         attr_set[dev] = true;
     }
@@ -130,23 +132,25 @@ static int launch_pair_t(const fame_attn_fwd_args* a, const CUtensorMap& tq, int
     p.lse = a->lse;
     p.kv_len = a->kv_len;
     p.drop = drop_cfg(a->drop);
+    p.pingpong = a->algo == 4 ? 1 : 0;      // algo 4: the warpgroups take turns on the exponential phase (A/B only)
     const int qpairs = (a->seq + 255) / 256;
     const long long items = (long long)a->batch * a->heads * qpairs;
     if (items > 0x7fffffffll) return FAME_ERR_SHAPE;
-    const int sms = persistent_sms(sm_count);
-    const int grid = items < sms ? (int)items : sms;
-    fame::attn_fwd_pair_kernel<D, kDrop><<<grid, fame::kApThreads, fame::ApCfg<D>::kSmemBytes, stream>>>(
-        tq, p, (int)items, qpairs);
+    const int slots = persistent_sms(sm_count) * Cfg::kCtasPerSm;
+    const int grid = items < slots ? (int)items : slots;
+    fame::attn_fwd_pair_kernel<D, kDrop, KB><<<grid, fame::kApThreads, Cfg::kSmemBytes, stream>>>(tq, tkv, p, (int)items,
+                                                                                              qpairs);
     return launch_status();
 }
 
-template <int D>
-static int launch_pair(const fame_attn_fwd_args* a, const CUtensorMap& tq, int sm_count, fame_stream_t stream) {
+template <int D, int KB>
+static int launch_pair(const fame_attn_fwd_args* a, const CUtensorMap& tq, const CUtensorMap& tkv, int sm_count,
+                       fame_stream_t stream) {
     if (a->drop.thresh16 != 0) {
         if (a->drop.thresh16 >= 65536u || a->drop.group_shift != 0) return FAME_ERR_SHAPE;
-        return launch_pair_t<D, true>(a, tq, sm_count, stream);
+        return launch_pair_t<D, true, KB>(a, tq, tkv, sm_count, stream);
     }
-    return launch_pair_t<D, false>(a, tq, sm_count, stream);
+    return launch_pair_t<D, false, KB>(a, tq, tkv, sm_count, stream);
 }
 
 
@@ -352,7 +356,7 @@ int fame_attn_fwd(const fame_attn_fwd_args* a, void*, size_t, fame_stream_t stre
     if (a == nullptr || a->qkv == nullptr || a->ctx == nullptr) return FAME_ERR_NULLPTR;
     if ((a->head_dim != 64 && a->head_dim != 96) || a->seq <= 0 || a->heads <= 0 || a->batch < 0)
         return FAME_ERR_SHAPE;
-    if (a->algo != 0 && a->algo != 3) return FAME_ERR_SHAPE;   // one kernel: the persistent two-tile kernel
+    if (a->algo != 0 && (a->algo < 3 || a->algo > 5)) return FAME_ERR_SHAPE;   // see fame_attn_fwd_args.algo
     const int64_t width = 3ll * a->heads * a->head_dim;
     if (a->ld_qkv < width || a->ld_ctx < (int64_t)a->heads * a->head_dim) return FAME_ERR_SHAPE;
     if ((a->ld_qkv & 7) || (a->ld_ctx & 7) || !aligned16(a->qkv) || !aligned16(a->ctx)) return FAME_ERR_ALIGN;
@@ -362,10 +366,15 @@ int fame_attn_fwd(const fame_attn_fwd_args* a, void*, size_t, fame_stream_t stre
     if (a->batch == 0) return FAME_OK;
     if (a->batch > 65535 || a->heads > 65535) return FAME_ERR_SHAPE;
 
-    CUtensorMap tq;
+    // head_dim 64: 64-key blocks, two CTAs per SM (algo 0 / 5); algo 3 / 4 force the 128-key, one-CTA-per-SM variant
+    const bool kb64 = a->head_dim == 64 && (a->algo == 0 || a->algo == 5);
+    CUtensorMap tq, tkv;
     rc = encode_bf16_2d(&tq, a->qkv, (uint64_t)a->batch * a->seq, (uint64_t)width, (uint64_t)a->ld_qkv, 128);
     if (rc != FAME_OK) return rc;
-    return a->head_dim == 64 ? launch_pair<64>(a, tq, d->sm_count, stream) : launch_pair<96>(a, tq, d->sm_count, stream);
+    rc = encode_bf16_2d(&tkv, a->qkv, (uint64_t)a->batch * a->seq, (uint64_t)width, (uint64_t)a->ld_qkv, kb64 ? 64 : 128);
+    if (rc != FAME_OK) return rc;
+    if (a->head_dim == 96) return launch_pair<96, 128>(a, tq, tkv, d->sm_count, stream);
+    return kb64 ? launch_pair<64, 64>(a, tq, tkv, d->sm_count, stream) : launch_pair<64, 128>(a, tq, tkv, d->sm_count, stream);
 }
 
 int fame_mask_kv_len(const uint8_t* key_mask, int32_t batch, int32_t seq, int32_t* kv_len, fame_stream_t stream) {

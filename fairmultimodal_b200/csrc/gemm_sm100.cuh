@@ -212,8 +212,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
             // ------------------------------------------------ MMA issuer (pair leader only): 256 x 256 x 16 per step
+            // the whole warp runs the loop so that descriptors / TMEM addresses are warp-uniform (uniform registers, one
+            // instruction per tcgen05.mma); only the elected lane issues
+            const bool leader = elect_one();
             constexpr uint32_t idesc = make_idesc_bf16(2 * kGemmBM, kGemmBN, kAMn ? 1 : 0, kBMn ? 1 : 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -229,20 +232,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem_a + stage * kGemmABytes);
                     const uint32_t b_addr = smem_u32(smem_b + stage * kGemmBBytes);
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < kGemmBK / 16; ++k) {
-                        // K-major: 16 k-elements = 32 B inside the 128 B row; SBO = 8 rows.  MN-major: 16 k-rows of
-                        // 128 B = 2 KB; LBO = distance between 64-wide MN sub-tiles, SBO = 8 k-rows.
-                        const uint64_t adesc = kAMn ? make_smem_desc_sw128(a_addr + k * 2048, kGemmSubTile, 1024)
-                                                    : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-                        const uint64_t bdesc = kBMn ? make_smem_desc_sw128(b_addr + k * 2048, kGemmSubTile, 1024)
-                                                    : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                        umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, (kb != kb_lo) || (k != 0));
+                        for (int k = 0; k < kGemmBK / 16; ++k) {
+                            // K-major: 16 k-elements = 32 B inside the 128 B row; SBO = 8 rows.  MN-major: 16 k-rows of
+                            // 128 B = 2 KB; LBO = distance between 64-wide MN sub-tiles, SBO = 8 k-rows.
+                            const uint64_t adesc = kAMn ? make_smem_desc_sw128(a_addr + k * 2048, kGemmSubTile, 1024)
+                                                        : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                            const uint64_t bdesc = kBMn ? make_smem_desc_sw128(b_addr + k * 2048, kGemmSubTile, 1024)
+                                                        : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                            umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, (kb != kb_lo) || (k != 0));
+                        }
+                        umma_commit_pair(&empty_bar[stage], 3);   // frees the slot in both CTAs' producers
                     }
-                    umma_commit_pair(&empty_bar[stage], 3);   // frees the slot in both CTAs' producers
                     if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_pair(&tmem_full[acc], 3);     // accumulators of both CTAs are complete
+                if (leader) umma_commit_pair(&tmem_full[acc], 3);     // accumulators of both CTAs are complete
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }

@@ -319,17 +319,26 @@ layernorm_bf16_rows2_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, 
     }
 }
 
-// kv_len[b] = 1 + index of the last non-zero byte of key_mask[b, :]  (0 for an all-zero row); warp per sequence
+// |kv_len[b]| = 1 + index of the last non-zero byte of key_mask[b, :]  (0 for an all-zero row); warp per sequence.
+// The sign says whether the mask is a PREFIX mask (every key before the last attended one is attended too -- what a
+// padded tokenizer batch produces): kv_len >= 0 then, and the attention kernel derives key validity from the length
+// alone; a mask with holes gets -last and the kernel reads the mask bytes.
 __global__ void __launch_bounds__(256)
 mask_kv_len_kernel(const uint8_t* __restrict__ key_mask, int batch, int seq, int* __restrict__ kv_len) {
     const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= batch) return;
-    int last = 0;
+    int last = 0, ones = 0;
     for (int k = lane; k < seq; k += 32)
-        if (key_mask[(long long)b * seq + k] != 0) last = k + 1;
+        if (key_mask[(long long)b * seq + k] != 0) {
+            last = k + 1;
+            ++ones;
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-    if (lane == 0) kv_len[b] = last;
+    for (int o = 16; o > 0; o >>= 1) {
+        last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+        ones += __shfl_xor_sync(0xffffffffu, ones, o);
+    }
+    if (lane == 0) kv_len[b] = ones == last ? last : -last;
 }
 
 // ---------------------------------------------------------------------------------------- K4 BERT embedding

@@ -191,8 +191,12 @@ typedef struct {
     int64_t ld_ctx;
     int32_t batch, seq, heads, head_dim;
     float scale;
-    int32_t algo; /* 0 (or 3, its former explicit name): the persistent kernel, two 128-query tiles per CTA.  The
-                     round-1 alternatives 1 / 2 were removed: FAME_ERR_SHAPE */
+    int32_t algo; /* 0: the persistent two-tile kernel in its default shape: head_dim 64 -> 64-key blocks, two CTAs per SM
+                     (four query tiles / sixteen softmax warps per SM); head_dim 96 -> 128-key blocks, one CTA per SM.
+                     3: 128-key blocks, one CTA per SM (any head_dim); 4: as 3 with the two softmax warpgroups taking
+                     turns on the exponential phase; 5: 64-key blocks (head_dim 64).  3-5 exist for A/B measurements;
+                     all variants produce the same result up to the order of the online-softmax blocks.
+                     Other values: FAME_ERR_SHAPE */
     float* lse;   /* optional f32 [batch, heads, seq]: log2-domain log-sum-exp of each row of scaled scores, saved for
                      fame_attn_bwd_pds (P = 2^(s * scale * log2 e - lse)); may be NULL */
     const int32_t* kv_len; /* optional int32 [batch] from fame_mask_kv_len: 1 + index of the last attended key of each
@@ -204,9 +208,11 @@ typedef struct {
 } fame_attn_fwd_args;
 int fame_attn_fwd(const fame_attn_fwd_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream);
 
-/* fame_mask_kv_len: kv_len[b] = 1 + max{k : key_mask[b, k] != 0} (0 when the row is all zero).  key_mask uint8
- * [batch, seq] as handed to fame_attn_fwd (the reference's attention_mask, HF:709-713), computed once per batch and
- * shared by the 12 layers. */
+/* fame_mask_kv_len: |kv_len[b]| = 1 + max{k : key_mask[b, k] != 0} (0 when the row is all zero); the value is >= 0
+ * when the row is a prefix mask (ones, then zeros: a padded tokenizer batch) and negative when the attended keys have
+ * holes.  fame_attn_fwd skips key blocks beyond |kv_len| and, for prefix rows, derives key validity from the length
+ * without reading the mask bytes.  key_mask uint8 [batch, seq] as handed to fame_attn_fwd (the reference's
+ * attention_mask, HF:709-713), computed once per batch and shared by the 12 layers. */
 int fame_mask_kv_len(const uint8_t* key_mask, int32_t batch, int32_t seq, int32_t* kv_len, fame_stream_t stream);
 
 /* fame_attn_cls: attention for ONE query row per sequence (head_dim 64) -- the last encoder layer of the note

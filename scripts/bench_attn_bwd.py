@@ -47,3 +47,21 @@ for B in (32, 1024):
         out[f"B{B}_p{p}_forward"] = {"ms": ms, "tflops": 4.0 * B * nh * L * L * D / ms / 1e9}
         print(B, p, "fwd", f"{ms:.3f} ms", flush=True)
 json.dump(out, open("gpurun_out/attn_bwd_bench.json", "w"), indent=1)
+
+# ---- forward, note-encoder shape (256 chunks x 12 heads x 512 tokens x 64): algo 0 / 5 = 64-key blocks, two CTAs per SM;
+# 3 = 128-key blocks, one CTA per SM; 4 = 3 + ping-pong of the softmax warpgroups
+B, L, nh, D = 256, 512, 12, 64
+qkv = (torch.randn(B * L, 3 * nh * D, device="cuda") * 0.7).bfloat16()
+for algo in (0, 3, 4, 5):
+    for _ in range(3):
+        ops.attn_fwd(qkv, B, L, nh, D, algo=algo)
+    ts = []
+    for _ in range(7):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.attn_fwd(qkv, B, L, nh, D, algo=algo); e1.record()
+        torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    out[f"note_fwd_algo{algo}"] = {"ms": ms, "tflops": 4.0 * B * nh * L * L * D / ms / 1e9}
+    print("note fwd algo", algo, f"{ms:.3f} ms  {4.0 * B * nh * L * L * D / ms / 1e9:.0f} TFLOP/s", flush=True)
+json.dump(out, open("gpurun_out/attn_bwd_bench.json", "w"), indent=1)

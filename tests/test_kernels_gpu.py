@@ -189,7 +189,9 @@ def test_attention_kv_len_skips_only_masked_blocks(H, D, B, S):
     mask = mask.to(torch.uint8).contiguous()
     kv_len = ops.mask_kv_len(mask)
     last = torch.where(mask.bool(), torch.arange(1, S + 1, device="cuda")[None, :], 0).max(dim=1).values
-    assert torch.equal(kv_len.long(), last)              # integer indexing: bit-exact
+    assert torch.equal(kv_len.long().abs(), last)        # integer indexing: bit-exact
+    prefix = mask.long().sum(dim=1) == last               # sign: prefix mask (validity from the length) or a mask with holes
+    assert torch.equal(kv_len >= 0, prefix) and not bool(prefix[2]) and bool(prefix[0])
     lse0 = torch.empty(B, H, S, device="cuda")
     lse1 = torch.empty(B, H, S, device="cuda")
     full = ops.attn_fwd(qkv, B, S, H, D, key_mask=mask, lse=lse0)
