@@ -18,11 +18,16 @@
 // Both passes recompute the scores (7 tile products per 128 x 128 pair instead of 5 with a dQ reduction across CTAs);
 // the softmax statistics come from the forward's row log-sum-exp, so there is no max / sum pass.
 //
-//   warp 8 lane 0 : TMA producer    stationary pair per item; streamed half-block ring (4 stages x 32 KB), SW128 boxes
-//   warp 9 lane 0 : MMA issuer      scores of half block g -> TMEM stage g & 1 (cols [128 s, +64) and [128 s + 64, +64));
+//   warp 16 lane 0 : TMA producer   stationary pair per item; streamed half-block ring (4 stages x 32 KB), SW128 boxes
+//   warp 17        : MMA issuer     scores of half block g -> TMEM stage g & 1 (cols [128 s, +64) and [128 s + 64, +64));
 //                                   accumulators at cols 256 (dQ | dV) and 384 (dK); runs two half blocks ahead
-//   warps 0-3     : softmax-backward warpgroup of even half blocks (thread = one stationary row)
-//   warps 4-7     : warpgroup of odd half blocks
+//   warps 0-7      : softmax-backward group of even half blocks: thread = one stationary row x 32 of the 64 streamed
+//                    columns (warps q and q + 4 share TMEM lane quadrant q and take columns [0, 32) / [32, 64))
+//   warps 8-15     : group of odd half blocks
+// Sixteen softmax warps (four per scheduler) instead of eight: with two per scheduler the S -> dS -> next-S chain of a
+// stage was exposed (ncu r02: 2 300 - 2 700 clk per half block against 576 / 768 clk of tensor pipe, the warps' issue
+// slots 25 % used).  A thread writes its bf16 results over columns it has itself read, so no ordering is needed
+// between the two warps of a quadrant: P of columns [32 h, 32 h + 32) lands in [32 h, 32 h + 16).
 // TMEM: 2 stages x 128 score columns + 2 x 96 accumulator columns.  Streamed traffic: 32 KB per 64-row half block
 // (head_dim 96 is loaded as two 64-column boxes) against 576 / 768 clk of tensor pipe: ~43-57 B/clk/SM from L2 -- the
 // kernel sits at the L2 -> SM bandwidth of the chip (~6.3 KB/clk), which is why the ring is four deep.
@@ -33,7 +38,7 @@
 
 namespace fame {
 
-constexpr int kAfThreads = 320;
+constexpr int kAfThreads = 576;          // 16 softmax-backward warps + TMA producer + MMA issuer
 
 template <int D>
 struct AfCfg {
@@ -104,13 +109,13 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&sd_full[i], 1);
-            mbar_init(&ds_full[i], 4);
+            mbar_init(&ds_full[i], 8);
         }
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 8);
+        mbar_init(acc_empty, 16);
         fence_barrier_init();
     }
-    if (warp == 8) {
+    if (warp == 16) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
@@ -123,7 +128,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
     const int a1_col0 = kKV ? p.k_col0 : p.q_col0;        // a2: V (qkv) | dO (dctx, column 0)
     const int b1_col0 = kKV ? p.q_col0 : p.k_col0;        // b2: dO (dctx) | V (qkv)
 
-    if (warp == 8) {
+    if (warp == 16) {
         if (lane == 0) {
             // ------------------------------------------------------------------------------------ TMA producer
             int st = 0;
@@ -166,7 +171,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 17) {
         if (blockIdx.x < num_items) {
             // ------------------------------------------------------------------------------------ MMA issuer
             // The whole warp runs the loop (warp-uniform control flow and operands: descriptors and TMEM addresses live
@@ -236,22 +241,23 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                     const uint32_t col = tmem_base + s * 128;
                     if (leader) {
                         if (kKV) {
-                            // dV_j += P^T (cols [0, 32) of the stage) . dO_ih ;  dK_j += dS^T (cols [64, 96)) . Q_ih
+                            // dV_j += P^T . dO_ih ;  dK_j += dS^T . Q_ih   (bf16 P^T at cols [0,16) u [32,48) of the stage, dS^T
+                            // at [64,80) u [96,112): each softmax thread writes over columns it has read itself)
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk)
-                                umma_bf16_ts(tmem_base + kColAcc0, col + kk * 8,
+                                umma_bf16_ts(tmem_base + kColAcc0, col + (kk >> 1) * 32 + (kk & 1) * 8,
                                              make_smem_desc_sw128(b2_addr + kk * 2048, Cfg::kHalfBoxBytes, 1024), idesc_ac,
                                              (hb | kk) != 0);
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk)
-                                umma_bf16_ts(tmem_base + kColAcc1, col + 64 + kk * 8,
+                                umma_bf16_ts(tmem_base + kColAcc1, col + 64 + (kk >> 1) * 32 + (kk & 1) * 8,
                                              make_smem_desc_sw128(b1_addr + kk * 2048, Cfg::kHalfBoxBytes, 1024), idesc_ac,
                                              (hb | kk) != 0);
                         } else {
-                            // dQ_i += dS (cols [64, 96) of the stage) . K_jh
+                            // dQ_i += dS . K_jh   (bf16 dS at cols [64,80) u [96,112) of the stage)
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk)
-                                umma_bf16_ts(tmem_base + kColAcc0, col + 64 + kk * 8,
+                                umma_bf16_ts(tmem_base + kColAcc0, col + 64 + (kk >> 1) * 32 + (kk & 1) * 8,
                                              make_smem_desc_sw128(b1_addr + kk * 2048, Cfg::kHalfBoxBytes, 1024), idesc_ac,
                                              (hb | kk) != 0);
                         }
@@ -271,11 +277,12 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
     } else {
         // -------------------------------------------------------------------------------- softmax-backward warpgroups
         const int q = warp & 3;       // TMEM lane quadrant
-        const int w = warp >> 2;      // warpgroup = parity of the CTA's half-block counter it serves
+        const int w = warp >> 3;      // group = parity of the CTA's half-block counter it serves
+        const int hcol = (warp >> 2) & 1;   // which 32 of the 64 streamed columns this warp owns
         const int r = q * 32 + lane;  // stationary row inside the tile
-        const int tw = threadIdx.x & 127;   // thread inside the warpgroup
+        const int tw = threadIdx.x & 255;   // thread inside the group
         const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
-        const uint32_t st_base = lane_base + w * 128;
+        const uint32_t st_base = lane_base + w * 128 + hcol * 32;
         float* stats = smem_stats + w * (2 * 3 * 64);     // [buffer][lse | delta * scale | row seed][64]
         const float sc = p.scale_log2e;
         const uint32_t drop_site = kDrop ? drop_site_seed(p.drop) : 0u;
@@ -322,10 +329,10 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                     if (tw < 64) {
                         sbuf[tw] = pf_lse;
                         sbuf[64 + tw] = pf_dls * p.scale;
-                    } else if (kDrop) {
+                    } else if (kDrop && tw < 128) {
                         reinterpret_cast<uint32_t*>(sbuf)[128 + tw - 64] = drop_row_seed(drop_site, (uint32_t)(stat0 + c0 + tw - 64));
                     }
-                    named_bar_sync(1 + w, 128);
+                    named_bar_sync(1 + w, 256);
                     prefetch_cols(hb + 2);
                 }
                 ++nproc;
@@ -334,14 +341,14 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                 tc_fence_after();
 #pragma unroll 1
                 for (int c = 0; c < 2; ++c) {
-                    uint32_t s[32], dp[32];
-                    tmem_ld_x32(st_base + c * 32, s);
-                    tmem_ld_x32(st_base + 64 + c * 32, dp);
+                    uint32_t s[16], dp[16];
+                    tmem_ld_x16(st_base + c * 16, s);
+                    tmem_ld_x16(st_base + 64 + c * 16, dp);
                     tmem_ld_wait();
-                    uint32_t pk[16], dk[16];
+                    uint32_t pk[8], dk[8];
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const int cc = c * 32 + i;         // column inside the half block
+                    for (int i = 0; i < 16; i += 2) {
+                        const int cc = hcol * 32 + c * 16 + i;   // column inside the half block
                         float p0, p1, d0, d1;
                         float dp0 = __uint_as_float(dp[i]), dp1 = __uint_as_float(dp[i + 1]);
                         if (!kKV) {
@@ -378,10 +385,10 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                         }
                         dk[i >> 1] = pack_bf16x2(d0, d1);
                     }
-                    // bf16 tiles over the fp32 scores they came from: P^T -> cols [0, 32), dS -> cols [64, 96) of the stage
-                    // (chunk c writes 16 columns that this thread has already read)
-                    if (kKV) tmem_st_x16(st_base + c * 16, pk);
-                    tmem_st_x16(st_base + 64 + c * 16, dk);
+                    // bf16 tiles over the fp32 scores this thread has read: 16 columns [32 h + 16 c, +16) -> 8 packed
+                    // columns at [32 h + 8 c, +8) of the S (P^T) and dP (dS) blocks
+                    if (kKV) tmem_st_x8(st_base + c * 8, pk);
+                    tmem_st_x8(st_base + 64 + c * 8, dk);
                 }
                 tmem_st_wait();
                 tc_fence_before();
@@ -394,31 +401,10 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
             tc_fence_after();
             __nv_bfloat16* dst_row = p.dqkv + (long long)(b * S + srow) * p.ld + h * D;
             if (kKV) {
-                // warpgroup 0: dV (accumulator 0), warpgroup 1: dK (accumulator 1); 96 columns each
-                const uint32_t acc = lane_base + (w == 0 ? kColAcc0 : kColAcc1);
-                __nv_bfloat16* dst = dst_row + (w == 0 ? p.v_col0 : p.k_col0);
-#pragma unroll
-                for (int c = 0; c < D / 32; ++c) {
-                    uint32_t o[32];
-                    tmem_ld_x32(acc + c * 32, o);
-                    tmem_ld_wait();
-                    if (row_ok) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            uint4 u;
-                            u.x = pack_bf16x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1]));
-                            u.y = pack_bf16x2(__uint_as_float(o[i + 2]), __uint_as_float(o[i + 3]));
-                            u.z = pack_bf16x2(__uint_as_float(o[i + 4]), __uint_as_float(o[i + 5]));
-                            u.w = pack_bf16x2(__uint_as_float(o[i + 6]), __uint_as_float(o[i + 7]));
-                            *reinterpret_cast<uint4*>(dst + c * 32 + i) = u;
-                        }
-                    }
-                }
-            } else {
-                // dQ: warpgroup w stores columns [w * D/2, (w + 1) * D/2) in 16-column pieces
+                // group 0: dV (accumulator 0), group 1: dK (accumulator 1); each warp of a quadrant pair stores D / 2 columns
                 constexpr int HALF = D / 2;
-                const uint32_t acc = lane_base + kColAcc0 + w * HALF;
-                __nv_bfloat16* dst = dst_row + p.q_col0 + w * HALF;
+                const uint32_t acc = lane_base + (w == 0 ? kColAcc0 : kColAcc1) + hcol * HALF;
+                __nv_bfloat16* dst = dst_row + (w == 0 ? p.v_col0 : p.k_col0) + hcol * HALF;
 #pragma unroll
                 for (int c = 0; c < HALF / 16; ++c) {
                     uint32_t o[16];
@@ -436,6 +422,26 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                         }
                     }
                 }
+            } else {
+                // dQ: the four warps of a quadrant (2 groups x 2 column halves) store D / 4 columns each
+                constexpr int QUART = D / 4;
+                const int part = 2 * w + hcol;
+                const uint32_t acc = lane_base + kColAcc0 + part * QUART;
+                __nv_bfloat16* dst = dst_row + p.q_col0 + part * QUART;
+#pragma unroll
+                for (int c = 0; c < QUART / 8; ++c) {
+                    uint32_t o[8];
+                    tmem_ld_x8(acc + c * 8, o);
+                    tmem_ld_wait();
+                    if (row_ok) {
+                        uint4 u;
+                        u.x = pack_bf16x2(__uint_as_float(o[0]), __uint_as_float(o[1]));
+                        u.y = pack_bf16x2(__uint_as_float(o[2]), __uint_as_float(o[3]));
+                        u.z = pack_bf16x2(__uint_as_float(o[4]), __uint_as_float(o[5]));
+                        u.w = pack_bf16x2(__uint_as_float(o[6]), __uint_as_float(o[7]));
+                        *reinterpret_cast<uint4*>(dst + c * 8) = u;
+                    }
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -445,7 +451,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 16) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }

@@ -672,7 +672,17 @@ int fame_eval_counts(const fame_eval_counts_args* a, void*, size_t, fame_stream_
     return launch_status();
 }
 
-size_t fame_rank_counts_workspace_bytes(int32_t n_i) { return sizeof(double) * (size_t)((n_i + 255) / 256 + 1); }
+static inline size_t rank_npad(int32_t n) {
+    size_t p = fame::kSortTile;
+    while (p < (size_t)n) p <<= 1;
+    return p;
+}
+// brute-force sub-range: per-block float64 partials; full range: padded key array + prefix-positives array
+size_t fame_rank_counts_workspace_bytes(int32_t n_i) {
+    const size_t brute = sizeof(double) * (size_t)((n_i + 255) / 256 + 1);
+    const size_t sorted = sizeof(uint32_t) * (rank_npad(n_i) + (size_t)n_i);
+    return brute > sorted ? brute : sorted;
+}
 
 int fame_rank_counts(const fame_rank_counts_args* a, void* workspace, size_t workspace_bytes, fame_stream_t stream) {
     if (a == nullptr || a->scores == nullptr || a->y == nullptr || a->auroc2 == nullptr || a->ap_sum == nullptr ||
@@ -686,6 +696,26 @@ int fame_rank_counts(const fame_rank_counts_args* a, void* workspace, size_t wor
     if (n_i == 0) return FAME_OK;
     if (workspace == nullptr) return FAME_ERR_NULLPTR;
     if (workspace_bytes < fame_rank_counts_workspace_bytes(n_i)) return FAME_ERR_WORKSPACE;
+    if (a->i0 == 0 && a->i1 == a->N) {
+        // full range: sort + tie-run scan, O(N log N)
+        const size_t npad = rank_npad(a->N);
+        if (npad > (size_t)1 << 30) return FAME_ERR_SHAPE;
+        uint32_t* keys = reinterpret_cast<uint32_t*>(workspace);
+        uint32_t* cpos = keys + npad;
+        fame::rank_keys_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, stream>>>(a->scores, a->y, a->N, (int)npad, keys);
+        const unsigned tiles = (unsigned)(npad / fame::kSortTile);
+        fame::bitonic_smem_kernel<<<tiles, 1024, 0, stream>>>(keys, 2, fame::kSortTile, fame::kSortTile / 2);
+        for (size_t k = 2 * (size_t)fame::kSortTile; k <= npad; k <<= 1) {
+            for (size_t j = k >> 1; j >= (size_t)fame::kSortTile; j >>= 1)
+                fame::bitonic_global_kernel<<<(unsigned)((npad / 2 + 255) / 256), 256, 0, stream>>>(keys, (int)npad, (int)k,
+                                                                                               (int)j);
+            fame::bitonic_smem_kernel<<<tiles, 1024, 0, stream>>>(keys, (int)k, (int)k, fame::kSortTile / 2);
+        }
+        fame::rank_scan_kernel<<<1, 1024, 0, stream>>>(keys, a->N, cpos, reinterpret_cast<unsigned long long*>(a->auroc2),
+                                                       a->ap_sum, reinterpret_cast<unsigned long long*>(a->npos_nneg));
+        return launch_status();
+    }
+    // a sub-range of i against all j (a caller that shards i across ranks): exact O(N^2 / ranks) compare
     fame::RankParams p;
     p.scores = a->scores; p.y = a->y; p.N = a->N; p.i0 = a->i0; p.i1 = a->i1;
     p.auroc2 = reinterpret_cast<unsigned long long*>(a->auroc2);

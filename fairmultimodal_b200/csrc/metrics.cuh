@@ -226,6 +226,153 @@ rank_counts_kernel(const RankParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ rank counts, sorted
+// The same statistics in O(N log N) for the FULL range [0, N): key = (score bits << 1) | label (scores are probabilities
+// in [0, 1]: their fp32 bit patterns are non-negative and order like the values), bitonic sort of the keys, then one pass
+// over the sorted keys in DESCENDING score order.  For a run of tied scores G (all keys with the same score bits), with
+// cpos / cneg = positives / negatives counted up to and including the run:
+//     every positive of G has  ge_pos = cpos(G), ge_neg = cneg(G), gt_neg = cneg(before G)
+//     ap_sum += npos(G) * cpos(G) / (cpos(G) + cneg(G))          auroc2 += npos(G) * (cneg(G) + cneg(before G))
+// Exactly the brute-force kernel's integers; the float64 AP sum runs in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+rank_keys_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ y, int N, int npad,
+                 uint32_t* __restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    keys[i] = i < N ? ((__float_as_uint(scores[i]) << 1) | (y[i] != 0 ? 1u : 0u)) : 0xffffffffu;   // padding sorts last
+}
+
+constexpr int kSortTile = 4096;      // keys per CTA in the shared-memory stages (1024 threads x 4)
+
+// all compare-exchange stages with stride < kSortTile for the merge sizes k = k_lo .. k_hi (one launch sorts every
+// 4096-key tile completely when k_lo = 2, k_hi = kSortTile; later launches finish a merge whose large strides ran in
+// global memory)
+__global__ void __launch_bounds__(1024)
+bitonic_smem_kernel(uint32_t* __restrict__ keys, int k_lo, int k_hi, int j_hi) {
+    __shared__ uint32_t sh[kSortTile];
+    const int base = blockIdx.x * kSortTile;
+    for (int t = threadIdx.x; t < kSortTile; t += 1024) sh[t] = keys[base + t];
+    __syncthreads();
+    for (int k = k_lo; k <= k_hi; k <<= 1) {
+        for (int j = min(k >> 1, j_hi); j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < kSortTile / 2; t += 1024) {
+                const int lo = ((t / j) * 2 * j) + (t % j), hi = lo + j;
+                const bool up = (((base + lo) & k) == 0);
+                const uint32_t a = sh[lo], b = sh[hi];
+                if ((a > b) == up) {
+                    sh[lo] = b;
+                    sh[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = threadIdx.x; t < kSortTile; t += 1024) keys[base + t] = sh[t];
+}
+
+// one compare-exchange stage with stride j >= kSortTile of merge size k, in global memory
+__global__ void __launch_bounds__(256)
+bitonic_global_kernel(uint32_t* __restrict__ keys, int npad, int k, int j) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npad / 2) return;
+    const int lo = ((t / j) * 2 * j) + (t % j), hi = lo + j;
+    const bool up = ((lo & k) == 0);
+    const uint32_t a = keys[lo], b = keys[hi];
+    if ((a > b) == up) {
+        keys[lo] = b;
+        keys[hi] = a;
+    }
+}
+
+// one CTA walks the sorted keys from the largest score down, 1024 positions per step
+__global__ void __launch_bounds__(1024)
+rank_scan_kernel(const uint32_t* __restrict__ keys, int N, uint32_t* __restrict__ cpos_g, unsigned long long* auroc2,
+                 double* ap_sum, unsigned long long* npos_nneg) {
+    __shared__ uint32_t wsum[32], wmax[32];
+    __shared__ double red[32];
+    __shared__ unsigned long long redu[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t carry_pos = 0, carry_start = 0;
+    double ap = 0.0;
+    unsigned long long au = 0ull;
+    for (int d0 = 0; d0 < N; d0 += 1024) {
+        const int d = d0 + threadIdx.x;                 // position in descending order <-> sorted index N - 1 - d
+        const bool live = d < N;
+        const uint32_t key = live ? keys[N - 1 - d] : 0u;
+        const uint32_t sc = key >> 1, pos = live ? (key & 1u) : 0u;
+        const bool starts = live && (d == 0 || (keys[N - d] >> 1) != sc);           // previous position has another score
+        const bool ends = live && (d == N - 1 || (keys[N - 2 - d] >> 1) != sc);     // next position has another score
+        // inclusive scans over the 1024 positions: positives (sum) and latest run start (max)
+        uint32_t ps = pos, st = starts ? (uint32_t)d : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, ps, o), b = __shfl_up_sync(0xffffffffu, st, o);
+            if (lane >= o) {
+                ps += a;
+                st = max(st, b);
+            }
+        }
+        if (lane == 31) {
+            wsum[warp] = ps;
+            wmax[warp] = st;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t a = wsum[lane], b = wmax[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xffffffffu, a, o), y2 = __shfl_up_sync(0xffffffffu, b, o);
+                if (lane >= o) {
+                    a += x;
+                    b = max(b, y2);
+                }
+            }
+            wsum[lane] = a;
+            wmax[lane] = b;
+        }
+        __syncthreads();
+        const uint32_t cpos = carry_pos + ps + (warp > 0 ? wsum[warp - 1] : 0u);
+        const uint32_t start = max(max(carry_start, st), warp > 0 ? wmax[warp - 1] : 0u);
+        if (live) cpos_g[d] = cpos;
+        __syncthreads();                                  // cpos of this step visible to the whole CTA (global, same block)
+        if (ends) {
+            const uint32_t before = start > 0 ? cpos_g[start - 1] : 0u;      // positives before the run
+            const uint32_t npos_g = cpos - before;
+            if (npos_g) {
+                const uint32_t cneg = (uint32_t)(d + 1) - cpos, cneg_before = start - before;
+                ap += (double)npos_g * ((double)cpos / (double)(d + 1));
+                au += (unsigned long long)npos_g * ((unsigned long long)cneg + cneg_before);
+            }
+        }
+        carry_pos += wsum[31];
+        carry_start = max(carry_start, wmax[31]);
+        __syncthreads();
+    }
+    // fixed-order block reduction
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ap += __shfl_xor_sync(0xffffffffu, ap, o);
+        au += __shfl_xor_sync(0xffffffffu, au, o);
+    }
+    if (lane == 0) {
+        red[warp] = ap;
+        redu[warp] = au;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+        unsigned long long u = 0ull;
+        for (int w = 0; w < 32; ++w) {
+            a += red[w];
+            u += redu[w];
+        }
+        *ap_sum += a;
+        *auroc2 += u;
+        npos_nneg[0] += carry_pos;
+        npos_nneg[1] += (unsigned long long)N - carry_pos;
+    }
+}
+
 // fixed-order sum of the per-block partials (deterministic), accumulated into *dst
 __global__ void sum_partials_kernel(const double* __restrict__ part, int n, double* __restrict__ dst) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {

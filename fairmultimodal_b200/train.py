@@ -376,6 +376,13 @@ class FlatTrainState:
             self._side = torch.cuda.Stream(device=self.p.device, priority=-1)   # short kernels first when an SM frees
         return self._side
 
+    def wgrad_stream(self):
+        """Branch for the weight gradients of the demographic tower: they are off the data-gradient chain (see
+        _demo_backward)."""
+        if getattr(self, "_wgs", None) is None:
+            self._wgs = torch.cuda.Stream(device=self.p.device)
+        return self._wgs
+
     def post_stream(self):
         if getattr(self, "_post", None) is None:
             self._post = torch.cuda.Stream(device=self.p.device, priority=-1)
@@ -661,7 +668,39 @@ class _GradReducer:
         self.st.sumsq_valid = True
 
 
+DEMO_WGRAD_BRANCH = os.environ.get("FAME_DEMO_WGRAD_BRANCH", "1") != "0"
+
+
+class _WgradBranch:
+    """Weight-gradient launches of the demographic tower on their own stream.  Per layer the backward is a chain of
+    LayerNorm-backward and data-gradient kernels (each needs the previous one's output); the four weight gradients of a
+    layer only CONSUME tensors of that chain (dY and the saved input), nothing on the chain waits for them.  At 32 rows
+    every kernel here is latency bound (4-12 us each, 15 per layer), so taking the 48 weight-gradient launches off the
+    chain shortens the tower's backward by about 40 %.  join() orders the branch before whatever follows on the current
+    stream (a bucket's collective, the end of the backward); the tensors a branch kernel reads stay referenced until
+    then (the caching allocator could otherwise hand their memory back to the chain's stream)."""
+
+    def __init__(self, st):
+        self.stream = st.wgrad_stream() if (DEMO_WGRAD_BRANCH and st is not None) else None
+        self.keep = []
+
+    def run(self, fn, *tensors):
+        if self.stream is None:
+            fn()
+            return
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            fn()
+        self.keep.extend(tensors)
+
+    def join(self):
+        if self.stream is not None and self.keep:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.keep.clear()
+
+
 def _demo_backward(st, model, saved, ddemo, reducer=None, ds=None, dpre="behrt_demo."):
+    wg = _WgradBranch(st)
     pre = dpre + "bert."
     ph = ds.p_demo_hidden if ds is not None else 0.0
     pa = ds.p_demo_attn if ds is not None else 0.0
@@ -683,16 +722,17 @@ def _demo_backward(st, model, saved, ddemo, reducer=None, ds=None, dpre="behrt_d
                                                 want_bf16=ph <= 0, want_f32=True, drop=site(f"demo.{i}.h2", ph))
         if dt2m is None:
             dt2m = dt2b
-            _lin_bwd(st, p + "output.dense.weight", p + "output.dense.bias", dt2m, s["h"], colsum_src=dt2f)
+            wg.run(lambda: _lin_bwd(st, p + "output.dense.weight", p + "output.dense.bias", dt2m, s["h"], colsum_src=dt2f),
+                   dt2m, dt2f)
         else:
-            _lin_bwd(st, p + "output.dense.weight", p + "output.dense.bias", dt2m, s["h"])
+            wg.run(lambda: _lin_bwd(st, p + "output.dense.weight", p + "output.dense.bias", dt2m, s["h"]), dt2m)
         if dt2m.shape[0] <= T.SKINNY_MAX_ROWS and FUSE_GELU and st.wt(p + "output.dense.weight") is not None:
             dpre = T.linear_dgrad(dt2m, st.w(p + "output.dense.weight"), wT=st.wt(p + "output.dense.weight"), aux=s["pre"],
                                   aux_mode=T.AUX_GELU_BWD_BF16)
         else:
             dh = T.linear_dgrad(dt2m, st.w(p + "output.dense.weight"), wT=st.wt(p + "output.dense.weight"))
             dpre = T.gelu_bwd(s["pre"], dh)
-        _lin_bwd(st, p + "intermediate.dense.weight", p + "intermediate.dense.bias", dpre, s["x1b"])
+        wg.run(lambda: _lin_bwd(st, p + "intermediate.dense.weight", p + "intermediate.dense.bias", dpre, s["x1b"]), dpre)
         dx1 = T.linear_dgrad(dpre, st.w(p + "intermediate.dense.weight"), out_dtype=torch.float32, aux=dt2f,
                              aux_mode=T.AUX_ADD_F32, wT=st.wt(p + "intermediate.dense.weight"))
         dt1b, dt1f, dt1m = T.layernorm_bwd_drop(s["t1"], dx1, s["st1"], st.f(p + "attention.output.LayerNorm.weight"),
@@ -701,19 +741,21 @@ def _demo_backward(st, model, saved, ddemo, reducer=None, ds=None, dpre="behrt_d
                                                 want_f32=True, drop=site(f"demo.{i}.h1", ph))
         if dt1m is None:
             dt1m = dt1b
-            _lin_bwd(st, p + "attention.output.dense.weight", p + "attention.output.dense.bias", dt1m, s["v"],
-                     colsum_src=dt1f)
+            wg.run(lambda: _lin_bwd(st, p + "attention.output.dense.weight", p + "attention.output.dense.bias", dt1m, s["v"],
+                                    colsum_src=dt1f), dt1m, dt1f)
         else:
-            _lin_bwd(st, p + "attention.output.dense.weight", p + "attention.output.dense.bias", dt1m, s["v"])
+            wg.run(lambda: _lin_bwd(st, p + "attention.output.dense.weight", p + "attention.output.dense.bias", dt1m, s["v"]),
+                   dt1m)
         # s["v"] is the context = head-dropped value projection; its gradient passes the same per-head mask
         dv = T.linear_dgrad(dt1m, st.w(p + "attention.output.dense.weight"),
                             wT=st.wt(p + "attention.output.dense.weight"), drop=site(f"demo.{i}.attn", pa, saved.get("hshift", 6)))
-        _lin_bwd(st, p + "attention.self.value.weight", p + "attention.self.value.bias", dv, s["xb"])
+        wg.run(lambda: _lin_bwd(st, p + "attention.self.value.weight", p + "attention.self.value.bias", dv, s["xb"]), dv)
         # one key per sequence: softmax == 1, so query / key receive exactly zero gradient (their .grad stays 0 and
         # AdamW still applies weight decay to them, as in the reference)
         dx = T.linear_dgrad(dv, st.w(p + "attention.self.value.weight"), out_dtype=torch.float32, aux=dt1f,
                             aux_mode=T.AUX_ADD_F32, wT=st.wt(p + "attention.self.value.weight"))
         if reducer is not None and i in cut_layers:
+            wg.join()                                               # the bucket's weight gradients are complete
             reducer.ready(("demo", i))
     e = pre + "embeddings."
     T.dropout_apply(dx, site("demo.emb", ph))                       # BertEmbeddings.dropout backward (no-op when off)
@@ -721,6 +763,7 @@ def _demo_backward(st, model, saved, ddemo, reducer=None, ds=None, dpre="behrt_d
                               st.gr(e + "LayerNorm.weight"), st.gr(e + "LayerNorm.bias"), want_bf16=False, want_f32=True)
     T.bert_embed_bwd(dsum, saved["ids"], st.gr(e + "word_embeddings.weight"), st.gr(e + "position_embeddings.weight"),
                      st.gr(e + "token_type_embeddings.weight")[0], 1, pad_idx=0)
+    wg.join()
 
 
 # ------------------------------------------------------------------------------------------------ lab tower
@@ -839,34 +882,43 @@ def _fusion_pack(st):
         b4=f("fusion_mlp.3.bias"))
 
 
-def _fusion_backward(st, fo, embs, dlogits, w_mod, lambda_l1, d_fus=None, w_mod_dev=None):
-    """Returns (d demo_emb, d lab_emb) f32 [B,768]; writes every head gradient into the flat buffer."""
+def _fusion_backward(st, fo, embs, dlogits, w_mod, lambda_l1, d_fus=None, w_mod_dev=None, branch=None):
+    """Returns (d demo_emb, d lab_emb) f32 [B,768]; writes every head gradient into the flat buffer.  The chain
+    dlogits -> dhid -> dgated -> dproj -> d embeddings is what both towers' backward passes wait for, so it is enqueued
+    first; the head's own parameter gradients (five small products, five column sums) only consume tensors of that chain
+    and run on `branch` (a _WgradBranch; the caller joins it before the tail bucket is reduced)."""
     B = dlogits.shape[0]
     dev = dlogits.device
     f, g = st.f, st.gr
+    branch = _WgradBranch(None) if branch is None else branch
     hid = fo["hid_drop"] if d_fus is not None else torch.relu(fo["pre_relu"])  # [B,512] input of fusion_mlp[3]
-    # fusion_mlp.3: dW4[3,512] = dlogits^T hid ; db4 = colsum(dlogits)
-    T.sgemm(dlogits, 1, 3, hid, 512, 1, g("fusion_mlp.3.weight"), 3, 512, B)
-    T.colsum(dlogits, g("fusion_mlp.3.bias"))
     dhid = T.fusion_bwd_hidden(dlogits, f("fusion_mlp.3.weight"), fo["pre_relu"])
     T.dropout_apply(dhid, d_fus)                                               # fusion_mlp[2] backward (no-op when off)
-    # fusion_mlp.0: dW3[512,768] = dhid^T gated ; db3 ; dgated[B,768] = dhid W3
-    T.sgemm(dhid, 1, 512, fo["gated"], 768, 1, g("fusion_mlp.0.weight"), 512, 768, B)
-    T.colsum(dhid, g("fusion_mlp.0.bias"))
     dgated = torch.empty((B, 768), device=dev, dtype=torch.float32)
-    T.sgemm(dhid, 512, 1, f("fusion_mlp.0.weight"), 768, 1, dgated, B, 768, 512)
+    T.sgemm(dhid, 512, 1, f("fusion_mlp.0.weight"), 768, 1, dgated, B, 768, 512)   # dgated[B,768] = dhid W3
     dproj = T.fusion_bwd_gate(dgated, fo["proj"], f("sig_weights"), w_mod, lambda_l1, g("sig_weights"),
                               w_mod_dev=w_mod_dev)
     demb = []
-    for m, pn in enumerate(_PROJ):
+    for m, pn in enumerate(_PROJ[:2]):                                          # the text embedding is an input
         dpm = dproj[:, 256 * m:256 * (m + 1)]                                   # [B,256] view, row stride 768
-        # dWp[256,768] = dpm^T emb ; dbp = colsum(dpm) ; demb = dpm Wp
-        T.sgemm(dpm, 1, 768, embs[m], 768, 1, g(pn + "weight"), 256, 768, B)
-        T.colsum(dpm, g(pn + "bias"))
-        if m < 2:                                                               # the text embedding is an input
-            de = torch.empty((B, 768), device=dev, dtype=torch.float32)
-            T.sgemm(dpm, 768, 1, f(pn + "weight"), 768, 1, de, B, 768, 256)
-            demb.append(de)
+        de = torch.empty((B, 768), device=dev, dtype=torch.float32)
+        T.sgemm(dpm, 768, 1, f(pn + "weight"), 768, 1, de, B, 768, 256)         # demb = dpm Wp
+        demb.append(de)
+
+    def param_grads():
+        # fusion_mlp.3: dW4[3,512] = dlogits^T hid ; db4 = colsum(dlogits)
+        T.sgemm(dlogits, 1, 3, hid, 512, 1, g("fusion_mlp.3.weight"), 3, 512, B)
+        T.colsum(dlogits, g("fusion_mlp.3.bias"))
+        # fusion_mlp.0: dW3[512,768] = dhid^T gated ; db3
+        T.sgemm(dhid, 1, 512, fo["gated"], 768, 1, g("fusion_mlp.0.weight"), 512, 768, B)
+        T.colsum(dhid, g("fusion_mlp.0.bias"))
+        for m, pn in enumerate(_PROJ):
+            dpm = dproj[:, 256 * m:256 * (m + 1)]
+            # dWp[256,768] = dpm^T emb ; dbp = colsum(dpm)
+            T.sgemm(dpm, 1, 768, embs[m], 768, 1, g(pn + "weight"), 256, 768, B)
+            T.colsum(dpm, g(pn + "bias"))
+
+    branch.run(param_grads, dlogits, hid, dhid, dproj, fo, embs)
     return demb
 
 
@@ -972,7 +1024,9 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
     # fusion head, lives in the 'rest' region and travels with the last demographic bucket)
     red = _GradReducer(st, group)
     main.wait_stream(post)                              # gradient buffer zeroed, transposed shadows current
-    ddemo, dlab = _fusion_backward(st, fo, (demo, labe, text), dlogits, w_mod, lambda_l1, d_fus, w_mod_dev=st.w_mod_dev)
+    head_branch = _WgradBranch(st)
+    ddemo, dlab = _fusion_backward(st, fo, (demo, labe, text), dlogits, w_mod, lambda_l1, d_fus, w_mod_dev=st.w_mod_dev,
+                                   branch=head_branch)
     if debug is not None:
         debug.update(demo=demo, lab=labe, dlogits=dlogits, ddemo=ddemo, dlab=dlab, logits=fo["logits"],
                      proj=fo["proj"], pre_relu=fo["pre_relu"])
@@ -989,6 +1043,7 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
     else:
         _demo_backward(st, model, sv_d, ddemo, red, ds)
         _lab_backward(st, model, sv_l, dlab, ds, reducer=red)
+    head_branch.join()                                  # the head's parameter gradients live in the tail bucket
     red.ready("tail")
     red.finish()
     # tensors that crossed streams (allocated on one, read on the other) stay referenced until both branches have been

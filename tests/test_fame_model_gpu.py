@@ -261,3 +261,25 @@ def test_rank_metrics_ties_and_large_n():
     assert res_flip[0][0] == pytest.approx(1 - res[0][0], abs=1e-12)
     res_c = M.rank_metrics(torch.zeros(1000, 3).cuda(), torch.from_numpy(y[:1000]).cuda())
     assert res_c[0][0] == 0.5
+
+
+@pytest.mark.parametrize("N", [1, 2, 777, 4096, 4097, 46000, 100003])
+def test_rank_counts_sorted_equals_brute_force(N):
+    """fame_rank_counts over the full range (key sort + tie-run scan, O(N log N)) produces the integers of the exact
+    O(N^2) compare (run here as two sub-ranges): auroc2, positives / negatives bit-exact, the float64 AP sum to rounding."""
+    from fairmultimodal_b200 import ops
+    rng = np.random.default_rng(N)
+    y = torch.from_numpy((rng.random(N) < 0.3).astype(np.uint8)).cuda()
+    s = rng.random(N).astype(np.float32)
+    s = np.round(s * 500) / 500 if N % 2 else s                 # odd sizes: heavy ties (501 distinct scores, incl. 0 and 1)
+    s = torch.from_numpy(s.astype(np.float32)).cuda()
+    full = ops.rank_counts(s, y)
+    half = ops.rank_counts(s, y, 0, N // 2)
+    half = ops.rank_counts(s, y, N // 2, N, acc=half)
+    torch.cuda.synchronize()
+    if N == 1:                                                   # [0, 0) is empty and [0, 1) is the full range itself
+        assert int(full["pn"].sum()) == 1
+        return
+    assert torch.equal(full["auroc2"], half["auroc2"]) and torch.equal(full["pn"], half["pn"])
+    assert abs(full["ap"].item() - half["ap"].item()) <= 1e-12 * max(1.0, abs(half["ap"].item()))
+
