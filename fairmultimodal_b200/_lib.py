@@ -196,6 +196,7 @@ FLAT_OPS = {
     "fame_fusion_bwd_gate": [_P, _P, _P, _F, _F, _F, _F, _P, _P, _I32, _P],
     "fame_grad_sumsq": [_P, _I64, _P],
     "fame_clip_adamw": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _I32, _P, _P, _P, _P],
+    "fame_decay_only": [_P, _I64, _F, _F, _P, _P],
     "fame_cast_bf16": [_P, _P, _I64],
     "fame_transpose_bf16_table": [_P, _I32, _I32],
     "fame_wgrad_small": [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P],

@@ -379,16 +379,22 @@ demo_add_bwd_kernel(const float* __restrict__ dout, const long long* __restrict_
 // C[m, n] = alpha * sum_k A(m, k) B(k, n) (+ C if accumulate), arbitrary element strides: A(m,k) = a[m*sam + k*sak],
 // B(k,n) = b[k*sbk + n*sbn].  32 x 32 output tile per block, 16-deep k slices through shared memory.  The fusion head's
 // matrices are at most 768 wide and the batch is 32 per GPU: latency matters here, not FLOPs.
+// 128-deep k slices: a slice is 2 x 16 independent loads per thread, so the whole product costs K / 128 global-memory
+// round trips (4 at K = 512) instead of K / 16 -- with 16-deep slices each call took 19-28 us, all of it load latency,
+// and four of them sit on the chain between the towers' forward and backward passes.
+constexpr int kSgKT = 128;
+
 __global__ void __launch_bounds__(256)
 sgemm_small_kernel(const float* __restrict__ a, long long sam, long long sak, const float* __restrict__ b, long long sbk,
                    long long sbn, float* __restrict__ c, long long ldc, int M, int N, int K, float alpha, int accumulate) {
-    __shared__ float As[16][33], Bs[16][33];
+    __shared__ float As[kSgKT][33], Bs[kSgKT][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads; each owns 4 rows x 1 column
     const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        for (int i = threadIdx.x; i < 512; i += 256) {
-            const int kk = i & 15, mm = i >> 4;
+    for (int k0 = 0; k0 < K; k0 += kSgKT) {
+#pragma unroll 4
+        for (int i = threadIdx.x; i < kSgKT * 32; i += 256) {
+            const int kk = i % kSgKT, mm = i / kSgKT;
             const int m = m0 + mm, k = k0 + kk;
             As[kk][mm] = (m < M && k < K) ? a[m * sam + k * sak] : 0.f;
             const int nn = i & 31, kb = i >> 5;
@@ -396,8 +402,8 @@ sgemm_small_kernel(const float* __restrict__ a, long long sam, long long sak, co
             Bs[kb][nn] = (n < N && k2 < K) ? b[k2 * sbk + n * sbn] : 0.f;
         }
         __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
+#pragma unroll 16
+        for (int kk = 0; kk < kSgKT; ++kk) {
             const float bv = Bs[kk][tx];
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[r] = fmaf(As[kk][ty * 4 + r], bv, acc[r]);
@@ -543,6 +549,38 @@ clip_adamw_kernel(const AdamWParams a) {
         p -= step * m / (sqrtf(v) * rbc2 + a.eps);
         a.p[i] = p; a.m[i] = m; a.v[i] = v;
         if (a.p_bf16 != nullptr) a.p_bf16[i] = __float2bfloat16(p);
+    }
+}
+
+// AdamW for a region whose gradient AND Adam moments are identically zero (the query / key projection weights of the
+// demographic BERT: one key per sequence, so the softmax is 1 and d loss / d (Q, K) = 0 exactly; 14.2 M of the 97.9 M
+// parameters).  With g = m = v = 0 the update term is 0 / (0 + eps) = 0 and the step reduces to the decoupled weight
+// decay p <- p (1 - lr wd): 8 bytes per parameter instead of 30 (+ 2 for the bf16 shadow).
+__global__ void __launch_bounds__(256)
+decay_only_kernel(float* __restrict__ p, long long n, float lr, float wd, const float* __restrict__ hyper_dev,
+                  __nv_bfloat16* __restrict__ p_bf16) {
+    if (hyper_dev != nullptr) {
+        lr = hyper_dev[0];
+        wd = hyper_dev[1];
+    }
+    const float decay = 1.0f - lr * wd;
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<float4*>(p)[i];
+        v.x *= decay; v.y *= decay; v.z *= decay; v.w *= decay;
+        reinterpret_cast<float4*>(p)[i] = v;
+        if (p_bf16 != nullptr) {
+            uint2 o;
+            o.x = pack2(v.x, v.y);
+            o.y = pack2(v.z, v.w);
+            reinterpret_cast<uint2*>(p_bf16)[i] = o;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const long long i = (n4 << 2) + threadIdx.x;
+        const float v = p[i] * decay;
+        p[i] = v;
+        if (p_bf16 != nullptr) p_bf16[i] = __float2bfloat16(v);
     }
 }
 

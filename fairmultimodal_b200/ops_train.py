@@ -227,6 +227,11 @@ def clip_adamw(p, g, m, v, sumsq, max_norm, lr, beta1, beta2, eps, weight_decay,
           _p(grad_norm_out), _p(step_dev), _p(hyper_dev), _p(p_bf16))
 
 
+def decay_only(p, lr, weight_decay, hyper_dev=None, p_bf16=None):
+    """AdamW step of a range whose gradient and moments are identically zero: p <- p (1 - lr wd)."""
+    _flat("fame_decay_only", p.data_ptr(), p.numel(), float(lr), float(weight_decay), _p(hyper_dev), _p(p_bf16))
+
+
 def transpose_bf16_table(table, n_entries, total_tiles):
     _flat("fame_transpose_bf16_table", table.data_ptr(), n_entries, total_tiles)
 

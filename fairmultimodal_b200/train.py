@@ -437,6 +437,9 @@ class FlatTrainState:
         self.v.copy_(sd["v"])
         self.step = int(sd["step"])
         self.step_dev.fill_(int(sd["step"]))
+        qk = self.grad_buckets().get("qk") if self.fame_layout else None
+        if qk is not None:      # moments of the zero-gradient region loaded from elsewhere: only then run the full AdamW on it
+            self.qk_moments_zero = not bool(self.m[qk[0]:qk[1]].any().item() or self.v[qk[0]:qk[1]].any().item())
 
     def clip_and_step(self, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0):
         """clip_grad_norm_(max_norm) + AdamW on the flat buffers (graph-capturable: lr / weight decay / step count are
@@ -459,13 +462,25 @@ class FlatTrainState:
         else:
             ranges = [self.my_range(k, plan) for k in self.grad_buckets()]
             self.masters_stale = True
+        # the 'qk' bucket (query / key weights of the length-1 demographic BERT) has gradient exactly 0 in every step, so
+        # its Adam moments stay 0 and its AdamW step is the weight decay alone (fame_decay_only: 10 instead of 32 bytes
+        # per parameter for 14.2 M of the 97.9 M parameters) -- unless moments were loaded from elsewhere (qk_moments_zero)
+        qk = self.grad_buckets().get("qk") if (self.fame_layout and getattr(self, "qk_moments_zero", True)) else None
         for a, b in ranges:
+            if qk is not None and a < qk[1] and b > qk[0]:
+                lo, hi = max(a, qk[0]), min(b, qk[1])
+                if a < lo:
+                    self._adamw(a, lo, max_norm, lr, betas, eps, weight_decay)
+                T.decay_only(self.p[lo:hi], lr, weight_decay, hyper_dev=self.hyper_dev, p_bf16=self.pb[lo:hi])
+                a = hi
             if b > a:
-                T.clip_adamw(self.p[a:b], self.g[a:b], self.m[a:b], self.v[a:b], self.sumsq, max_norm, lr, betas[0],
-                             betas[1], eps, weight_decay, 0, self.grad_norm, step_dev=self.step_dev,
-                             hyper_dev=self.hyper_dev, p_bf16=self.pb[a:b])
+                self._adamw(a, b, max_norm, lr, betas, eps, weight_decay)
         # the transposed shadows are refreshed by the next forward_backward (beside its forward pass, not here)
         self.invalidate_caches()
+
+    def _adamw(self, a, b, max_norm, lr, betas, eps, weight_decay):
+        T.clip_adamw(self.p[a:b], self.g[a:b], self.m[a:b], self.v[a:b], self.sumsq, max_norm, lr, betas[0], betas[1], eps,
+                     weight_decay, 0, self.grad_norm, step_dev=self.step_dev, hyper_dev=self.hyper_dev, p_bf16=self.pb[a:b])
 
     def invalidate_caches(self):
         """The kernels update the flat buffer behind torch's back (no version bump): drop the inference-path
@@ -930,11 +945,14 @@ def _lab_budget(group=None):
 
 def begin_step(st, group=None):
     """Start of a training step, off the critical path on the third stream while the forward runs: zero the gradient
-    buffer (53 us) and refresh the transposed bf16 shadows the demographic backward reads (77 us); the backward waits
+    buffer (55 us) and refresh the transposed bf16 shadows the demographic backward reads (85 us); the backward waits
     for this stream.  With a sharded optimizer the previous step's AdamW refreshed only this rank's 1/N of the large
     matrices' bf16 shadows: the rest is all-gathered now, on NCCL's stream, bucket by bucket in the order the forward
     consumes them (lab tower first: it is the critical path).  Returns {bucket: work}; a tower waits for its own
-    buckets only (work.wait() on the stream that runs it)."""
+    buckets only (work.wait() on the stream that runs it).
+    (Tried and measured no better, r02 device timelines: the refresh under the fusion head instead of beside the forward
+    -- the head's short kernels then queue behind its 20 k CTAs; a grid-stride refresh with two CTAs per SM -- its
+    long-lived CTAs hold shared memory the persistent tensor-core kernels need, whichever phase it runs in.)"""
     post = st.post_stream()
     post.wait_stream(torch.cuda.current_stream())
     plan = st.shard_plan(group)
@@ -959,8 +977,8 @@ def forward_backward(model, batch, pos_weight, lambda_edd, lambda_l1, w_mod, gro
     st = get_state(model)
     st.set_w_mod(w_mod)
     (ids, mask, age, gender, eth, ins, lab, text, labels) = batch
-    # off the critical path, on the third stream while the forward runs: zero the gradient buffer (53 us), refresh the
-    # transposed bf16 shadows the demographic backward reads (77 us); the backward waits for this stream below
+    # off the critical path, on the third stream while the forward runs: zero the gradient buffer, refresh the transposed
+    # bf16 shadows the demographic backward reads; the backward waits for this stream below
     post = st.post_stream()
     gathers = begin_step(st, group)
     demo_gathers = [w for k, w in gathers.items() if isinstance(k, tuple) and k[0] == "demo"]

@@ -473,6 +473,12 @@ int fame_grad_sumsq(const float* g, int64_t n, double* out, fame_stream_t stream
 int fame_clip_adamw(float* p, const float* g, float* m, float* v, int64_t n, const double* sumsq, float max_norm, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int32_t step, float* grad_norm_out,
                     const int32_t* step_dev, const float* hyper_dev, void* p_bf16, fame_stream_t stream);
+/* fame_decay_only: the AdamW step of a parameter range whose gradient and Adam moments are identically zero (the
+ * query / key projection weights of the length-1 demographic BERT, 10_FAME.py:199): p <- p (1 - lr wd),
+ * bf16 shadow refreshed.  Equal to fame_clip_adamw on that range (update term 0 / (0 + eps)), at 10 instead of 32 bytes
+ * per parameter.  hyper_dev {lr, weight_decay} overrides the scalars when not NULL. */
+int fame_decay_only(float* p, int64_t n, float lr, float weight_decay, const float* hyper_dev, void* p_bf16,
+                    fame_stream_t stream);
 /* step_dev / hyper_dev = {lr, weight_decay} (device, may be NULL) override the by-value arguments at run time so that a
  * captured CUDA graph follows the step count and learning-rate schedule; p_bf16 (may be NULL) receives a bf16 copy of
  * the updated parameters for the tensor-core GEMMs. */

@@ -117,6 +117,13 @@ def _adamw_stub(p, g, m, v, sumsq, max_norm, lr, b1, b2, eps, wd, step, grad_nor
         grad_norm_out.fill_(norm)
 
 
+def _decay_stub(p, lr, wd, hyper_dev=None, p_bf16=None):
+    """CPU stand-in for fame_decay_only (the AdamW step of the zero-gradient query / key region)."""
+    p.mul_(1 - lr * wd)
+    if p_bf16 is not None:
+        p_bf16.copy_(p)
+
+
 class _NoStream:
     def wait_stream(self, s):
         pass
@@ -136,6 +143,7 @@ def _sharded_worker(rank, world, port, ret):
         ops_train.transpose_bf16_table = lambda *a, **k: None
         ops_train.grad_sumsq = lambda g, out: out.add_((g.double() ** 2).sum())
         ops_train.clip_adamw = _adamw_stub
+        ops_train.decay_only = _decay_stub
         train.torch.cuda.stream = lambda s: contextlib.nullcontext()
         train.torch.cuda.current_stream = lambda *a: _NoStream()
         train.torch.cuda.is_current_stream_capturing = lambda: False
