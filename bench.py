@@ -334,10 +334,12 @@ def _kernel_table(trace, steps):
 
 
 def _traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of the same command
+    (profiles/roofline_traffic.json, written by scripts/summarize_profiles.py; keys '<workload>:<kernel>')."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(path):
         t = json.load(open(path))
-        return t.get(kernel), t.get("_source")
+        return t.get(kernel), t.get("_source_" + kernel)
     return None, None
 
 

@@ -178,7 +178,7 @@ _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 FLAT_OPS = {
     "fame_mask_kv_len": [_P, _I32, _I32, _P],
     "fame_attn_cls": [_P, _I64, _P, _I64, _I32, _I32, _P, _P, _I64, _I32, _I32, _I32, _I32, _F],
-    "fame_layernorm_bwd": [_P, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P],
+    "fame_layernorm_bwd": [_P, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P],
     "fame_dropout_apply": [_P, _I32, _I64, _I32, _I32, _P],
     "fame_focal_loss_fwd_bwd": [_P, _P, _P, _F, _F, _I32, _P, _P, _P],
     "fame_relu_fwd": [_P, _I64],

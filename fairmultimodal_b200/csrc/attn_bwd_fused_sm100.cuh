@@ -38,6 +38,16 @@
 
 namespace fame {
 
+// measurement only (FAME_ATTN_DEBUG & 16): CTA 0 records (event, clock64) pairs of its MMA issuer and of softmax warp 0
+__device__ long long g_af_trace[2][4096];
+__device__ __forceinline__ void af_trace(int who, int& n, int ev) {
+    if (n < 2047) {
+        g_af_trace[who][2 * n] = ev;
+        g_af_trace[who][2 * n + 1] = clock64();
+        ++n;
+    }
+}
+
 constexpr int kAfThreads = 576;          // 16 softmax-backward warps + TMA producer + MMA issuer
 
 template <int D>
@@ -61,6 +71,8 @@ struct AfParams {
     int q_col0, k_col0, v_col0;
     float scale, scale_log2e;
     DropCfg drop;              // dropout of the attention probabilities in the forward (kDrop instantiations only)
+    int debug;                 // measurement switches (FAME_ATTN_DEBUG, results are then WRONG): 1 skip the exponential / FMA
+                               // math, 2 also skip the TMEM score loads, 4 skip the accumulating MMAs, 8 stream half the bytes
 };
 
 // kDrop: the forward dropped entries of P (mask m, scale c = 1 / (1 - p)):  O = (m c P) V.  Then
@@ -153,11 +165,13 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                 }
                 for (int hb = 0; hb < nhb; ++hb) {
                     mbar_wait(&b_empty[st], bph ^ 1);
-                    mbar_arrive_expect_tx(&b_full[st], Cfg::kStageBytes);
+                    const int nbx = (p.debug & 8) ? 1 : NB;      // measurement: half of the streamed bytes
+                    mbar_arrive_expect_tx(&b_full[st], 2 * nbx * Cfg::kHalfBoxBytes);
                     uint8_t* b1 = smem_b + st * Cfg::kStageBytes;
                     uint8_t* b2 = b1 + Cfg::kStreamBytes;
 #pragma unroll
                     for (int x = 0; x < NB; ++x) {
+                        if (x >= nbx) break;
                         tma_load_2d(b1 + x * Cfg::kHalfBoxBytes, &tmap_qkv64, &b_full[st], b1_col0 + h * D + x * 64,
                                     row0 + hb * 64, kEvictLast);
                         if (kKV)
@@ -180,6 +194,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
             // set), and the single issuing thread, not the tensor pipe, paced the kernel (ncu r02: 3 300 clk per half
             // block, tensor pipe 24 % active).
             const bool leader = elect_one();
+            const bool tr = (p.debug & 16) && blockIdx.x == 0 && leader;
+            int tn = 0;
             constexpr uint32_t idesc_sc = make_idesc_bf16(128, 64, 0, 0);     // scores: [128 stationary rows] x [64 streamed rows]
             constexpr uint32_t idesc_ac = make_idesc_bf16(128, D, 0, 1);      // accumulators: A from TMEM, B MN-major
             const uint32_t a1_addr = smem_u32(smem_a1), a2_addr = smem_u32(smem_a2);
@@ -191,8 +207,10 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                     mbar_wait(a_full, n_aph);
                     n_aph ^= 1;
                 }
+                if (tr) af_trace(0, tn, 100 + (n_hb == 0 ? 50 : 0));      // before the waits of a score pair
                 mbar_wait(&b_full[n_st], n_bph);
                 tc_fence_after();
+                if (tr) af_trace(0, tn, 101);                               // operands ready, issuing
                 const uint32_t b1_addr = smem_u32(smem_b + n_st * Cfg::kStageBytes);
                 const uint32_t b2_addr = b1_addr + Cfg::kStreamBytes;
                 const uint32_t col = tmem_base + (n_g & 1) * 128;
@@ -230,7 +248,9 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
             for (int item = blockIdx.x; item < num_items; item += gridDim.x, first_item = false) {
                 for (int hb = 0; hb < nhb; ++hb, ++g) {
                     const int s = g & 1;
+                    if (tr) af_trace(0, tn, 200);                           // waiting for the stage's dS
                     mbar_wait(&ds_full[s], (g >> 1) & 1);
+                    if (tr) af_trace(0, tn, 201);
                     if (hb == 0 && !first_item) {          // the previous item's accumulators have been read
                         mbar_wait(acc_empty, eph);
                         eph ^= 1;
@@ -239,7 +259,11 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                     const uint32_t b1_addr = smem_u32(smem_b + c_st * Cfg::kStageBytes);
                     const uint32_t b2_addr = b1_addr + Cfg::kStreamBytes;
                     const uint32_t col = tmem_base + s * 128;
-                    if (leader) {
+                    if (leader && (p.debug & 4)) {
+                        // measurement only: free the stage and the streamed tiles without the accumulating products
+                        umma_commit(&b_empty[c_st]);
+                        if (hb == nhb - 1) umma_commit(acc_full);
+                    } else if (leader) {
                         if (kKV) {
                             // dV_j += P^T . dO_ih ;  dK_j += dS^T . Q_ih   (bf16 P^T at cols [0,16) u [32,48) of the stage, dS^T
                             // at [64,80) u [96,112): each softmax thread writes over columns it has read itself)
@@ -289,6 +313,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
         const float drop_inv = kDrop ? drop_inv_keep(p.drop.thresh16) : 1.0f;
         const uint32_t thr = p.drop.thresh16;
         int g0 = 0, nproc = 0;        // half blocks of this CTA before the current item; half blocks this warpgroup has done
+        int tns = 0;
         uint32_t fph = 0, aph = 0;
         for (int item = blockIdx.x; item < num_items; item += gridDim.x, g0 += nhb) {
             const int rt = item % rtiles, bh = item / rtiles;
@@ -336,16 +361,36 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                     prefetch_cols(hb + 2);
                 }
                 ++nproc;
+                const bool trs = (p.debug & 16) && blockIdx.x == 0 && warp == 0 && lane == 0;
+                if (trs) af_trace(1, tns, 300);
                 mbar_wait(&sd_full[w], fph);
                 fph ^= 1;
                 tc_fence_after();
+                if (trs) af_trace(1, tns, 301);
 #pragma unroll 1
                 for (int c = 0; c < 2; ++c) {
                     uint32_t s[16], dp[16];
+                    uint32_t pk[8], dk[8];
+                    if (p.debug & 2) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) pk[i] = dk[i] = 0u;
+                        if (kKV) tmem_st_x8(st_base + c * 8, pk);
+                        tmem_st_x8(st_base + 64 + c * 8, dk);
+                        continue;
+                    }
                     tmem_ld_x16(st_base + c * 16, s);
                     tmem_ld_x16(st_base + 64 + c * 16, dp);
                     tmem_ld_wait();
-                    uint32_t pk[8], dk[8];
+                    if (p.debug & 1) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            pk[i] = s[2 * i] ^ s[2 * i + 1];
+                            dk[i] = dp[2 * i] ^ dp[2 * i + 1];
+                        }
+                        if (kKV) tmem_st_x8(st_base + c * 8, pk);
+                        tmem_st_x8(st_base + 64 + c * 8, dk);
+                        continue;
+                    }
 #pragma unroll
                     for (int i = 0; i < 16; i += 2) {
                         const int cc = hcol * 32 + c * 16 + i;   // column inside the half block
@@ -394,11 +439,14 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ds_full[w]);
+                if (trs) af_trace(1, tns, 302);
             }
             // ---- epilogue: accumulators -> bf16 -> the packed gradient tensor
+            if ((p.debug & 16) && blockIdx.x == 0 && warp == 0 && lane == 0) af_trace(1, tns, 400);
             mbar_wait(acc_full, aph);
             aph ^= 1;
             tc_fence_after();
+            if ((p.debug & 16) && blockIdx.x == 0 && warp == 0 && lane == 0) af_trace(1, tns, 401);
             __nv_bfloat16* dst_row = p.dqkv + (long long)(b * S + srow) * p.ld + h * D;
             if (kKV) {
                 // group 0: dV (accumulator 0), group 1: dK (accumulator 1); each warp of a quadrant pair stores D / 2 columns
@@ -446,6 +494,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty);
+            if ((p.debug & 16) && blockIdx.x == 0 && warp == 0 && lane == 0) af_trace(1, tns, 402);
         }
     }
 

@@ -44,7 +44,10 @@ __global__ void __launch_bounds__(kLnWarpsPerBlock * 32, CH <= 3 ? 2 : 1)
 layernorm_bwd_kernel(const void* __restrict__ x, const void* __restrict__ dy, const float2* __restrict__ stats,
                      const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dx_f32,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int cols,
-                     __nv_bfloat16* __restrict__ dx_drop, const DropCfg drop) {
+                     __nv_bfloat16* __restrict__ dx_drop, const DropCfg drop,
+                     const __nv_bfloat16* __restrict__ residual = nullptr) {
+    // residual (bf16, optional): the LayerNorm input was x + residual, added inside the forward LayerNorm kernel (the
+    // attention-output projection of the lab tower: its K = 768 GEMM is shorter than a residual-adding epilogue)
     // dx_drop (optional): dx with the dropout mask of the layer that produced the residual branch re-applied
     // (t = residual + dropout(linear(.)): the residual path takes dx, the linear layer's backward takes dx_drop)
     __shared__ float red[2][kLnWarpsPerBlock][1024 / 4];  // staged in 4 passes of 256 columns
@@ -69,6 +72,12 @@ layernorm_bwd_kernel(const void* __restrict__ x, const void* __restrict__ dy, co
                 float xv[8], dv[8];
                 load8<kXF32>(x, (long long)row * cols + 8 * ch, xv);
                 load8<kDyF32>(dy, (long long)row * cols + 8 * ch, dv);
+                if (residual != nullptr) {
+                    float rv[8];
+                    load8<false>(residual, (long long)row * cols + 8 * ch, rv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) xv[j] += rv[j];
+                }
                 const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * ch);
                 const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * ch + 1);
                 const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};

@@ -94,16 +94,18 @@ def layernorm_bwd(x, dy, stats, gamma, dgamma, dbeta, want_bf16=True, want_f32=F
     return layernorm_bwd_drop(x, dy, stats, gamma, dgamma, dbeta, want_bf16, want_f32, None)[:2]
 
 
-def layernorm_bwd_drop(x, dy, stats, gamma, dgamma, dbeta, want_bf16=True, want_f32=False, drop=None):
+def layernorm_bwd_drop(x, dy, stats, gamma, dgamma, dbeta, want_bf16=True, want_f32=False, drop=None, residual=None):
     """Returns (dx bf16 | None, dx f32 | None, dx_drop bf16 | None): with `drop` (a _lib.DropoutCfg) dx_drop is dx
-    with that dropout mask re-applied -- the gradient of the layer under the dropout."""
+    with that dropout mask re-applied -- the gradient of the layer under the dropout.  residual (bf16, optional): the
+    forward LayerNorm ran on x + residual (ops.layernorm(..., residual=))."""
     rows, cols = x.shape
     dxb = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     dxf = torch.empty((rows, cols), device=x.device, dtype=torch.float32) if want_f32 else None
     on = drop is not None and drop.thresh16 > 0
     dxd = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16) if on else None
     _flat("fame_layernorm_bwd", x.data_ptr(), _dt(x), dy.data_ptr(), _dt(dy), stats.data_ptr(), gamma.data_ptr(),
-          _p(dxb), _p(dxf), _p(dgamma), _p(dbeta), rows, cols, _p(dxd), ctypes.addressof(drop) if on else None)
+          _p(dxb), _p(dxf), _p(dgamma), _p(dbeta), rows, cols, _p(dxd), ctypes.addressof(drop) if on else None,
+          _p(residual))
     return dxb, dxf, dxd
 
 

@@ -800,10 +800,13 @@ def _lab_forward(st, model, lab, ds=None, lab_module=None, pre="behrt_lab."):
         lse = torch.empty((B, nh, L), device=dev, dtype=torch.float32)       # saved for the attention backward
         ctx = ops.attn_fwd(qkv, B, L, nh, H // nh, lse=lse, drop=site("attn", pr["attn"]))
         # x = norm1(x + dropout1(out_proj(ctx)));  x = norm2(x + dropout2(linear2(dropout(relu(linear1(x))))))
-        t1 = ops.gemm_bias_act(ctx, st.w(p + "self_attn.out_proj.weight"), st.f(p + "self_attn.out_proj.bias"), residual=x,
+        # the residual of this K = 768 projection is added by the LayerNorm kernel (and again by its backward), not by
+        # the GEMM epilogue, whose scattered residual loads made the launch 3x longer than its main loop (ncu r02:
+        # 57 us, tensor pipe 25 % active, against 19 us of math)
+        t1 = ops.gemm_bias_act(ctx, st.w(p + "self_attn.out_proj.weight"), st.f(p + "self_attn.out_proj.bias"),
                                drop=site("d1", pr["d1"]))
         st1 = torch.empty((B * L, 2), device=dev, dtype=torch.float32)
-        x1 = ops.layernorm(t1, st.f(p + "norm1.weight"), st.f(p + "norm1.bias"), layer.norm1.eps, stats=st1)
+        x1 = ops.layernorm(t1, st.f(p + "norm1.weight"), st.f(p + "norm1.bias"), layer.norm1.eps, stats=st1, residual=x)
         h = ops.gemm_bias_act(x1, st.w(p + "linear1.weight"), st.f(p + "linear1.bias"), act=ops.ACT_RELU,
                               drop=site("act", pr["act"]))
         t2 = ops.gemm_bias_act(h, st.w(p + "linear2.weight"), st.f(p + "linear2.bias"), residual=x1,
@@ -870,7 +873,7 @@ def _lab_backward(st, model, saved, dlab, ds=None, lab_module=None, pre="behrt_l
         _lin_bwd(st, p + "linear1.weight", p + "linear1.bias", dh, s["x1"])
         dx1 = T.linear_dgrad(dh, st.w(p + "linear1.weight"), aux=dt2, aux_mode=T.AUX_ADD_BF16)
         dt1, _, dt1m = T.layernorm_bwd_drop(s["t1"], dx1, s["st1"], st.f(p + "norm1.weight"), st.gr(p + "norm1.weight"),
-                                            st.gr(p + "norm1.bias"), drop=site("d1", pr["d1"]))
+                                            st.gr(p + "norm1.bias"), drop=site("d1", pr["d1"]), residual=s["x"])
         dt1m = dt1 if dt1m is None else dt1m
         _lin_bwd(st, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", dt1m, s["ctx"])
         dctx = T.linear_dgrad(dt1m, st.w(p + "self_attn.out_proj.weight"))

@@ -432,7 +432,8 @@ int fame_sigmoid_probs(const fame_sigmoid_probs_args* a, void* workspace, size_t
  * dropout. */
 int fame_layernorm_bwd(const void* x, int32_t x_dtype, const void* dy, int32_t dy_dtype, const float* stats,
                        const float* gamma, void* dx_bf16, float* dx_f32, float* dgamma, float* dbeta, int32_t rows,
-                       int32_t cols, void* dx_drop, const fame_dropout_cfg* drop, fame_stream_t stream);
+                       int32_t cols, void* dx_drop, const fame_dropout_cfg* drop,
+                       const void* residual /* bf16 [rows, cols] or NULL: the LayerNorm input was x + residual */, fame_stream_t stream);
 /* In-place dropout of x [rows, cols] (bf16 or f32, row stride ld): the sites with no producing GEMM epilogue
  * (BertEmbeddings dropout HF:111, fusion_mlp[2] 10_FAME.py:255) and their gradients. */
 int fame_dropout_apply(void* x, int32_t x_dtype, int64_t ld, int32_t rows, int32_t cols, const fame_dropout_cfg* drop,

@@ -80,25 +80,34 @@ def full_summary(rep, dst):
 
 if __name__ == "__main__":
     tag = sys.argv[1]
-    cmd = "python bench.py --steps 2 --warmup 3 --skip-train --cpu-chunks 0"
-    p = os.path.join(OUT, f"launches_{tag}.csv")
+    # ---- round-2 layout (scripts/gpu_final.sh): train-step and note-encoder commands profiled separately
+    tcmd = "FAME_NO_GRAPH=1 python bench.py --steps 2 --warmup 3 --skip-note-encoder --skip-eager --cpu-train-steps 0"
+    ncmd = "python bench.py --config 2 --steps 2 --warmup 3 --cpu-chunks 0"
+    p = os.path.join(OUT, f"launches_note_{tag}.csv")
+    if not os.path.exists(p):
+        p = os.path.join(OUT, f"launches_{tag}.csv")
     if os.path.exists(p):
         launch_summary(p, os.path.join(PROF, f"{tag}_launches_summary_note_encoder.csv"),
-                       f"ncu --metrics gpu__time_duration.sum --clock-control none -c 600: {cmd}")
+                       f"ncu --metrics gpu__time_duration.sum --clock-control none -c 1000: {ncmd}  (all launches of the run; "
+                       "cold-cache serialised launches: shares, not absolute times)")
     p = os.path.join(OUT, f"launches_train_{tag}.csv")
     if os.path.exists(p):
         launch_summary(p, os.path.join(PROF, f"{tag}_launches_summary_train_step.csv"),
-                       "ncu --metrics gpu__time_duration.sum --clock-control none -c 3000: FAME_NO_GRAPH=1 python "
-                       "scripts/bench_train.py 32 542 2  (last step only; cold-cache serialised launches)", "clip_adamw")
+                       f"ncu --metrics gpu__time_duration.sum --clock-control none -c 6000: {tcmd}  (last step only; "
+                       "cold-cache serialised launches: shares, not absolute times)", "clip_adamw")
     traffic_path = os.path.join(PROF, "roofline_traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
-    for kern, op in (("gemm", "fame_gemm_bias_act"), ("attn", "fame_attn_fwd"), ("ln", "fame_layernorm")):
+    jobs = (("gemm_train", "train_step:gemm_bf16_tcgen05_kernel", tcmd), ("gemm_note", "note_encoder:gemm_bf16_tcgen05_kernel", ncmd),
+            ("attn_bwd", "train_step:attn_bwd_fused_kernel", tcmd), ("attn_fwd", "note_encoder:attn_fwd_pair_kernel", ncmd),
+            ("gemm", "fame_gemm_bias_act", ncmd), ("attn", "fame_attn_fwd", ncmd), ("ln", "fame_layernorm", ncmd))
+    for kern, key, cmd in jobs:
         rep = os.path.join(OUT, f"prof_{kern}_{tag}.ncu-rep")
         if os.path.exists(rep):
             tr = full_summary(rep, os.path.join(PROF, f"{tag}_ncu_{kern}_full_summary.csv"))
             if tr:
-                traffic[op] = int(sum(tr) / len(tr))
-                traffic[f"_source_{op}"] = (f"profiles/{tag}_ncu_{kern}_full_summary.csv: dram__bytes_read.sum + "
-                                            f"dram__bytes_write.sum, mean over the {len(tr)} captured launches")
+                traffic[key] = int(sum(tr) / len(tr))
+                traffic[f"_source_{key}"] = (f"profiles/{tag}_ncu_{kern}_full_summary.csv: dram__bytes_read.sum + "
+                                             f"dram__bytes_write.sum, mean over the {len(tr)} launches captured with "
+                                             f"ncu --set full --clock-control none under: {cmd}")
     json.dump(traffic, open(traffic_path, "w"), indent=1)
     print("traffic", {k: v for k, v in traffic.items() if not k.startswith("_")})

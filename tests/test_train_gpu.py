@@ -119,6 +119,30 @@ def test_layernorm_backward():
     assert (db - br.grad).abs().max() <= 1e-4 * br.grad.abs().max()
 
 
+def test_layernorm_residual_forward_backward():
+    """LayerNorm(x + residual) with the residual added inside the kernels (the lab tower's attention-output block):
+    forward and backward against torch on the explicit sum."""
+    from fairmultimodal_b200 import ops, ops_train as T
+    torch.manual_seed(4)
+    rows = 1085
+    x = torch.randn(rows, 768, device="cuda").bfloat16()
+    r = torch.randn(rows, 768, device="cuda").bfloat16()
+    dy = torch.randn(rows, 768, device="cuda").bfloat16()
+    g, b = torch.randn(768, device="cuda"), torch.randn(768, device="cuda")
+    stats = torch.empty(rows, 2, device="cuda")
+    y = ops.layernorm(x, g, b, 1e-5, stats=stats, residual=r)
+    xr = (x.float() + r.float()).requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (768,), gr, br, 1e-5)
+    assert (y.float() - ref).abs().max() <= 2e-2 * ref.abs().max()
+    ref.backward(dy.float())
+    dg, db = torch.zeros(768, device="cuda"), torch.zeros(768, device="cuda")
+    _, dx, _ = T.layernorm_bwd_drop(x, dy, stats, g, dg, db, want_bf16=False, want_f32=True, residual=r)
+    assert (dx - xr.grad).abs().max() <= 1e-3 * xr.grad.abs().max()
+    assert (dg - gr.grad).abs().max() <= 1e-3 * gr.grad.abs().max()
+    assert (db - br.grad).abs().max() <= 1e-4 * br.grad.abs().max()
+
+
 def test_clip_adamw_matches_torch():
     from fairmultimodal_b200 import ops_train as T
     torch.manual_seed(3)
