@@ -29,7 +29,10 @@
 // P_t(j) was consumed.  A commit on s_full[t] for block j also covers P.V of block j-1 (same issuing thread), so the
 // softmax warps may rescale O_t right after that wait.
 //
-// Tried and measured slower (kept out): (1) a third, rotating score buffer with per-(tile, buffer) barriers so that a
+// Tried and measured slower (kept out): (0, r02) one MMA-issuing warp PER QUERY TILE (two independent instruction
+// streams, K / V slots and the Q pair released by two arrivals): 0.48 instead of 0.38 ms at 256 x 12 x 512 x 64 with
+// 64-key blocks, 2.48 instead of 2.39 ms at 1024 x 8 x 542 x 96 -- the ~65-130 clk a small tcgen05.mma costs is paid in
+// the tensor pipe / operand fetch, not in the issuing thread; (1) a third, rotating score buffer with per-(tile, buffer) barriers so that a
 // tile's next score block is in TMEM before its warpgroup finishes the current one (0.50 ms vs 0.41 ms at 256 x 12 x
 // 512 x 64: the extra commits and cursor arithmetic in the single MMA-issuing thread cost more than the wait saved);
 // (2) fetching the key-mask bytes one block ahead (0.45 ms: the extra live registers spill in the softmax loop).
