@@ -308,7 +308,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     // accumulator fully read: hand the TMEM buffer back to the MMA warp before the math
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
+                    // relaxed arrival: a release-scoped one made every epilogue warp wait here for its own outstanding
+                    // stores (ncu r02: MEMBAR.ALL.CTA + ERRBAR = 12 % of the FFN1 launch's samples)
+                    if (lane == 0) mbar_arrive_cluster_relaxed(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
                 }
                 if (!active) continue;
                 if (with_bias && col0 + 64 > p.N) {      // ragged last chunk: bias added under the column guard

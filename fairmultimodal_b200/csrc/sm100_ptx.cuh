@@ -131,6 +131,12 @@ __device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorM
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
+// Arrival that orders NOTHING in the memory model (no MEMBAR / ERRBAR): for barriers that only hand a TMEM buffer back
+// -- the reads of TMEM are ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync, and a release-scoped
+// arrive would additionally wait for the thread's outstanding global / shared stores to drain.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2,
                                              int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
