@@ -38,14 +38,16 @@ namespace fame {
 constexpr int kGemmBM = 128;
 constexpr int kGemmBN = 256;
 constexpr int kGemmBK = 64;
-constexpr int kGemmStages = 6;
+constexpr int kGemmStages = 5;                      // 5 x 32 KB ring + 4 x 16 KB store staging = 224 KB
 constexpr int kGemmABytes = kGemmBM * kGemmBK * 2;        // 16 KB: this CTA's 128 rows of A
 constexpr int kGemmBBytes = (kGemmBN / 2) * kGemmBK * 2;  // 16 KB: this CTA's half (128 n rows) of the pair's B tile
 constexpr int kGemmStageBytes = kGemmABytes + kGemmBBytes;
 constexpr int kGemmCBoxBytes = 128 * 64 * 2;        // 16 KB staging box per epilogue warpgroup
 constexpr int kGemmSubTile = 64 * 64 * 2;           // 8 KB: one {64 mn x 64 k} box of an MN-major operand
 constexpr int kGemmThreads = 384;
-constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + 2 * kGemmCBoxBytes + 1024 /*align slack*/ + 256;
+// two staging boxes per epilogue warpgroup (one per 64-column chunk of its half): a chunk's TMA store may still be
+// reading its box while the next chunk is written into the other one
+constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + 4 * kGemmCBoxBytes + 1024 /*align slack*/ + 256;
 
 enum { kActNone = 0, kActGelu = 1, kActRelu = 2 };
 enum { kResNone = 0, kResAddBf16 = 1, kResAddF32 = 2, kResReluMaskBf16 = 3, kResGeluBwdBf16 = 4 /* skinny only */ };
@@ -124,8 +126,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kGemmStages * kGemmABytes;
-    uint8_t* smem_c = smem + kGemmStages * kGemmStageBytes;  // 2 x 16 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * kGemmCBoxBytes);
+    uint8_t* smem_c = smem + kGemmStages * kGemmStageBytes;  // 4 x 16 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 4 * kGemmCBoxBytes);
     uint64_t* full_bar = bars;                       // [kStages]
     uint64_t* empty_bar = bars + kGemmStages;        // [kStages]
     uint64_t* tmem_full = bars + 2 * kGemmStages;    // [2]
@@ -257,8 +259,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int half = (warp - 4) >> 2;  // which 128-column half of the accumulator (= warpgroup)
         const int r_local = q * 32 + lane; // row inside the tile
         const bool wg_leader = (q == 0 && lane == 0);
-        uint8_t* cbox = smem_c + half * kGemmCBoxBytes;
-        uint8_t* crow = cbox + r_local * 128;
+        uint8_t* cbox0 = smem_c + half * 2 * kGemmCBoxBytes;       // boxes [2 half, 2 half + 1]: chunk cc uses box cc
+        const uint32_t crow_s0 = smem_u32(cbox0 + r_local * 128);  // shared-window address: st.shared, not a generic store
         const int sw = r_local & 7;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -400,8 +402,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         }
                     }
                 } else {
-                    // the previous TMA store out of this warpgroup's box must have finished reading it
-                    if (wg_leader) tma_store_wait_read();
+                    // the TMA store issued out of THIS box two chunks ago must have finished reading it (the one out of
+                    // the other box may still be in flight)
+                    uint8_t* cbox = cbox0 + cc * kGemmCBoxBytes;
+                    const uint32_t crow_s = crow_s0 + cc * kGemmCBoxBytes;
+                    if (wg_leader) tma_store_wait_read_1();
                     named_bar_sync(1 + half, 128);
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
@@ -410,7 +415,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
                         o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
                         o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
-                        *reinterpret_cast<uint4*>(crow + ((c ^ sw) << 4)) = o;  // SW128: 16-byte chunk ^= row % 8
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"      // SW128: 16-byte chunk ^= row % 8
+                                     ::"r"(crow_s + ((c ^ sw) << 4)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                     }
                     fence_proxy_async_smem();
                     named_bar_sync(1 + half, 128);
