@@ -38,7 +38,16 @@
 
 namespace fame {
 
-// measurement only (FAME_ATTN_DEBUG & 16): CTA 0 records (event, clock64) pairs of its MMA issuer and of softmax warp 0
+// Measurement switches (profiles/r02_attn_bwd_switch_experiments.log, r02_attn_bwd_event_trace_cta0.log) are compiled in
+// only with -DFAME_ATTN_INSTRUMENT: left in as run-time branches they cost the kernel 15 % (18.9 -> 22 ms per config-3
+// step).  With the macro, FAME_ATTN_DEBUG selects: 1 skip the exponential / FMA math, 2 also skip the TMEM score loads,
+// 4 skip the accumulating MMAs, 8 stream half the bytes, 16 record the event trace below (results are then wrong).
+#ifdef FAME_ATTN_INSTRUMENT
+#define AF_DBG(bit) ((p.debug & (bit)) != 0)
+#else
+#define AF_DBG(bit) (false)
+#endif
+// AF_DBG(16): CTA 0 records (event, clock64) pairs of its MMA issuer and of softmax warp 0
 __device__ long long g_af_trace[2][4096];
 __device__ __forceinline__ void af_trace(int who, int& n, int ev) {
     if (n < 2047) {
@@ -165,7 +174,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                 }
                 for (int hb = 0; hb < nhb; ++hb) {
                     mbar_wait(&b_empty[st], bph ^ 1);
-                    const int nbx = (p.debug & 8) ? 1 : NB;      // measurement: half of the streamed bytes
+                    const int nbx = AF_DBG(8) ? 1 : NB;      // measurement: half of the streamed bytes
                     mbar_arrive_expect_tx(&b_full[st], 2 * nbx * Cfg::kHalfBoxBytes);
                     uint8_t* b1 = smem_b + st * Cfg::kStageBytes;
                     uint8_t* b2 = b1 + Cfg::kStreamBytes;
@@ -194,7 +203,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
             // set), and the single issuing thread, not the tensor pipe, paced the kernel (ncu r02: 3 300 clk per half
             // block, tensor pipe 24 % active).
             const bool leader = elect_one();
-            const bool tr = (p.debug & 16) && blockIdx.x == 0 && leader;
+            const bool tr = AF_DBG(16) && blockIdx.x == 0 && leader;
             int tn = 0;
             constexpr uint32_t idesc_sc = make_idesc_bf16(128, 64, 0, 0);     // scores: [128 stationary rows] x [64 streamed rows]
             constexpr uint32_t idesc_ac = make_idesc_bf16(128, D, 0, 1);      // accumulators: A from TMEM, B MN-major
@@ -259,7 +268,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                     const uint32_t b1_addr = smem_u32(smem_b + c_st * Cfg::kStageBytes);
                     const uint32_t b2_addr = b1_addr + Cfg::kStreamBytes;
                     const uint32_t col = tmem_base + s * 128;
-                    if (leader && (p.debug & 4)) {
+                    if (leader && AF_DBG(4)) {
                         // measurement only: free the stage and the streamed tiles without the accumulating products
                         umma_commit(&b_empty[c_st]);
                         if (hb == nhb - 1) umma_commit(acc_full);
@@ -361,7 +370,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                     prefetch_cols(hb + 2);
                 }
                 ++nproc;
-                const bool trs = (p.debug & 16) && blockIdx.x == 0 && warp == 0 && lane == 0;
+                const bool trs = AF_DBG(16) && blockIdx.x == 0 && warp == 0 && lane == 0;
                 if (trs) af_trace(1, tns, 300);
                 mbar_wait(&sd_full[w], fph);
                 fph ^= 1;
@@ -371,7 +380,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                 for (int c = 0; c < 2; ++c) {
                     uint32_t s[16], dp[16];
                     uint32_t pk[8], dk[8];
-                    if (p.debug & 2) {
+                    if (AF_DBG(2)) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) pk[i] = dk[i] = 0u;
                         if (kKV) tmem_st_x8(st_base + c * 8, pk);
@@ -381,7 +390,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                     tmem_ld_x16(st_base + c * 16, s);
                     tmem_ld_x16(st_base + 64 + c * 16, dp);
                     tmem_ld_wait();
-                    if (p.debug & 1) {
+                    if (AF_DBG(1)) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             pk[i] = s[2 * i] ^ s[2 * i + 1];
@@ -442,11 +451,11 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
                 if (trs) af_trace(1, tns, 302);
             }
             // ---- epilogue: accumulators -> bf16 -> the packed gradient tensor
-            if ((p.debug & 16) && blockIdx.x == 0 && warp == 0 && lane == 0) af_trace(1, tns, 400);
+            if (AF_DBG(16) && blockIdx.x == 0 && warp == 0 && lane == 0) af_trace(1, tns, 400);
             mbar_wait(acc_full, aph);
             aph ^= 1;
             tc_fence_after();
-            if ((p.debug & 16) && blockIdx.x == 0 && warp == 0 && lane == 0) af_trace(1, tns, 401);
+            if (AF_DBG(16) && blockIdx.x == 0 && warp == 0 && lane == 0) af_trace(1, tns, 401);
             __nv_bfloat16* dst_row = p.dqkv + (long long)(b * S + srow) * p.ld + h * D;
             if (kKV) {
                 // group 0: dV (accumulator 0), group 1: dK (accumulator 1); each warp of a quadrant pair stores D / 2 columns
@@ -494,7 +503,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __g
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty);
-            if ((p.debug & 16) && blockIdx.x == 0 && warp == 0 && lane == 0) af_trace(1, tns, 402);
+            if (AF_DBG(16) && blockIdx.x == 0 && warp == 0 && lane == 0) af_trace(1, tns, 402);
         }
     }
 

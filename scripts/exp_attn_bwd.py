@@ -1,4 +1,5 @@
-"""Where does the fused attention backward spend its time?  FAME_ATTN_DEBUG switches (results are wrong, timing only):
+"""(Needs the instrumented build: FAME_NVCC_EXTRA=-DFAME_ATTN_INSTRUMENT python __graft_entry__.py --force.)
+Where does the fused attention backward spend its time?  FAME_ATTN_DEBUG switches (results are wrong, timing only):
 0 baseline, 1 no exponential / FMA math, 3 no math and no TMEM score loads, 4 no accumulating MMAs, 7 all three,
 8 half of the streamed bytes, 15 everything."""
 import os, subprocess, sys

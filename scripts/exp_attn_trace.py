@@ -1,4 +1,5 @@
-"""Event timeline (clock64) of CTA 0 of the fused attention backward: MMA issuer and softmax warp 0.  FAME_ATTN_DEBUG=16 (+7)."""
+"""(Needs the instrumented build: FAME_NVCC_EXTRA=-DFAME_ATTN_INSTRUMENT python __graft_entry__.py --force.)
+Event timeline (clock64) of CTA 0 of the fused attention backward: MMA issuer and softmax warp 0.  FAME_ATTN_DEBUG=16 (+7)."""
 import ctypes, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
