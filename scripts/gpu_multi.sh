@@ -1,5 +1,5 @@
 #!/bin/bash
-# Multi-GPU trip: data-parallel parity test, training-step bench and the config-5 sweep at N ranks.  usage: gpu_r02d.sh N TAG
+# Multi-GPU trip: data-parallel parity test, training-step bench and the config-5 sweep at N ranks.  usage: gpu_multi.sh N TAG
 set -u
 N=${1:-2}; TAG=${2:-r02d}
 mkdir -p gpurun_out

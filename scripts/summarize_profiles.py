@@ -1,4 +1,4 @@
-"""Turn the raw ncu outputs of scripts/gpu_round.sh (gpurun_out/) into the small tracked summaries under profiles/.
+"""Turn the raw ncu outputs of scripts/gpu_final.sh (gpurun_out/) into the small tracked summaries under profiles/.
 
     python scripts/summarize_profiles.py r01c
 
