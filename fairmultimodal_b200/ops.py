@@ -175,7 +175,9 @@ def bert_embed(ids, word, pos, type_emb, gamma, beta, eps, seq_len, err_flag=Non
 
 
 def mask_kv_len(key_mask):
-    """uint8 [batch, seq] key mask -> int32 [batch]: 1 + index of the last attended key (0 if none)."""
+    """uint8 [batch, seq] key mask -> int32 [batch]: |value| = 1 + index of the last attended key (0 if none); the value
+    is >= 0 for a prefix mask (ones then zeros: a padded batch) and negative when the attended keys have holes (the
+    attention kernel then reads the mask bytes instead of deriving key validity from the length)."""
     _cuda(key_mask, "key_mask", torch.uint8)
     if not key_mask.is_contiguous() or key_mask.dim() != 2:
         raise _lib.FameError("key_mask must be contiguous uint8 [batch, seq]")
