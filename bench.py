@@ -506,6 +506,43 @@ def bench_train(args, world, rank, dev, barrier, pk, sampler):
             e1.record()
             barrier()
         res[name] = e0.elapsed_time(e1)
+    # ---- variant 4b: the note encoder inside the loop -- every step first encodes the step's 4 chunks per
+    # patient (128 chunks x 512 tokens, no gradient) and pools them into the text embedding the step consumes; the
+    # reference precomputes these once (10_FAME.py:729-731), so 4a above is the reference-faithful number
+    in_loop = None
+    if not args.skip_note_encoder:
+        from fairmultimodal_b200 import modules, synth
+        sd = {k: torch.from_numpy(v) for k, v in synth.synth_state_dict(synth.bert_shapes("BioBert.", synth.VOCAB), WSEED).items()}
+        enc = modules.BioClinicalBERT_FT.from_state_dict(sd).to(dev)
+        del sd
+        co = synth.make_cohort(TRAIN_B * n_batches, lab_tokens=4, chunks="fixed4", seq_len=SEQ, seed=4321 + rank)
+        cpb = TRAIN_B * CHUNKS_PER_PATIENT
+        ids_d = torch.from_numpy(co["input_ids"]).view(n_batches, cpb, SEQ).to(dev)
+        mask_d = torch.from_numpy(co["attention_mask"]).view(n_batches, cpb, SEQ).to(dev)
+        offs = torch.arange(0, cpb + 1, CHUNKS_PER_PATIENT, dtype=torch.int32, device=dev)
+
+        def step_in_loop(i):
+            k = i % n_batches
+            text = modules.pool_chunks(enc.encode_cls(ids_d[k], mask_d[k]), offs)
+            b = list(devb[k])
+            b[7] = text
+            train.optimisation_step(model, b, pw, 0.8, 0.01, w, hp, group=group)
+
+        for i in range(3):
+            step_in_loop(i)
+        barrier()
+        with sampler.region():
+            e0.record()
+            for i in range(args.steps):
+                step_in_loop(i)
+            e1.record()
+            barrier()
+        ms_loop = _max_over_ranks([e0.elapsed_time(e1)], world, dev)[0]
+        in_loop = {"value": world * TRAIN_B * args.steps / (ms_loop * 1e-3), "unit": "patients/s", "ms_per_step": ms_loop / args.steps,
+                   "workload": f"variant 4b: {cpb} note chunks x {SEQ} tokens encoded and pooled (no gradient) + the training "
+                               "step, per step and GPU"}
+        del enc, ids_d, mask_d
+        torch.cuda.empty_cache()
     # trace pass (eager, outside the timed regions): CUDA events around every launch, on the stream it is launched on
     tsteps = 3
     l0 = ops.LAUNCHES
@@ -547,6 +584,7 @@ def bench_train(args, world, rank, dev, barrier, pk, sampler):
                                 "WHOLE step time (both towers, head, loss, clip, AdamW); the demographic tower at 32 rows "
                                 "is weight streaming, not tensor-bound work, and is not counted"},
         "kernels": table,
+        "encoder_in_loop": in_loop,
     }
 
 
