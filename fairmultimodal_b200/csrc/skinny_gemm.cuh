@@ -58,6 +58,16 @@ skinny_gemm_kernel(const SkinnyParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int n0 = blockIdx.x * kSkBN;
+    // All of this CTA's weight bytes (8 rows x K) are requested from HBM at once, before the first dependent load: the
+    // 4-chunk software pipeline below then runs against L2 (A/B on one box, three runs each: 3.53 -> 3.45-3.50 ms per training step).
+    {
+        const char* wbase = reinterpret_cast<const char*>(p.w + (long long)n0 * p.ldw);
+        const int lines = (p.K * 2 + 127) >> 7;
+        for (int i = threadIdx.x; i < kSkBN * lines; i += kSkThreads) {
+            const int r = i / lines, l = i - r * lines;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(wbase + (long long)r * p.ldw * 2 + l * 128));
+        }
+    }
     // K slice of this warp, in 32-element chunks
     const int chunks = p.K >> 5;
     const int per = (chunks + kSkWarps - 1) / kSkWarps;
