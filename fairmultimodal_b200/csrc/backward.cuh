@@ -39,6 +39,9 @@ __device__ __forceinline__ void store8(__nv_bfloat16* yb, float* yf, long long e
 // x: pre-LN input (bf16 or f32), stats: {mean, rstd} saved by the forward kernel.  cols % 8 == 0, <= 1024.
 // CH = 8-column chunks per lane (3 for cols <= 768: 96 instead of 128 accumulator / operand registers, which lets two
 // CTAs share an SM -- at one CTA the 8 resident warps kept 24 KB of loads in flight and the kernel ran at 1.8 TB/s).
+// (Measured and dropped, r02: the column partials in shared memory instead of registers -- 78 registers, three CTAs per
+// SM -- ran the 17 344 x 768 case in 75 instead of 48 us: the 36 16-byte shared-memory read-modify-writes per lane and
+// row cost more than the third CTA brings, and without any column partials both variants take 41 us.)
 template <bool kXF32, bool kDyF32, int CH = kLnMaxChunks>
 __global__ void __launch_bounds__(kLnWarpsPerBlock * 32, CH <= 3 ? 2 : 1)
 layernorm_bwd_kernel(const void* __restrict__ x, const void* __restrict__ dy, const float2* __restrict__ stats,
@@ -262,51 +265,83 @@ __global__ void seq_mean_bwd_kernel(const float* __restrict__ dout, __nv_bfloat1
 
 // ---------------------------------------------------------------------------------------- lab embedding backward
 // x[b,l,:] = lab[b,l] * w + bias + pos[l,:]:  dpos[l,:] = sum_b dx[b,l,:];  dw += sum dx * lab;  dbias += sum dx
-// One block per l (128 threads x 8-column chunks), deterministic dpos, atomics for dw / dbias.
-__global__ void __launch_bounds__(128)
+// One CTA per SM walks over positions l; a thread owns one 8-column chunk for one slice of the batch (hidden / 8 chunks
+// x S slices = the block), 8 independent 16-byte loads in flight.  dpos is the fixed-order sum of the S slice partials
+// (deterministic); dw / dbias are kept in registers over all of the CTA's positions and leave as ONE atomic per
+// column per CTA.  (One block per l with its own atomics -- 542 x 1 536 adds onto 1 536 addresses -- took 57 us at
+// 32 x 542 x 768: the L2 atomic units serialise per address.)
+constexpr int kLebThreads = 384;
+
+__global__ void __launch_bounds__(kLebThreads)
 lab_embed_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const float* __restrict__ lab, float* __restrict__ dpos,
                      float* __restrict__ dw, float* __restrict__ dbias, int batch, int L, int hidden) {
-    const int l = blockIdx.x;
-    for (int c0 = threadIdx.x * 8; c0 < hidden; c0 += blockDim.x * 8) {
-        float sp[8], sw[8];
+    extern __shared__ __align__(16) float leb_part[];          // [S][hidden]
+    const int nch = hidden >> 3;                               // <= kLebThreads (checked by the launcher)
+    const int S = kLebThreads / nch;
+    const int q = threadIdx.x / nch, ch = threadIdx.x - q * nch;
+    const bool live = q < S;
+    const int per = (batch + S - 1) / S;
+    const int b_lo = q * per, b_hi = min(batch, b_lo + per);
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    float aw[8], ab[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sp[j] = sw[j] = 0.f;
-        int b = 0;
-        for (; b + 8 <= batch; b += 8) {          // 8 independent 16-byte loads in flight (one at a time: 54 us at 32 x 542)
-            uint4 raw[8];
-            float v[8];
+    for (int j = 0; j < 8; ++j) aw[j] = ab[j] = 0.f;
+    for (int l = blockIdx.x; l < L; l += gridDim.x) {
+        if (live) {
+            float sp[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                raw[u] = __ldg(reinterpret_cast<const uint4*>(dx + ((long long)(b + u) * L + l) * hidden + c0));
-                v[u] = __ldg(lab + (long long)(b + u) * L + l);
-            }
+            for (int j = 0; j < 8; ++j) sp[j] = 0.f;
+            for (int b = b_lo; b < b_hi; b += 8) {
+                uint4 raw[8];
+                float v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                float f[8];
-                bf16x8_to_float(raw[u], f);
+                for (int u = 0; u < 8; ++u) {
+                    const bool ok = b + u < b_hi;
+                    raw[u] = ok ? __ldg(reinterpret_cast<const uint4*>(dx + ((long long)(b + u) * L + l) * hidden) + ch) : zero;
+                    v[u] = ok ? __ldg(lab + (long long)(b + u) * L + l) : 0.f;
+                }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    sp[j] += f[j];
-                    sw[j] += f[j] * v[u];
+                for (int u = 0; u < 8; ++u) {
+                    float f[8];
+                    bf16x8_to_float(raw[u], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        sp[j] += f[j];
+                        aw[j] = fmaf(f[j], v[u], aw[j]);
+                    }
                 }
             }
-        }
-        for (; b < batch; ++b) {
-            float f[8];
-            bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(dx + ((long long)b * L + l) * hidden + c0)), f);
-            const float v = __ldg(lab + (long long)b * L + l);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                sp[j] += f[j];
-                sw[j] += f[j] * v;
-            }
+            for (int j = 0; j < 8; ++j) ab[j] += sp[j];
+            float4* dst = reinterpret_cast<float4*>(leb_part + (long long)q * hidden + 8 * ch);
+            dst[0] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            dst[1] = make_float4(sp[4], sp[5], sp[6], sp[7]);
         }
+        __syncthreads();
+        for (int c = threadIdx.x; c < hidden; c += kLebThreads) {
+            float t = leb_part[c];
+            for (int s2 = 1; s2 < S; ++s2) t += leb_part[(long long)s2 * hidden + c];
+            dpos[(long long)l * hidden + c] = t;
+        }
+        __syncthreads();
+    }
+    // the CTA's dw, then dbias: slice partials through shared memory, one atomic per column
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            dpos[(long long)l * hidden + c0 + j] = sp[j];
-            atomicAdd(dw + c0 + j, sw[j]);
-            atomicAdd(dbias + c0 + j, sp[j]);
+    for (int pass = 0; pass < 2; ++pass) {
+        if (live) {
+            const float* src = pass == 0 ? aw : ab;
+            float4* dst = reinterpret_cast<float4*>(leb_part + (long long)q * hidden + 8 * ch);
+            dst[0] = make_float4(src[0], src[1], src[2], src[3]);
+            dst[1] = make_float4(src[4], src[5], src[6], src[7]);
         }
+        __syncthreads();
+        float* out = pass == 0 ? dw : dbias;
+        for (int c = threadIdx.x; c < hidden; c += kLebThreads) {
+            float t = leb_part[c];
+            for (int s2 = 1; s2 < S; ++s2) t += leb_part[(long long)s2 * hidden + c];
+            atomicAdd(out + c, t);
+        }
+        __syncthreads();
     }
 }
 

@@ -157,6 +157,8 @@ def attn_bwd_softmax(s, dp, rows, seq, ld, scale):
 
 def attn_delta(dctx, ctx, batch, seq, heads, head_dim):
     """delta f32 [batch, heads, seq] = rowsum(dO * O) per (token, head)."""
+    if dctx.stride(0) != ctx.stride(0):
+        raise ValueError("attn_delta: dO and O must share one row stride")
     delta = torch.empty((batch, heads, seq), device=ctx.device, dtype=torch.float32)
     _flat("fame_attn_delta", dctx.data_ptr(), ctx.data_ptr(), ctx.stride(0), delta.data_ptr(), batch, seq, heads, head_dim)
     return delta

@@ -143,6 +143,38 @@ def test_layernorm_residual_forward_backward():
     assert (db - br.grad).abs().max() <= 1e-4 * br.grad.abs().max()
 
 
+@pytest.mark.parametrize("rows,cols,res,drop", [(1085, 768, True, True), (17344, 768, False, True), (999, 768, True, False),
+                                                (261, 1024, False, False), (77, 256, True, True), (5, 768, False, False)])
+def test_layernorm_bwd_bf16_streams(rows, cols, res, drop):
+    """LayerNorm backward on all-bf16 streams (the lab tower's case) at ragged row counts and three widths: dx, dgamma,
+    dbeta against torch.autograd; the masked copy against the stand-alone dropout kernel applied to dx."""
+    from fairmultimodal_b200 import ops, ops_train as T
+    torch.manual_seed(rows + cols)
+    x = torch.randn(rows, cols, device="cuda").bfloat16()
+    r = torch.randn(rows, cols, device="cuda").bfloat16() if res else None
+    dy = torch.randn(rows, cols, device="cuda").bfloat16()
+    g, b = torch.randn(cols, device="cuda"), torch.randn(cols, device="cuda")
+    stats = torch.empty(rows, 2, device="cuda")
+    ops.layernorm(x, g, b, 1e-5, stats=stats, residual=r)
+    xr = (x.float() + (r.float() if res else 0.0)).requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (cols,), gr, br, 1e-5).backward(dy.float())
+    dg, db = torch.zeros(cols, device="cuda"), torch.zeros(cols, device="cuda")
+    step = torch.full((1,), 3, dtype=torch.int32, device="cuda")
+    cfg = _drop_cfg("lnb", 0.1, step) if drop else None
+    dx, _, dxd = T.layernorm_bwd_drop(x, dy, stats, g, dg, db, drop=cfg, residual=r)
+    assert (dx.float() - xr.grad).abs().max() <= 1e-2 * xr.grad.abs().max()
+    assert (dg - gr.grad).abs().max() <= 1e-3 * gr.grad.abs().max()
+    assert (db - br.grad).abs().max() <= 1e-3 * br.grad.abs().max()
+    if drop:
+        ref_d = dx.clone()
+        T.dropout_apply(ref_d, cfg)                                       # same site, same step: the same mask
+        assert ((dxd != 0) == (ref_d != 0)).all()
+        assert (dxd.float() - ref_d.float()).abs().max() <= 2e-2 * ref_d.float().abs().max()
+    else:
+        assert dxd is None
+
+
 def test_clip_adamw_matches_torch():
     from fairmultimodal_b200 import ops_train as T
     torch.manual_seed(3)
@@ -640,3 +672,38 @@ def test_full_step_parity_at_bench_shape(B):
     # 9 of 64 rows at the bench shape -- enough rows to catch a wrong per-patient gradient formula
     assert n_same >= max(2, B // 16)
     assert row_err["dlogits"] <= 2e-2 and row_err["ddemo"] <= 3e-2 and row_err["dlab"] <= 3e-2, row_err
+
+
+@pytest.mark.parametrize("B,L,nh,D", [(2, 37, 8, 96), (32, 542, 8, 96), (3, 50, 12, 64), (2, 9, 4, 64), (1, 5, 6, 128)])
+def test_attn_delta_against_torch(B, L, nh, D):
+    """delta[b, h, i] = sum_d dO * O per (token, head): the one-warp-per-token kernel (heads dividing 32) and the
+    per-(token, head) kernel (12 / 6 heads), on a strided view as the training step passes it."""
+    from fairmultimodal_b200 import ops_train as T
+    torch.manual_seed(B * L + nh)
+    ctx = torch.randn(B * L, nh * D + 64, device="cuda").bfloat16()[:, :nh * D]     # row stride nh * D + 64
+    dctx = torch.randn(B * L, nh * D + 64, device="cuda").bfloat16()[:, :nh * D]    # (one stride for both tensors)
+    got = T.attn_delta(dctx, ctx, B, L, nh, D)
+    ref = (dctx.float() * ctx.float()).view(B, L, nh, D).sum(-1).permute(0, 2, 1)
+    assert got.shape == (B, nh, L)
+    assert (got - ref).abs().max() <= 1e-4 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,L,H", [(32, 542, 768), (5, 7, 768), (1, 1, 768), (33, 12, 256), (9, 200, 1024)])
+def test_lab_embed_bwd_against_torch(B, L, H):
+    """Gradients of x[b, l, :] = lab[b, l] * w + bias + pos[l, :] given dx: dpos = sum_b dx, dw = sum dx * lab,
+    dbias = sum dx; dw / dbias ACCUMULATE into the (zeroed) gradient buffer, dpos is overwritten."""
+    from fairmultimodal_b200 import ops_train as T
+    torch.manual_seed(B + L)
+    dx = torch.randn(B * L, H, device="cuda").bfloat16()
+    lab = torch.randn(B, L, device="cuda")
+    dpos = torch.full((L, H), 7.0, device="cuda")
+    dw, dbias = torch.ones(H, device="cuda"), torch.ones(H, device="cuda")
+    T.lab_embed_bwd(dx, lab, dpos, dw, dbias)
+    d3 = dx.float().view(B, L, H)
+    ref_pos = d3.sum(0)
+    ref_w = (d3 * lab[:, :, None]).sum((0, 1)) + 1.0
+    ref_b = d3.sum((0, 1)) + 1.0
+    scale = (B * L) ** 0.5
+    assert (dpos - ref_pos).abs().max() <= 1e-5 * B
+    assert (dw - ref_w).abs().max() <= 2e-5 * scale * 4
+    assert (dbias - ref_b).abs().max() <= 2e-5 * scale * 4
