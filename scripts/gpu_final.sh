@@ -13,7 +13,6 @@ timeout 900 python bench.py --config 5 --steps 2 --warmup 1 > gpurun_out/bench_c
 timeout 600 python scripts/bench_hbm_kernels.py gpurun_out/hbm_kernels_${TAG}.json > gpurun_out/hbm_kernels_${TAG}.log 2>&1; echo "hbm exit=$?"; tail -12 gpurun_out/hbm_kernels_${TAG}.log
 timeout 300 python scripts/bench_lab_small_kernels.py gpurun_out/lab_small_kernels_${TAG}.json > gpurun_out/lab_small_kernels_${TAG}.log 2>&1; echo "small kernels exit=$?"
 # ---- ncu: launch lists (same commands, after each exited 0 without ncu), then full captures of the dominant kernels
-export FAME_NO_GRAPH=1
 TCMD="python bench.py --steps 2 --warmup 3 --skip-note-encoder --skip-eager --cpu-train-steps 0"
 $TCMD > gpurun_out/plain_train_${TAG}.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_train_${TAG}.csv $TCMD > gpurun_out/ncu_train_${TAG}.log 2>&1
@@ -24,7 +23,6 @@ echo "ncu train gemm exit=$?"
 $TCMD > gpurun_out/plain_train_${TAG}.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:attn_bwd_fused -s 6 -c 2 -o gpurun_out/prof_attn_bwd_${TAG} -f $TCMD > gpurun_out/ncu_attn_bwd_${TAG}.log 2>&1
 echo "ncu attn bwd exit=$?"
-unset FAME_NO_GRAPH
 NCMD="python bench.py --config 2 --steps 2 --warmup 3 --cpu-chunks 0"
 $NCMD > gpurun_out/plain_note_${TAG}.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1000 --csv --log-file gpurun_out/launches_note_${TAG}.csv $NCMD > gpurun_out/ncu_note_${TAG}.log 2>&1

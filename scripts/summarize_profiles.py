@@ -81,7 +81,7 @@ def full_summary(rep, dst):
 if __name__ == "__main__":
     tag = sys.argv[1]
     # ---- round-2 layout (scripts/gpu_final.sh): train-step and note-encoder commands profiled separately
-    tcmd = "FAME_NO_GRAPH=1 python bench.py --steps 2 --warmup 3 --skip-note-encoder --skip-eager --cpu-train-steps 0"
+    tcmd = "python bench.py --steps 2 --warmup 3 --skip-note-encoder --skip-eager --cpu-train-steps 0"
     ncmd = "python bench.py --config 2 --steps 2 --warmup 3 --cpu-chunks 0"
     p = os.path.join(OUT, f"launches_note_{tag}.csv")
     if not os.path.exists(p):
