@@ -445,7 +445,9 @@ int fame_gelu_bwd(const void* pre, const void* dh, void* dpre, int64_t n, fame_s
 int fame_colsum(const void* x, int32_t x_dtype, int64_t ld, int32_t rows, int32_t cols, float* out, fame_stream_t stream);
 /* Backward of x.mean(dim=1) (10_FAME.py:224): dx[b*L + l, :] = dout[b, :] / L  (bf16). */
 int fame_seq_mean_bwd(const float* dout, void* dx, int32_t batch, int32_t L, int32_t cols, fame_stream_t stream);
-/* Backward of the lab token embedding (10_FAME.py:218-220): dpos written, dw / dbias accumulated. */
+/* Backward of the lab token embedding (10_FAME.py:218-220): dpos [L, hidden] written (fixed summation order), dw / dbias
+ * [hidden] accumulated with one f32 atomic per column and CTA.  dx bf16 [batch * L, hidden], 16-byte aligned;
+ * hidden % 8 == 0, hidden <= 3072. */
 int fame_lab_embed_bwd(const void* dx, const float* lab, float* dpos, float* dw, float* dbias, int32_t batch, int32_t L,
                        int32_t hidden, fame_stream_t stream);
 /* Attention backward, softmax part: from f32 scores S = Q K^T and dP = dO V^T (rows = batch*heads*seq, leading
@@ -498,7 +500,9 @@ int fame_wgrad_small(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x,
  * P = softmax(Q K^T scale) and dS = scale P (dO V^T - delta) per (sequence, head), both bf16 [batch, heads, seq, ldp]
  * (columns >= seq zero), from the packed qkv tensor, dO = dctx, the forward's lse and delta = rowsum(dO * O)
  * (fame_attn_delta).  Both score products stay in TMEM.  The three products dV = P^T dO, dK = dS^T Q, dQ = dS K follow
- * through fame_gemm_ex.  head_dim 64 or 96; ldp % 8 == 0, ldp >= seq. */
+ * through fame_gemm_ex.  head_dim 64 or 96; ldp % 8 == 0, ldp >= seq.
+ * fame_attn_delta: delta f32 [batch, heads, seq] from dctx and ctx (bf16 [batch * seq, ld], ONE row stride for both; any
+ * even head_dim -- heads that divide 32 with head_dim * heads % 256 == 0 take the one-warp-per-token kernel). */
 int fame_attn_delta(const void* dctx, const void* ctx, int64_t ld, float* delta, int32_t batch, int32_t seq,
                     int32_t heads, int32_t head_dim, fame_stream_t stream);
 int fame_attn_bwd_pds(const void* qkv, int64_t ld_qkv, const void* dctx, int64_t ld_dctx, const float* lse,
